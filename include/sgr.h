@@ -1,0 +1,162 @@
+/* sgr.h — C ABI of the B200-native Gaussian-splat rasteriser (libsgr_b200.so).
+ *
+ * Drop-in boundary for the rasteriser hot path of yyvhang/SIGMAN_release.  The reference reaches this
+ * path only through the third-party pybind module `diff_gaussian_rasterization._C`
+ * (`rasterize_gaussians`, `rasterize_gaussians_backward`, `mark_visible`), called from
+ * /root/reference/core/gaussians/gs.py:82-106, and through `simple_knn._C.distCUDA2`
+ * (gs.py:6,70).  Each entry point below names the reference interface it replaces.
+ *
+ * Conventions
+ *  - plain C: device pointers + sizes, no torch / C++ types.  All tensors fp32, contiguous.
+ *  - the library never allocates user-visible memory: outputs, `state` (kept between forward and
+ *    backward; replaces upstream's geomBuffer/binningBuffer/imgBuffer) and `scratch` are caller-owned
+ *    device buffers sized with sgr_state_bytes() / sgr_scratch_bytes().
+ *  - everything is enqueued on `stream` (a cudaStream_t passed as void*); no device synchronisation,
+ *    no device->host copy on the launch path.  The number of (Gaussian, tile) instances is counted on
+ *    the device; if it exceeds `max_instances` the affected renders are emitted as background only and
+ *    the overflow is reported by sgr_read_status() so the caller can grow `state` and retry.
+ *  - renders are batched: B subjects x V views per subject in one call (B = V = 1 reproduces one
+ *    upstream rasterizer call).  Render index r = b * V + v.
+ *  - return value: 0 on success, negative SgrError otherwise; sgr_last_error() gives the message
+ *    (thread-local).  The library never calls abort()/exit().
+ */
+#ifndef SGR_H_
+#define SGR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGR_ABI_VERSION 1
+
+typedef enum SgrError {
+    SGR_OK = 0,
+    SGR_E_INVALID_ARGUMENT = -1,
+    SGR_E_BUFFER_TOO_SMALL = -2,   /* state / scratch smaller than sgr_*_bytes() */
+    SGR_E_CUDA = -3,               /* a CUDA runtime call failed; message in sgr_last_error() */
+    SGR_E_INSTANCE_OVERFLOW = -4   /* reported by sgr_read_status(): grow max_instances and retry */
+} SgrError;
+
+enum {
+    SGR_FLAG_SIMPLE_BLEND = 1,     /* use the straightforward (upstream-shaped) blend kernels: debugging aid */
+    SGR_FLAG_CLAMP_COLOR = 2       /* fuse gs.py:107 `rendered_image.clamp(0, 1)` into the blend epilogue */
+};
+
+/* Problem description shared by forward and backward.
+ * Replaces the argument list of upstream `_C.rasterize_gaussians(...)` as assembled from
+ * GaussianRasterizationSettings at gs.py:82-95 and the tensors at gs.py:99-106. */
+typedef struct SgrProblem {
+    int32_t num_subjects;        /* B */
+    int32_t views_per_subject;   /* V */
+    int32_t num_gaussians;       /* N (per subject) */
+    int32_t image_height;        /* gs.py:83 */
+    int32_t image_width;         /* gs.py:84 */
+    float tanfovx;               /* gs.py:85 */
+    float tanfovy;               /* gs.py:86 */
+    const float* means3D;        /* [B,N,3]  gs.py:100 */
+    const float* cov3D;          /* [B,N,6]  gs.py:105 (xx,xy,xz,yy,yz,zz; order of gs.py:32-37) */
+    const float* colors;         /* [B,N,3]  gs.py:103 colors_precomp */
+    const float* opacities;      /* [B,N]    gs.py:104 */
+    const float* viewmatrix;     /* [B,V,16] gs.py:89  (W2C transposed, i.e. flat column-major W2C) */
+    const float* projmatrix;     /* [B,V,16] gs.py:90  (flat column-major P*W2C) */
+    const float* bg;             /* [3]      gs.py:87 */
+    uint64_t max_instances;      /* capacity of the instance arrays inside `state` (all renders together) */
+    int32_t renders_per_chunk;   /* 0 = library default; renders processed per launch set */
+    int32_t flags;               /* SGR_FLAG_* */
+} SgrProblem;
+
+/* Replaces `_C.rasterize_gaussians` (forward).  Outputs match the tuple unpacked at gs.py:99:
+ * color [B,V,3,H,W], radii [B,V,N] int32, depth [B,V,1,H,W], alpha [B,V,1,H,W]. */
+typedef struct SgrForwardArgs {
+    SgrProblem p;
+    float* out_color;
+    float* out_depth;
+    float* out_alpha;
+    int32_t* radii;
+    void* state;    uint64_t state_bytes;
+    void* scratch;  uint64_t scratch_bytes;
+    void* stream;
+} SgrForwardArgs;
+
+/* Replaces `_C.rasterize_gaussians_backward`.  Gradient slots follow the tuple returned by upstream's
+ * autograd Function: means3D, means2D, colors_precomp, opacities, cov3D_precomp.
+ * dL_ddepth / dL_dalpha may be NULL (treated as zeros — SIGMAN's case, gs.py:107-112 uses colour only).
+ * Gradients of one subject are summed over its V views; dL_dmeans2D (optional, may be NULL) is per
+ * render: [B,V,N,3] with z = 0, in NDC units like upstream's viewspace-point gradient. */
+typedef struct SgrBackwardArgs {
+    SgrProblem p;
+    const float* out_alpha;      /* [B,V,1,H,W] as produced by the forward */
+    const int32_t* radii;        /* [B,V,N] as produced by the forward */
+    const float* dL_dcolor;      /* [B,V,3,H,W] */
+    const float* dL_ddepth;      /* [B,V,1,H,W] or NULL */
+    const float* dL_dalpha;      /* [B,V,1,H,W] or NULL */
+    float* dL_dmeans3D;          /* [B,N,3] */
+    float* dL_dcov3D;            /* [B,N,6] */
+    float* dL_dcolors;           /* [B,N,3] */
+    float* dL_dopacities;        /* [B,N] */
+    float* dL_dmeans2D;          /* [B,V,N,3] or NULL */
+    void* state;    uint64_t state_bytes;
+    void* scratch;  uint64_t scratch_bytes;
+    void* stream;
+} SgrBackwardArgs;
+
+/* Device-side status of the last forward that used `state` (read with sgr_read_status). */
+typedef struct SgrStatus {
+    uint64_t instances_required;   /* total (Gaussian, tile) instances of all renders */
+    uint64_t instances_capacity;   /* max_instances the forward ran with */
+    uint32_t overflow;             /* != 0: some renders were dropped (background only) */
+    uint32_t max_tile_instances;   /* longest per-tile list */
+    uint32_t nonempty_tiles;       /* tiles with at least one instance (all renders) */
+    uint32_t reserved;
+} SgrStatus;
+
+int sgr_abi_version(void);
+const char* sgr_last_error(void);
+
+/* Buffer sizes for a problem shape (bytes; 256-byte aligned). */
+uint64_t sgr_state_bytes(int32_t num_subjects, int32_t views_per_subject, int32_t num_gaussians,
+                         int32_t image_height, int32_t image_width, uint64_t max_instances);
+uint64_t sgr_scratch_bytes(int32_t num_subjects, int32_t views_per_subject, int32_t num_gaussians,
+                           int32_t image_height, int32_t image_width, uint64_t max_instances,
+                           int32_t renders_per_chunk);
+
+int sgr_forward(const SgrForwardArgs* args);
+int sgr_backward(const SgrBackwardArgs* args);
+
+/* Copies the status block of `state` to the host.  Synchronises `stream` (the only synchronising call).
+ * Returns SGR_E_INSTANCE_OVERFLOW if the forward overflowed max_instances (status is still filled in). */
+int sgr_read_status(const void* state, void* stream, SgrStatus* host_status);
+
+/* Replaces `_C.mark_visible` (upstream GaussianRasterizer.markVisible): visible[i] = view-space z > 0.2. */
+int sgr_mark_visible(const float* means3D, int32_t num_gaussians, const float* viewmatrix,
+                     const float* projmatrix, uint8_t* visible, void* stream);
+
+/* Optional input paths of the upstream API (unused by SIGMAN, which passes cov3D_precomp and
+ * colors_precomp): cov3D from scale * modifier and a (r,x,y,z) quaternion, and its backward. */
+int sgr_cov3d_from_scale_rot(const float* scales, const float* rotations, float scale_modifier,
+                             int32_t num_gaussians, float* cov3D, void* stream);
+int sgr_cov3d_from_scale_rot_backward(const float* scales, const float* rotations, float scale_modifier,
+                                      int32_t num_gaussians, const float* dL_dcov3D, float* dL_dscales,
+                                      float* dL_drotations, void* stream);
+
+/* Replaces `simple_knn._C.distCUDA2` (gs.py:70): mean squared distance to the 3 nearest other points.
+ * `scratch` must hold sgr_knn_scratch_bytes(num_points) bytes. */
+uint64_t sgr_knn_scratch_bytes(int32_t num_points);
+int sgr_knn_mean_dist2(const float* points, int32_t num_points, float* out_mean_dist2, void* scratch,
+                       uint64_t scratch_bytes, void* stream);
+
+/* Debug/inspection: copies intermediate state of render `r` to caller-provided DEVICE buffers (any may be NULL).
+ *   tile_ranges  uint32[tiles][2]  (start, end) offsets into the global instance arrays
+ *   n_contrib    uint32[H*W]
+ * and exposes the base pointers of the sorted instance arrays. */
+int sgr_debug_state_view(const void* state, int32_t render, const uint32_t** tile_offsets,
+                         const uint32_t** tile_counts, const uint32_t** n_contrib, const uint32_t** sorted_ids,
+                         const float** rec0, const float** rec1, const float** rec2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGR_H_ */

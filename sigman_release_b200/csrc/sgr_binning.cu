@@ -1,0 +1,315 @@
+// sgr_binning.cu — tile binning: per-tile offsets (scan), work lists, and the per-tile depth sort that emits the
+// depth-ordered instance stream (sorted ids + gathered 48-byte records) consumed by the blend kernels.
+//
+// Replaces upstream's InclusiveSum + global 64-bit DeviceRadixSort + identifyTileRanges.  Upstream
+// sorts ONE global array keyed (tile << 32 | depth bits); the stable sort resolves (tile, depth) ties by ascending
+// Gaussian index.  Here instances are first counting-sorted by tile (atomics in sgr_preprocess.cu), then every tile is
+// sorted independently on the 64-bit key (depth bits << 32 | gaussian index) — the same total order, so the per-tile
+// lists are identical to upstream's ranges (bit-exact against the oracle's point_list).
+//
+// Per-tile sort = one MSD bucket pass over the tile's key range in shared memory followed by an exact rank inside
+// each (small) bucket; linear work in the list length, no power-of-two padding.
+#include "sgr_common.cuh"
+
+namespace sgr {
+namespace {
+
+// ------------------------------------------------------------------------------------------------ scan
+struct ScanArgs {
+    int n;                        // tiles in the chunk (renders * tiles per render)
+    unsigned int* tile_cnt;       // chunk slice
+    unsigned int* tile_off;       // chunk slice
+    unsigned int* cursor;         // chunk scatter cursors (zeroed here)
+    StateHeader* header;
+    WorkCounts* wc;
+    unsigned int *work_small, *work_big;
+};
+
+constexpr int kScanThreads = 1024;
+
+__global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(ScanArgs a) {
+    __shared__ unsigned int s_warp[32];
+    __shared__ unsigned int s_total, s_nsmall, s_nbig, s_max, s_nonempty, s_dropped;
+    __shared__ unsigned long long s_base;
+    const int t = threadIdx.x;
+    const int ipt = (a.n + kScanThreads - 1) / kScanThreads;
+    const int lo = min(a.n, t * ipt), hi = min(a.n, lo + ipt);
+    unsigned int sum = 0, mx = 0, ne = 0;
+    for (int k = lo; k < hi; ++k) {
+        const unsigned int c = a.tile_cnt[k];
+        sum += c; mx = max(mx, c); ne += (c != 0);
+    }
+    if (t == 0) { s_nsmall = 0; s_nbig = 0; s_max = 0; s_nonempty = 0; }
+    // block exclusive scan of `sum`
+    unsigned int inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int v = __shfl_up_sync(0xffffffffu, inc, d);
+        if ((t & 31) >= d) inc += v;
+    }
+    if ((t & 31) == 31) s_warp[t >> 5] = inc;
+    __syncthreads();
+    if (t < 32) {
+        unsigned int w = s_warp[t], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int v = __shfl_up_sync(0xffffffffu, wi, d);
+            if (t >= d) wi += v;
+        }
+        s_warp[t] = wi - w;                       // exclusive warp prefix
+        if (t == 31) s_total = wi;
+    }
+    __syncthreads();
+    const unsigned int excl = inc - sum + s_warp[t >> 5];
+    if (t == 0) {
+        const unsigned long long base = a.header->inst_cursor;
+        const unsigned long long total = s_total;
+        a.header->inst_required += total;
+        const bool fits = base + total <= a.header->capacity;
+        s_dropped = fits ? 0u : 1u;
+        s_base = base;
+        if (fits) a.header->inst_cursor = base + total; else a.header->overflow = 1u;
+    }
+    __syncthreads();
+    const bool dropped = s_dropped != 0;
+    unsigned int run = static_cast<unsigned int>(s_base) + excl;
+    for (int k = lo; k < hi; ++k) {
+        const unsigned int c = a.tile_cnt[k];
+        a.cursor[k] = 0;
+        if (dropped) {                            // render(s) emitted as background; reported via the status block
+            a.tile_cnt[k] = 0;
+            a.tile_off[k] = static_cast<unsigned int>(s_base);
+            continue;
+        }
+        a.tile_off[k] = run;
+        run += c;
+        if (c != 0) {
+            if (c <= static_cast<unsigned int>(kSmallSortCap)) a.work_small[atomicAdd(&s_nsmall, 1u)] = k;
+            else a.work_big[atomicAdd(&s_nbig, 1u)] = k;
+        }
+    }
+    atomicMax(&s_max, mx);
+    atomicAdd(&s_nonempty, ne);
+    __syncthreads();
+    if (t == 0) {
+        a.wc->n_small = s_nsmall;
+        a.wc->n_big = s_nbig;
+        a.wc->chunk_instances = dropped ? 0u : s_total;
+        a.wc->chunk_dropped = s_dropped;
+        if (!dropped) {
+            a.header->max_tile_instances = max(a.header->max_tile_instances, s_max);
+            a.header->nonempty_tiles += s_nonempty;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ sort
+struct SortArgs {
+    int N, num_tiles, render_base;
+    const unsigned int* tile_off;    // global arrays
+    const unsigned int* tile_cnt;
+    const unsigned long long* keys;
+    unsigned int* sorted_ids;
+    float4 *rec0, *rec1, *rec2;
+    const float4 *g0, *g1, *g2;
+    const unsigned int* work;        // chunk-local tile indices
+    const unsigned int* work_count;
+};
+
+template <int THREADS>
+__device__ __forceinline__ void block_minmax(unsigned long long& mn, unsigned long long& mx, unsigned long long* s_red) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, mn, d);
+        const unsigned long long b = __shfl_xor_sync(0xffffffffu, mx, d);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    const int w = threadIdx.x >> 5;
+    __syncthreads();                               // s_red may still be read from a previous use
+    if ((threadIdx.x & 31) == 0) { s_red[2 * w] = mn; s_red[2 * w + 1] = mx; }
+    __syncthreads();
+    unsigned long long rmn = s_red[0], rmx = s_red[1];
+#pragma unroll
+    for (int k = 1; k < THREADS / 32; ++k) {
+        rmn = s_red[2 * k] < rmn ? s_red[2 * k] : rmn;
+        rmx = s_red[2 * k + 1] > rmx ? s_red[2 * k + 1] : rmx;
+    }
+    mn = rmn; mx = rmx;
+}
+
+// In-place exclusive scan of hist[NB] (NB = THREADS * PER).
+template <int THREADS, int NB>
+__device__ __forceinline__ void block_exclusive_scan(unsigned int* hist, unsigned int* s_warp) {
+    constexpr int PER = NB / THREADS;
+    static_assert(NB % THREADS == 0, "bucket count must be a multiple of the block size");
+    const int t = threadIdx.x;
+    unsigned int v[PER], sum = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { v[j] = hist[t * PER + j]; sum += v[j]; }
+    unsigned int inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int u = __shfl_up_sync(0xffffffffu, inc, d);
+        if ((t & 31) >= d) inc += u;
+    }
+    if ((t & 31) == 31) s_warp[t >> 5] = inc;
+    __syncthreads();
+    if (t < 32) {
+        unsigned int w = (t < THREADS / 32) ? s_warp[t] : 0u, wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int u = __shfl_up_sync(0xffffffffu, wi, d);
+            if (t >= d) wi += u;
+        }
+        if (t < THREADS / 32) s_warp[t] = wi - w;
+    }
+    __syncthreads();
+    unsigned int run = inc - sum + s_warp[t >> 5];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { hist[t * PER + j] = run; run += v[j]; }
+    __syncthreads();
+}
+
+// Sorts the n keys of one tile, writes ids + gathered records.  kb: n-element key buffer (shared or global).
+template <int THREADS, int NB>
+__device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local, unsigned long long* kb,
+                                              unsigned int* hist, unsigned int* s_warp, unsigned long long* s_red) {
+    const int t = threadIdx.x;
+    const int rl = tile_local / a.num_tiles;
+    const size_t tg = size_t(a.render_base) * a.num_tiles + tile_local;      // global tile index
+    const unsigned int n = a.tile_cnt[tg];
+    const size_t off = a.tile_off[tg];
+    const unsigned long long* keys = a.keys + off;
+
+    // 0. key range
+    unsigned long long mn = ~0ull, mx = 0ull;
+    for (unsigned int k = t; k < n; k += THREADS) {
+        const unsigned long long key = keys[k];
+        mn = key < mn ? key : mn;
+        mx = key > mx ? key : mx;
+    }
+    block_minmax<THREADS>(mn, mx, s_red);
+    const unsigned long long range = mx - mn;
+    const int bits = range ? 64 - __clzll(static_cast<long long>(range)) : 0;
+    constexpr int LOG_NB = (NB == 1024) ? 10 : (NB == 2048 ? 11 : 12);
+    static_assert((1 << LOG_NB) == NB, "NB must be 1024, 2048 or 4096");
+    const int shift = max(0, bits - LOG_NB);
+
+    // 1. bucket histogram
+    for (int k = t; k < NB; k += THREADS) hist[k] = 0;
+    __syncthreads();
+    for (unsigned int k = t; k < n; k += THREADS)
+        atomicAdd(&hist[static_cast<unsigned int>((keys[k] - mn) >> shift)], 1u);
+    __syncthreads();
+    // 2. bucket starts
+    block_exclusive_scan<THREADS, NB>(hist, s_warp);
+    // 3. scatter into bucket order (arbitrary order inside a bucket); afterwards hist[b] = end of bucket b
+    for (unsigned int k = t; k < n; k += THREADS) {
+        const unsigned long long key = keys[k];
+        const unsigned int pos = atomicAdd(&hist[static_cast<unsigned int>((key - mn) >> shift)], 1u);
+        kb[pos] = key;
+    }
+    __syncthreads();
+    // 4. exact rank inside the bucket -> final position
+    unsigned int* ids = a.sorted_ids + off;
+    for (unsigned int p = t; p < n; p += THREADS) {
+        const unsigned long long key = kb[p];
+        const unsigned int b = static_cast<unsigned int>((key - mn) >> shift);
+        const unsigned int s = b ? hist[b - 1] : 0u;
+        const unsigned int e = hist[b];
+        unsigned int cnt = 0;
+        for (unsigned int j = s; j < e; ++j) cnt += (kb[j] < key) ? 1u : 0u;
+        ids[s + cnt] = static_cast<unsigned int>(key & 0xffffffffull);
+    }
+    __syncthreads();
+    // 5. gather the 48-byte records into depth order (the stream the blend kernels read)
+    const size_t gb = size_t(rl) * a.N;
+    for (unsigned int q = t; q < n; q += THREADS) {
+        const unsigned int id = ids[q];
+        a.rec0[off + q] = __ldg(a.g0 + gb + id);
+        a.rec1[off + q] = __ldg(a.g1 + gb + id);
+        a.rec2[off + q] = __ldg(a.g2 + gb + id);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSmallSortThreads) sort_small_kernel(SortArgs a) {
+    __shared__ unsigned long long kb[kSmallSortCap];
+    __shared__ unsigned int hist[kSmallSortBuckets];
+    __shared__ unsigned int s_warp[32];
+    __shared__ unsigned long long s_red[2 * (kSmallSortThreads / 32)];
+    const unsigned int nw = *a.work_count;
+    for (unsigned int w = blockIdx.x; w < nw; w += gridDim.x)
+        sort_one_tile<kSmallSortThreads, kSmallSortBuckets>(a, a.work[w], kb, hist, s_warp, s_red);
+}
+
+__global__ void __launch_bounds__(kBigSortThreads) sort_big_kernel(SortArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* kb_s = reinterpret_cast<unsigned long long*>(smem_raw);                 // kBigSortSmemCap
+    unsigned int* hist = reinterpret_cast<unsigned int*>(kb_s + kBigSortSmemCap);               // kBigSortBuckets
+    __shared__ unsigned int s_warp[32];
+    __shared__ unsigned long long s_red[2 * (kBigSortThreads / 32)];
+    const unsigned int nw = *a.work_count;
+    for (unsigned int w = blockIdx.x; w < nw; w += gridDim.x) {
+        const int tile_local = a.work[w];
+        const size_t tg = size_t(a.render_base) * a.num_tiles + tile_local;
+        const unsigned int n = a.tile_cnt[tg];
+        // lists that do not fit in shared memory borrow the tile's own rec0 segment (16 B/instance, not yet written)
+        unsigned long long* kb = (n <= static_cast<unsigned int>(kBigSortSmemCap))
+                                     ? kb_s
+                                     : reinterpret_cast<unsigned long long*>(a.rec0 + a.tile_off[tg]);
+        sort_one_tile<kBigSortThreads, kBigSortBuckets>(a, tile_local, kb, hist, s_warp, s_red);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_scan_tiles(const ChunkCtx& c) {
+    ScanArgs a;
+    const size_t base = size_t(c.render_base) * c.g.num_tiles;
+    a.n = c.num_renders * c.g.num_tiles;
+    a.tile_cnt = c.tile_cnt + base;
+    a.tile_off = c.tile_off + base;
+    a.cursor = c.cursor;
+    a.header = c.header;
+    a.wc = c.work_counts;
+    a.work_small = c.work_small;
+    a.work_big = c.work_big;
+    scan_tiles_kernel<<<1, kScanThreads, 0, c.stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sort_tiles(const ChunkCtx& c) {
+    SortArgs a;
+    a.N = c.g.N; a.num_tiles = c.g.num_tiles; a.render_base = c.render_base;
+    a.tile_off = c.tile_off; a.tile_cnt = c.tile_cnt; a.keys = c.keys; a.sorted_ids = c.sorted_ids;
+    a.rec0 = c.rec0; a.rec1 = c.rec1; a.rec2 = c.rec2; a.g0 = c.g0; a.g1 = c.g1; a.g2 = c.g2;
+    static int num_sms = 0;
+    static bool attr_set = false;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    const size_t big_smem = size_t(kBigSortSmemCap) * 8 + size_t(kBigSortBuckets) * 4;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(big_smem));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int total_tiles = c.num_renders * c.g.num_tiles;
+    // big lists first (longest processing time first), one persistent CTA per SM
+    a.work = c.work_big;
+    a.work_count = &c.work_counts->n_big;
+    sort_big_kernel<<<min(num_sms, total_tiles), kBigSortThreads, big_smem, c.stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    a.work = c.work_small;
+    a.work_count = &c.work_counts->n_small;
+    sort_small_kernel<<<min(num_sms * 5, total_tiles), kSmallSortThreads, 0, c.stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace sgr
