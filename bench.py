@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Benchmark of the rasteriser hot path (BASELINE.json metric: Gaussians rasterised / s and views / s on a ~100K-
+Gaussian human at 512x512).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload at N = 1 (BASELINE.json configs[1]): one ~100K-Gaussian human-shaped subject, 8 views of 512x512,
+forward + backward (L1 loss on the clamped RGB, SIGMAN's case).  A step is one such pass.  With N > 1 every rank
+renders its own subject (independent (subject, view) pairs shard with no data-path collective; the per-rank loss is
+all-gathered, mirroring /root/reference/train_vae.py:256-257) -> weak scaling.
+
+``--impl reference`` times the CPU oracle (the only executable restatement of the reference's rasteriser: the
+third-party package itself is absent from the reference tree) on the host cores, on a bounded sample of the same
+workload.  Prints ONE JSON line.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_GAUSS = 100_000
+H = W = 512
+VIEWS = [30, 37, 45, 53, 65, 85, 0, 8]           # /root/reference/core/dataset/dataloader_VAE.py:79
+METRIC = "gaussians_rasterised_per_sec (N x views / step time; forward+backward)"
+UNIT = "Gaussians/s"
+
+
+def alg_bytes(n, p):
+    """algorithmic bytes per (subject, view)."""
+    return dict(forward=56 * n + 20 * p, backward=116 * n + 28 * p)
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "BASELINE configs[1]: 1 subject x ~100K Gaussians (procedural SMPL-X-shaped body), 8 views "
+                    "512x512, forward+backward, L1 on clamped RGB",
+        "num_gaussians": N_GAUSS, "views": len(VIEWS), "image": [H, W], "subjects_per_gpu": 1,
+        "parallelism": f"{n_gpus} rank(s), one subject each (independent renders, no data-path collective)",
+        "l2": "256 MiB memset between steps (outside the per-step event pairs)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def oracle_step_fn(sc, n_views):
+    import oracle
+    from sigman_release_b200 import cameras
+
+    tan = cameras.tan_half_fov()
+    vm, pm, _ = cameras.orbit_cameras(VIEWS[:n_views])
+    rng = np.random.default_rng(1)
+    target = rng.uniform(0, 1, (3, H, W)).astype(np.float32)
+    rs = [oracle.Rasterizer(np.float32) for _ in range(n_views)]
+
+    def step():
+        for v in range(n_views):
+            o = rs[v].forward(sc["means3D"], sc["cov3D"], sc["colors"], sc["opacities"], vm[v].reshape(-1),
+                              pm[v].reshape(-1), tan, tan, (1, 1, 1), H, W)
+            c = o.color
+            g = (np.sign(np.clip(c, 0, 1) - target) * ((c >= 0) & (c <= 1)) / (target.size * n_views)).astype(np.float32)
+            rs[v].backward(g)
+
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from sigman_release_b200 import scenes
+
+    oracle.build()
+    sc = scenes.body_gaussians(N_GAUSS, seed=0)
+    sample_views = 1
+    step = oracle_step_fn(sc, sample_views)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = N_GAUSS * sample_views / dt
+    cores = oracle.num_threads()
+    sample = (f"each step = forward+backward of {sample_views} of the 8 views of the same subject "
+              f"(512x512, {N_GAUSS} Gaussians), OpenMP over {cores} host threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+        "views_per_sec": sample_views / dt,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU oracle (oracle/sgr_oracle.cpp): restatement of the published algorithm; the reference's own "
+                "rasteriser is an un-vendored third-party CUDA package (parity unpinned)",
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from sigman_release_b200 import _native, cameras, rasterizer, scenes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _native.lib()
+
+    sc = scenes.body_gaussians(N_GAUSS, seed=rank)
+    tan = cameras.tan_half_fov()
+    vm, pm, _ = cameras.orbit_cameras(VIEWS)
+    V = len(VIEWS)
+    f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32)
+    host = dict(means3D=f32(sc["means3D"])[None], cov3D=f32(sc["cov3D"])[None], colors=f32(sc["colors"])[None],
+                opacities=f32(sc["opacities"])[None])
+    host = {k: v.pin_memory() for k, v in host.items()}
+    d = {k: v.to(dev).requires_grad_(True) for k, v in host.items()}
+    vmt, pmt = f32(vm)[None].to(dev), f32(pm)[None].to(dev)
+    bg = torch.ones(3, device=dev)
+    target = torch.rand((1, V, 3, H, W), device=dev, generator=torch.Generator(device=dev).manual_seed(1 + rank))
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    gathered = torch.zeros(world, device=dev) if world > 1 else None
+
+    def render_step(t):
+        for v in t.values():
+            v.grad = None
+        color, radii, depth, alpha = rasterizer.rasterize_batch(t["means3D"], t["cov3D"], t["colors"], t["opacities"],
+                                                                vmt, pmt, bg, H, W, tan, tan)
+        loss = (color.clamp(0, 1) - target).abs().mean()
+        loss.backward()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, loss.detach().reshape(1))
+        return loss
+
+    # e2e: host buffers in, gradients + loss out, through the public API
+    e2e_dev = {k: torch.empty_like(v, device=dev).requires_grad_(True) for k, v in host.items()}
+    grads_host = {k: torch.empty_like(v).pin_memory() for k, v in host.items()}
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    h2d_bytes = sum(v.numel() * 4 for v in host.values())
+    d2h_bytes = sum(v.numel() * 4 for v in grads_host.values()) + 4
+
+    def e2e_step():
+        with torch.no_grad():
+            for k in host:
+                e2e_dev[k].copy_(host[k], non_blocking=True)
+        loss = render_step(e2e_dev)
+        for k in host:
+            grads_host[k].copy_(e2e_dev[k].grad, non_blocking=True)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s, e in evs:
+            flush_buf.zero_()
+            s.record()
+            fn()
+            e.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = sum(s.elapsed_time(e) for s, e in evs)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
+    warm = max(args.warmup, 3)
+    sampler = ClockSampler(local_rank)
+    for _ in range(warm):
+        render_step(d)
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = int(L.sgr_launch_count())
+    ms_step = timed(lambda: render_step(d), args.steps, 0)
+    launches = int(L.sgr_launch_count()) - launches0         # kernels of libsgr_b200.so launched in the timed region
+    ms_e2e = timed(e2e_step, args.steps, 2)
+    clocks = sampler.stop()
+
+    # roofline leg: per-stage device time with events around every stage launch (separate pass, same workload)
+    L.sgr_profile_enable(1)
+    for _ in range(args.steps):
+        flush_buf.zero_()
+        render_step(d)
+    torch.cuda.synchronize()
+    stage_ms = (ctypes.c_double * len(_native.STAGES))()
+    stage_n = (ctypes.c_uint32 * len(_native.STAGES))()
+    _native.check(L.sgr_profile_collect(stage_ms, stage_n))
+    L.sgr_profile_enable(0)
+    stages = {nme: {"ms_per_step": stage_ms[i] / args.steps, "launches_per_step": stage_n[i] / args.steps}
+              for i, nme in enumerate(_native.STAGES)}
+    dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
+    dom_launch_ms = stage_ms[_native.STAGES.index(dom)] / max(1, stage_n[_native.STAGES.index(dom)])
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    ab = alg_bytes(N_GAUSS, H * W)
+    side = "backward" if dom in ("blend_backward", "preprocess_backward") else "forward"
+    dom_bytes = ab[side] * V
+    achieved = dom_bytes / (dom_launch_ms * 1e-3) / 1e9
+    step_bytes = (ab["forward"] + ab["backward"]) * V
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": dom_bytes,
+        "definition": f"SURVEY 8(d) {side} bytes per (subject, view) x {V} renders per launch / mean launch duration",
+        "launch_ms": dom_launch_ms,
+        "pipeline": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
+                     "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
+        "stages": stages,
+    }
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = N_GAUSS * V * world / (ms_step * 1e-3)
+    e2e_value = N_GAUSS * V * world / (ms_e2e * 1e-3)
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(world),
+        "views_per_sec": V * world / (ms_step * 1e-3),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": ms_e2e, "views_per_sec": V * world / (ms_e2e * 1e-3)},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        "status": rasterizer.last_status(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        import oracle
+
+        oracle.build()
+        step = oracle_step_fn(sc, 1)
+        step()
+        reps, t0 = 0, time.perf_counter()
+        while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 50):
+            step()
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        out["cpu_baseline"] = {
+            "value": N_GAUSS / dt, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+            "sample": f"forward+backward of 1 of the 8 views (view 0030) of the same subject, {reps} repetitions, "
+                      f"{dt * 1e3:.1f} ms each, OpenMP over {oracle.num_threads()} host threads",
+        }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

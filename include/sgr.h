@@ -103,7 +103,9 @@ typedef struct SgrBackwardArgs {
     void* stream;
 } SgrBackwardArgs;
 
-/* Device-side status of the last forward that used `state` (read with sgr_read_status). */
+/* Device-side status of the last forward that used `state` (read with sgr_read_status).  It is stored in the first
+ * sizeof(SgrStatus) bytes of `state`, so a caller that must not synchronise can also fetch it with its own
+ * asynchronous device->host copy of the head of `state`. */
 typedef struct SgrStatus {
     uint64_t instances_required;   /* total (Gaussian, tile) instances of all renders */
     uint64_t instances_capacity;   /* max_instances the forward ran with */
@@ -148,13 +150,28 @@ uint64_t sgr_knn_scratch_bytes(int32_t num_points);
 int sgr_knn_mean_dist2(const float* points, int32_t num_points, float* out_mean_dist2, void* scratch,
                        uint64_t scratch_bytes, void* stream);
 
-/* Debug/inspection: copies intermediate state of render `r` to caller-provided DEVICE buffers (any may be NULL).
- *   tile_ranges  uint32[tiles][2]  (start, end) offsets into the global instance arrays
- *   n_contrib    uint32[H*W]
- * and exposes the base pointers of the sorted instance arrays. */
-int sgr_debug_state_view(const void* state, int32_t render, const uint32_t** tile_offsets,
-                         const uint32_t** tile_counts, const uint32_t** n_contrib, const uint32_t** sorted_ids,
-                         const float** rec0, const float** rec1, const float** rec2);
+/* Measurement hooks (bench.py): per-stage device time with CUDA events recorded on the launch stream around every
+ * stage of sgr_forward / sgr_backward while enabled, and a counter of the kernels this library has launched.
+ * Stage order: preprocess, scan, scatter, sort, worklist, blend_forward, blend_backward, preprocess_backward.
+ * sgr_profile_collect synchronises on the recorded events, returns summed milliseconds and the number of timed
+ * stage invocations, and resets the accumulators. */
+#define SGR_NUM_STAGES 8
+void sgr_profile_enable(int on);
+int sgr_profile_collect(double* stage_ms, uint32_t* stage_invocations);
+uint64_t sgr_launch_count(void);
+
+/* Debug/inspection (used by the parity tests): copies intermediate state of render `render` of the last forward
+ * to caller-provided DEVICE buffers (any may be NULL), enqueued on `stream`:
+ *   tile_ranges  uint32[tiles][2]  (start, end) offsets of each tile's depth-ordered list, relative to the render's
+ *                                  first instance — upstream's `ranges` (identifyTileRanges)
+ *   n_contrib    uint32[H*W]       upstream's per-pixel n_contrib
+ *   point_list   uint32[point_list_capacity]  Gaussian index of every instance of the render in sorted order —
+ *                                  upstream's binningState.point_list restricted to the render
+ * The shape arguments must be those of the forward that filled `state`. */
+int sgr_debug_copy_state(const void* state, int32_t num_subjects, int32_t views_per_subject, int32_t num_gaussians,
+                         int32_t image_height, int32_t image_width, uint64_t max_instances, int32_t render,
+                         uint32_t* tile_ranges, uint32_t* n_contrib, uint32_t* point_list,
+                         uint64_t point_list_capacity, void* stream);
 
 #ifdef __cplusplus
 }

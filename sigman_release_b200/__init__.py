@@ -2,3 +2,13 @@
 ``GaussianRasterizer`` / ``GaussianRasterizationSettings`` API used by
 ``/root/reference/core/gaussians/gs.py``.  See DESIGN.md."""
 __version__ = "0.1.0"
+
+from .rasterizer import (  # noqa: E402,F401
+    GaussianRasterizationSettings,
+    GaussianRasterizer,
+    rasterize_batch,
+    rasterize_gaussians,
+    cov3d_from_scale_rot,
+    last_status,
+)
+from .renderer import GaussianRenderer, distCUDA2, get_covariance  # noqa: E402,F401

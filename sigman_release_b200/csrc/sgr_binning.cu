@@ -103,6 +103,49 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(ScanArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ blend work lists
+struct WorkArgs {
+    int n;                            // tiles in the chunk
+    const unsigned int* tile_cnt;     // chunk slice
+    unsigned int *work_blend, *work_empty;
+    WorkCounts* wc;
+};
+
+constexpr int kSizeClasses = 66;      // 2 * (bit length of the count) + next-lower bit; class 0 = empty
+
+__device__ __forceinline__ int size_class(unsigned int c) {
+    if (c == 0) return 0;
+    const int msb = 31 - __clz(c);
+    const int half = msb ? int((c >> (msb - 1)) & 1u) : 0;
+    return 2 * (msb + 1) + half;
+}
+
+// Non-empty tiles ordered by descending size class (longest-processing-time-first for the persistent blend kernels)
+// and the list of empty tiles (background only).  One CTA; the chunk has at most a few 10^4 tiles.
+__global__ void __launch_bounds__(kScanThreads) worklist_kernel(WorkArgs a) {
+    __shared__ unsigned int s_hist[kSizeClasses], s_start[kSizeClasses];
+    const int t = threadIdx.x;
+    if (t < kSizeClasses) s_hist[t] = 0;
+    __syncthreads();
+    for (int k = t; k < a.n; k += kScanThreads) atomicAdd(&s_hist[size_class(a.tile_cnt[k])], 1u);
+    __syncthreads();
+    if (t == 0) {
+        unsigned int run = 0;
+        for (int c = kSizeClasses - 1; c >= 1; --c) { s_start[c] = run; run += s_hist[c]; }
+        s_start[0] = 0;
+        a.wc->n_blend = run;
+        a.wc->n_empty = s_hist[0];
+        a.wc->blend_cursor = 0;
+        a.wc->empty_cursor = 0;
+    }
+    __syncthreads();
+    for (int k = t; k < a.n; k += kScanThreads) {
+        const int c = size_class(a.tile_cnt[k]);
+        const unsigned int pos = atomicAdd(&s_start[c], 1u);
+        if (c == 0) a.work_empty[pos] = k; else a.work_blend[pos] = k;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ sort
 struct SortArgs {
     int N, num_tiles, render_base;
@@ -277,6 +320,17 @@ cudaError_t launch_scan_tiles(const ChunkCtx& c) {
     a.work_small = c.work_small;
     a.work_big = c.work_big;
     scan_tiles_kernel<<<1, kScanThreads, 0, c.stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_worklist(const ChunkCtx& c) {
+    WorkArgs a;
+    a.n = c.num_renders * c.g.num_tiles;
+    a.tile_cnt = c.tile_cnt + size_t(c.render_base) * c.g.num_tiles;
+    a.work_blend = c.work_blend;
+    a.work_empty = c.work_empty;
+    a.wc = c.work_counts;
+    worklist_kernel<<<1, kScanThreads, 0, c.stream>>>(a);
     return cudaGetLastError();
 }
 

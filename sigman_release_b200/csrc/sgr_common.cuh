@@ -13,15 +13,18 @@ constexpr int kDefaultRendersPerChunk = 16;
 
 // ------------------------------------------------------------------------------------------------
 // Device-resident status / counters at the start of `state`.
+// The first sizeof(SgrStatus) bytes mirror SgrStatus (include/sgr.h) so a caller may also fetch the status with its
+// own asynchronous copy of the head of `state`.
 struct alignas(256) StateHeader {
-    unsigned long long inst_cursor;        // instances consumed so far (global offset of the next chunk)
     unsigned long long inst_required;      // total instances all renders need (even when overflowing)
     unsigned long long capacity;
     unsigned int overflow;
     unsigned int max_tile_instances;
     unsigned int nonempty_tiles;
     unsigned int pad;
+    unsigned long long inst_cursor;        // instances consumed so far (global offset of the next chunk)
 };
+static_assert(sizeof(SgrStatus) == 32, "SgrStatus layout is part of the ABI");
 
 // Layout of `state` (kept forward -> backward) for a problem shape.
 struct StateLayout {
@@ -29,7 +32,7 @@ struct StateLayout {
 };
 // Layout of `scratch` (valid only inside one call).
 struct ScratchLayout {
-    uint64_t keys, g0, g1, g2, rect, cursor, work_small, work_big, work_counts, accum, total;
+    uint64_t keys, g0, g1, g2, rect, cursor, work_small, work_big, work_blend, work_empty, work_counts, accum, total;
 };
 
 __host__ __device__ inline uint64_t align_up(uint64_t x, uint64_t a = 256) { return (x + a - 1) / a * a; }
@@ -69,6 +72,8 @@ inline ScratchLayout make_scratch_layout(int B, int V, int N, int H, int W, uint
     L.cursor = o;      o = align_up(o + Rc * T * 4);
     L.work_small = o;  o = align_up(o + Rc * T * 4);
     L.work_big = o;    o = align_up(o + Rc * T * 4);
+    L.work_blend = o;  o = align_up(o + Rc * T * 4);
+    L.work_empty = o;  o = align_up(o + Rc * T * 4);
     L.work_counts = o; o = align_up(o + 256);
     L.accum = o;       o = align_up(o + Rc * N * 4 * kAccumPlanes);
     L.total = o;
@@ -81,6 +86,10 @@ struct WorkCounts {
     unsigned int n_big;        // tiles with more
     unsigned int chunk_instances;
     unsigned int chunk_dropped;   // != 0: chunk did not fit into max_instances
+    unsigned int n_blend;      // non-empty tiles, longest lists first (blend work list)
+    unsigned int n_empty;      // tiles without instances (background only)
+    unsigned int blend_cursor; // dynamic work queue heads of the persistent blend kernels
+    unsigned int empty_cursor;
 };
 
 constexpr int kSmallSortCap = 4096;       // instances sorted in a 40 KB shared-memory CTA
@@ -152,7 +161,7 @@ struct ChunkCtx {
     float4 *g0, *g1, *g2;     // [Rc*N]
     uint2* rect;              // [Rc*N] packed tile rectangle
     unsigned int* cursor;     // [Rc*T]
-    unsigned int *work_small, *work_big;
+    unsigned int *work_small, *work_big, *work_blend, *work_empty;
     WorkCounts* work_counts;
     float* accum;             // [kAccumPlanes][Rc*N]
     cudaStream_t stream;
@@ -160,6 +169,7 @@ struct ChunkCtx {
 
 cudaError_t launch_preprocess(const ChunkCtx& c, int32_t* radii);
 cudaError_t launch_scan_tiles(const ChunkCtx& c);
+cudaError_t launch_worklist(const ChunkCtx& c);     // blend/empty work lists from tile_cnt (forward and backward)
 cudaError_t launch_scatter(const ChunkCtx& c);
 cudaError_t launch_sort_tiles(const ChunkCtx& c);
 cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out_depth, float* out_alpha);

@@ -1,0 +1,265 @@
+// sgr_knn.cu — mean squared distance to the 3 nearest other points (replaces `simple_knn._C.distCUDA2`,
+// /root/reference/core/gaussians/gs.py:70; oracle: knn_mean_dist2).
+//
+// Exact.  Points are binned into a uniform grid (counting sort by cell), and every point scans the cells around it
+// shell by shell until the shell's distance bound exceeds its current third-best distance.  Distances are evaluated
+// as (dx*dx + dy*dy) + dz*dz in fp32 without contraction (file built with --fmad=false), so the three smallest values
+// — and therefore the result — are bit-identical to the brute-force oracle regardless of visiting order.
+#include <cfloat>
+
+#include "sgr_common.cuh"
+
+namespace sgr {
+namespace {
+
+struct KnnHeader {
+    float lo[3], hi[3];
+    float cell, inv_cell;
+    int dim[3];
+    unsigned int num_cells;
+};
+
+struct KnnLayout {
+    uint64_t header, cell_of, cell_start, cell_fill, sorted, total;
+};
+
+constexpr unsigned int kMaxCells = 1u << 21;
+
+KnnLayout knn_layout(int N) {
+    KnnLayout L;
+    uint64_t o = 0;
+    L.header = o;     o = align_up(o + sizeof(KnnHeader));
+    L.cell_of = o;    o = align_up(o + uint64_t(N) * 4);
+    L.cell_start = o; o = align_up(o + uint64_t(kMaxCells + 1) * 4);
+    L.cell_fill = o;  o = align_up(o + uint64_t(kMaxCells) * 4);
+    L.sorted = o;     o = align_up(o + uint64_t(N) * 16);
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ float atomic_min_float(float* addr, float v) {   // valid for any sign via int/uint trick
+    return (v >= 0.0f) ? __int_as_float(atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v)))
+                       : __uint_as_float(atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v)));
+}
+__device__ __forceinline__ float atomic_max_float(float* addr, float v) {
+    return (v >= 0.0f) ? __int_as_float(atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v)))
+                       : __uint_as_float(atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v)));
+}
+
+__global__ void knn_init_kernel(KnnHeader* h) {
+    for (int k = 0; k < 3; ++k) { h->lo[k] = FLT_MAX; h->hi[k] = -FLT_MAX; }
+}
+
+__global__ void __launch_bounds__(256) knn_bbox_kernel(const float* __restrict__ pts, int N, KnnHeader* h) {
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float v = pts[3 * i + k];
+            lo[k] = fminf(lo[k], v); hi[k] = fmaxf(hi[k], v);
+        }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], d));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], d));
+        }
+        if ((threadIdx.x & 31) == 0) { atomic_min_float(&h->lo[k], lo[k]); atomic_max_float(&h->hi[k], hi[k]); }
+    }
+}
+
+// Cell edge so that an average occupied neighbourhood holds a handful of points: the points are a surface sample, so
+// the edge is derived from the bounding-box surface scale rather than its volume.
+__global__ void knn_grid_kernel(KnnHeader* h, int N) {
+    float ext[3];
+    for (int k = 0; k < 3; ++k) ext[k] = fmaxf(h->hi[k] - h->lo[k], 1e-12f);
+    const float area = 2.0f * (ext[0] * ext[1] + ext[1] * ext[2] + ext[0] * ext[2]);
+    float cell = sqrtf(area * 2.0f / float(N > 0 ? N : 1));
+    const float emax = fmaxf(ext[0], fmaxf(ext[1], ext[2]));
+    cell = fmaxf(cell, emax / 1024.0f);
+    for (;;) {
+        unsigned long long cells = 1;
+        for (int k = 0; k < 3; ++k) {
+            int d = int(ext[k] / cell) + 1;
+            d = d < 1 ? 1 : d;
+            h->dim[k] = d;
+            cells *= (unsigned long long)d;
+        }
+        if (cells <= kMaxCells) { h->num_cells = (unsigned int)cells; break; }
+        cell *= 1.26f;
+    }
+    h->cell = cell;
+    h->inv_cell = 1.0f / cell;
+}
+
+__device__ __forceinline__ int3 cell_coord(const KnnHeader* h, float x, float y, float z) {
+    int3 c;
+    c.x = min(h->dim[0] - 1, max(0, int((x - h->lo[0]) * h->inv_cell)));
+    c.y = min(h->dim[1] - 1, max(0, int((y - h->lo[1]) * h->inv_cell)));
+    c.z = min(h->dim[2] - 1, max(0, int((z - h->lo[2]) * h->inv_cell)));
+    return c;
+}
+
+__global__ void __launch_bounds__(256) knn_count_kernel(const float* __restrict__ pts, int N, const KnnHeader* h,
+                                                        unsigned int* cell_of, unsigned int* cell_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int3 c = cell_coord(h, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+    const unsigned int id = (unsigned(c.z) * h->dim[1] + c.y) * h->dim[0] + c.x;
+    cell_of[i] = id;
+    atomicAdd(cell_count + id, 1u);
+}
+
+// single-CTA exclusive scan of cell counts (<= 2^21 cells): cell_start[c], cell_start[num_cells] = N
+__global__ void __launch_bounds__(1024) knn_scan_kernel(const KnnHeader* h, unsigned int* cell_start /* in: counts */) {
+    __shared__ unsigned int s_warp[32];
+    __shared__ unsigned int s_carry;
+    const unsigned int n = h->num_cells;
+    const int t = threadIdx.x;
+    if (t == 0) s_carry = 0;
+    __syncthreads();
+    for (unsigned int base = 0; base < n; base += 1024 * 8) {
+        unsigned int v[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const unsigned int k = base + t * 8 + j;
+            v[j] = k < n ? cell_start[k] : 0u;
+            sum += v[j];
+        }
+        unsigned int inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int u = __shfl_up_sync(0xffffffffu, inc, d);
+            if ((t & 31) >= d) inc += u;
+        }
+        if ((t & 31) == 31) s_warp[t >> 5] = inc;
+        __syncthreads();
+        if (t < 32) {
+            unsigned int w = s_warp[t], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned int u = __shfl_up_sync(0xffffffffu, wi, d);
+                if (t >= d) wi += u;
+            }
+            s_warp[t] = wi - w;
+        }
+        __syncthreads();
+        unsigned int run = s_carry + s_warp[t >> 5] + inc - sum;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const unsigned int k = base + t * 8 + j;
+            if (k < n) cell_start[k] = run;
+            run += v[j];
+        }
+        __syncthreads();
+        if (t == 1023) s_carry = run;
+        __syncthreads();
+    }
+    if (t == 0) cell_start[n] = s_carry;
+}
+
+__global__ void __launch_bounds__(256) knn_fill_kernel(const float* __restrict__ pts, int N,
+                                                       const unsigned int* __restrict__ cell_of,
+                                                       const unsigned int* __restrict__ cell_start,
+                                                       unsigned int* cell_fill, float4* sorted) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const unsigned int c = cell_of[i];
+    const unsigned int pos = cell_start[c] + atomicAdd(cell_fill + c, 1u);
+    sorted[pos] = make_float4(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], __int_as_float(i));
+}
+
+__device__ __forceinline__ void insert3(float d, float& b0, float& b1, float& b2) {
+    if (d < b2) {
+        if (d < b1) {
+            b2 = b1;
+            if (d < b0) { b1 = b0; b0 = d; } else b1 = d;
+        } else b2 = d;
+    }
+}
+
+__global__ void __launch_bounds__(128) knn_query_kernel(const float* __restrict__ pts, int N, const KnnHeader* h,
+                                                        const unsigned int* __restrict__ cell_start,
+                                                        const float4* __restrict__ sorted, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
+    const int3 c = cell_coord(h, px, py, pz);
+    const int dx = h->dim[0], dy = h->dim[1], dz = h->dim[2];
+    const float cell = h->cell;
+    float b0, b1, b2;
+    b0 = b1 = b2 = __int_as_float(0x7f800000);      // fewer than 3 other points -> +inf, like the oracle
+    const int max_ring = max(dx, max(dy, dz));
+    for (int ring = 0; ring <= max_ring; ++ring) {
+        if (ring >= 1) {
+            // every unvisited point lies at least (ring - 1) * cell + (distance to the nearest face of the own cell)
+            // away; use the weaker bound (ring - 1) * cell, shrunk slightly for rounding of the cell assignment
+            const float bound = float(ring - 1) * cell * 0.999f;
+            if (bound * bound > b2) break;
+        }
+        const int z0 = c.z - ring, z1 = c.z + ring, y0 = c.y - ring, y1 = c.y + ring, x0 = c.x - ring, x1 = c.x + ring;
+        for (int z = max(z0, 0); z <= min(z1, dz - 1); ++z)
+            for (int y = max(y0, 0); y <= min(y1, dy - 1); ++y) {
+                const bool shell_row = (z == z0 || z == z1 || y == y0 || y == y1);
+                const int step = shell_row ? 1 : max(1, x1 - x0);        // interior rows: only the two end cells
+                for (int x = x0; x <= x1; x += step) {
+                    if (x < 0 || x >= dx) continue;
+                    const unsigned int id = (unsigned(z) * dy + y) * dx + x;
+                    const unsigned int s = cell_start[id], e = cell_start[id + 1];
+                    for (unsigned int k = s; k < e; ++k) {
+                        const float4 q = __ldg(sorted + k);
+                        if (__float_as_int(q.w) == i) continue;
+                        const float ddx = q.x - px, ddy = q.y - py, ddz = q.z - pz;
+                        insert3(ddx * ddx + ddy * ddy + ddz * ddz, b0, b1, b2);
+                    }
+                }
+            }
+    }
+    out[i] = (b0 + b1 + b2) / 3.0f;
+}
+
+}  // namespace
+}  // namespace sgr
+
+using namespace sgr;
+
+extern "C" {
+
+uint64_t sgr_knn_scratch_bytes(int32_t num_points) {
+    if (num_points < 0) return 0;
+    return knn_layout(num_points).total;
+}
+
+// defined in sgr_api.cu
+int sgr_set_error_(int code, const char* msg);
+
+int sgr_knn_mean_dist2(const float* points, int32_t N, float* out, void* scratch, uint64_t scratch_bytes,
+                       void* stream) {
+    if (N < 0 || (N > 0 && (!points || !out))) return sgr_set_error_(SGR_E_INVALID_ARGUMENT, "bad knn arguments");
+    if (N == 0) return SGR_OK;
+    const KnnLayout L = knn_layout(N);
+    if (!scratch || scratch_bytes < L.total) return sgr_set_error_(SGR_E_BUFFER_TOO_SMALL, "knn scratch buffer too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    char* x = static_cast<char*>(scratch);
+    KnnHeader* h = reinterpret_cast<KnnHeader*>(x + L.header);
+    unsigned int* cell_of = reinterpret_cast<unsigned int*>(x + L.cell_of);
+    unsigned int* cell_start = reinterpret_cast<unsigned int*>(x + L.cell_start);
+    unsigned int* cell_fill = reinterpret_cast<unsigned int*>(x + L.cell_fill);
+    float4* sorted = reinterpret_cast<float4*>(x + L.sorted);
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(cell_start, 0, (uint64_t(kMaxCells) + 1) * 4, s)) != cudaSuccess ||
+        (e = cudaMemsetAsync(cell_fill, 0, uint64_t(kMaxCells) * 4, s)) != cudaSuccess)
+        return sgr_set_error_(SGR_E_CUDA, cudaGetErrorString(e));
+    knn_init_kernel<<<1, 1, 0, s>>>(h);
+    knn_bbox_kernel<<<min((N + 255) / 256, 592), 256, 0, s>>>(points, N, h);
+    knn_grid_kernel<<<1, 1, 0, s>>>(h, N);
+    knn_count_kernel<<<(N + 255) / 256, 256, 0, s>>>(points, N, h, cell_of, cell_start);
+    knn_scan_kernel<<<1, 1024, 0, s>>>(h, cell_start);
+    knn_fill_kernel<<<(N + 255) / 256, 256, 0, s>>>(points, N, cell_of, cell_start, cell_fill, sorted);
+    knn_query_kernel<<<(N + 127) / 128, 128, 0, s>>>(points, N, h, cell_start, sorted, out);
+    if ((e = cudaGetLastError()) != cudaSuccess) return sgr_set_error_(SGR_E_CUDA, cudaGetErrorString(e));
+    return SGR_OK;
+}
+
+}  // extern "C"

@@ -8,6 +8,8 @@
 // Replaces upstream preprocessCUDA / duplicateWithKeys / computeCov2DCUDA+preprocessCUDA(backward)
 // (third-party diff_gaussian_rasterization; call site /root/reference/core/gaussians/gs.py:99-106;
 // SURVEY.md A.2, A.3, A.6).
+#include <cuda_fp16.h>
+
 #include "sgr_common.cuh"
 
 namespace sgr {
@@ -163,7 +165,11 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(PreArgs a) {
                         }
                     }
                 }
-                a.g0[oi] = make_float4(px, py, ex, ey);
+                // rec0 = (x, y, half2(ex, ey) rounded up, pthr): power < pthr can never reach alpha >= 1/255
+                const float pthr = (opac >= kAlphaMin) ? -(logf(255.0f * opac) + 1.0e-3f) : 1.0e30f;
+                const unsigned int exy = uint32_t(__half_as_ushort(__float2half_ru(ex))) |
+                                         (uint32_t(__half_as_ushort(__float2half_ru(ey))) << 16);
+                a.g0[oi] = make_float4(px, py, __uint_as_float(exy), pthr);
                 a.g1[oi] = make_float4(c2.c * det_inv, -c2.b * det_inv, c2.a * det_inv, opac);
                 a.g2[oi] = make_float4(s_col[3 * t], s_col[3 * t + 1], s_col[3 * t + 2], pvz);
                 unsigned int* cnt = a.tile_cnt + size_t(r) * a.g.num_tiles;

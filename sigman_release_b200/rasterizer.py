@@ -1,0 +1,348 @@
+"""Drop-in for the third-party ``diff_gaussian_rasterization`` Python API used by
+``/root/reference/core/gaussians/gs.py:8-11,82-106``, backed by the
+sm_100a C-ABI library ``libsgr_b200.so``.
+
+* ``GaussianRasterizationSettings`` — NamedTuple with upstream's 12 fields in upstream's order.
+* ``GaussianRasterizer(raster_settings)(means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
+  rotations=None, cov3D_precomp=None)`` -> ``(color [3,H,W], radii [N] int32, depth [1,H,W], alpha [1,H,W])``.
+* ``rasterize_batch`` — the B200-native entry point: B subjects x V views in ONE launch set (replaces the Python
+  double loop of gs.py:62-109).
+
+PyTorch is used for device memory, streams and autograd plumbing only; all arithmetic runs in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import NamedTuple, Optional
+
+import torch
+
+from . import _native
+
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_batch", "rasterize_gaussians",
+           "cov3d_from_scale_rot", "last_status"]
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+# ------------------------------------------------------------------------------------------------ workspace policy
+# Number of (Gaussian, tile) instances is data dependent and counted on the device.  The shim sizes the instance
+# arrays from a per-shape estimate; the first call for a shape (and every call in "sync" mode) reads the device status
+# back and retries on overflow, later calls in "deferred" mode fetch the status with an asynchronous copy that is
+# verified when the backward pass (or the next call) runs.
+_OVERFLOW_MODE = os.environ.get("SGR_OVERFLOW_CHECK", "deferred")      # "sync" | "deferred"
+_HEADROOM = 1.5
+_est_per_render: dict = {}
+_last_status: Optional[dict] = None
+_pending: list = []            # deferred status checks: (event, pinned tensor, key, renders)
+
+
+def last_status() -> Optional[dict]:
+    """Status block of the most recent synchronously checked forward (instances, longest tile list, ...)."""
+    return _last_status
+
+
+def _status_from_bytes(t: torch.Tensor) -> dict:
+    st = _native.SgrStatus.from_buffer_copy(bytes(t.numpy().tobytes()[: ctypes.sizeof(_native.SgrStatus)]))
+    return dict(instances_required=int(st.instances_required), instances_capacity=int(st.instances_capacity),
+                overflow=int(st.overflow), max_tile_instances=int(st.max_tile_instances),
+                nonempty_tiles=int(st.nonempty_tiles))
+
+
+def _drain_pending(block: bool) -> None:
+    global _last_status
+    keep = []
+    for ev, pinned, key, R in _pending:
+        if not block and not ev.query():
+            keep.append((ev, pinned, key, R))
+            continue
+        ev.synchronize()
+        st = _status_from_bytes(pinned)
+        _last_status = st
+        per = int(st["instances_required"] / max(R, 1) * _HEADROOM) + 1024
+        _est_per_render[key] = max(_est_per_render.get(key, 0), per)
+        if st["overflow"]:
+            _pending[:] = keep
+            raise _native.SgrError(
+                _native.SGR_E_INSTANCE_OVERFLOW,
+                f"a previous deferred-check render overflowed its instance capacity "
+                f"({st['instances_required']} needed, {st['instances_capacity']} available); its outputs are "
+                "background-only for the dropped renders.  The estimate has been raised; re-run the step "
+                "(or set SGR_OVERFLOW_CHECK=sync).")
+    _pending[:] = keep
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _check_input(name: str, t: torch.Tensor, shape) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (sigman_release_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name} must be float32, got {t.dtype}")
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def _fill_problem(p: _native.SgrProblem, B, V, N, H, W, tanfovx, tanfovy, means3D, cov3D, colors, opacities, viewm,
+                  projm, bg, cap, flags, rpc):
+    p.num_subjects, p.views_per_subject, p.num_gaussians = B, V, N
+    p.image_height, p.image_width = H, W
+    p.tanfovx, p.tanfovy = float(tanfovx), float(tanfovy)
+    p.means3D, p.cov3D, p.colors, p.opacities = _ptr(means3D), _ptr(cov3D), _ptr(colors), _ptr(opacities)
+    p.viewmatrix, p.projmatrix, p.bg = _ptr(viewm), _ptr(projm), _ptr(bg)
+    p.max_instances = cap
+    p.renders_per_chunk = rpc
+    p.flags = flags
+
+
+class _RasterizeBatch(torch.autograd.Function):
+    """means3D [B,N,3], cov3D [B,N,6], colors [B,N,3], opacities [B,N], means2D [B,V,N,3] (gradient slot only)."""
+
+    @staticmethod
+    def forward(ctx, means3D, cov3D, colors, opacities, means2D, viewmatrix, projmatrix, bg, H, W, tanfovx, tanfovy,
+                flags, renders_per_chunk):
+        global _last_status
+        L = _native.lib()
+        B, N = int(means3D.shape[0]), int(means3D.shape[1])
+        V = int(viewmatrix.shape[1])
+        R = B * V
+        dev = means3D.device
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            color = torch.empty((B, V, 3, H, W), dtype=torch.float32, device=dev)
+            depth = torch.empty((B, V, 1, H, W), dtype=torch.float32, device=dev)
+            alpha = torch.empty((B, V, 1, H, W), dtype=torch.float32, device=dev)
+            radii = torch.empty((B, V, N), dtype=torch.int32, device=dev)
+            key = (dev.index, N, H, W)
+            _drain_pending(block=False)
+            first = key not in _est_per_render
+            per = _est_per_render.get(key, max(3 * N, 4096))
+            sync_check = first or _OVERFLOW_MODE == "sync"
+            while True:
+                cap = min(int(per) * R, (1 << 32) - 2)
+                state_bytes = int(L.sgr_state_bytes(B, V, N, H, W, cap))
+                scratch_bytes = int(L.sgr_scratch_bytes(B, V, N, H, W, cap, renders_per_chunk))
+                state = torch.empty((state_bytes,), dtype=torch.uint8, device=dev)
+                scratch = torch.empty((scratch_bytes,), dtype=torch.uint8, device=dev)
+                a = _native.SgrForwardArgs()
+                _fill_problem(a.p, B, V, N, H, W, tanfovx, tanfovy, means3D, cov3D, colors, opacities, viewmatrix,
+                              projmatrix, bg, cap, flags, renders_per_chunk)
+                a.out_color, a.out_depth, a.out_alpha, a.radii = _ptr(color), _ptr(depth), _ptr(alpha), _ptr(radii)
+                a.state, a.state_bytes = _ptr(state), state_bytes
+                a.scratch, a.scratch_bytes = _ptr(scratch), scratch_bytes
+                a.stream = ctypes.c_void_p(stream.cuda_stream)
+                _native.check(L.sgr_forward(ctypes.byref(a)))
+                if not sync_check:
+                    pinned = torch.empty((64,), dtype=torch.uint8, pin_memory=True)
+                    pinned.copy_(state[:64], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(stream)
+                    _pending.append((ev, pinned, key, R))
+                    break
+                st = _native.SgrStatus()
+                rc = L.sgr_read_status(_ptr(state), ctypes.c_void_p(stream.cuda_stream), ctypes.byref(st))
+                if rc not in (_native.SGR_OK, _native.SGR_E_INSTANCE_OVERFLOW):
+                    _native.check(rc)
+                need_per = int(st.instances_required / max(R, 1) * _HEADROOM) + 1024
+                _est_per_render[key] = max(_est_per_render.get(key, 0), need_per)
+                _last_status = dict(instances_required=int(st.instances_required),
+                                    instances_capacity=int(st.instances_capacity), overflow=int(st.overflow),
+                                    max_tile_instances=int(st.max_tile_instances),
+                                    nonempty_tiles=int(st.nonempty_tiles))
+                if rc == _native.SGR_OK:
+                    break
+                if int(st.instances_required) >= (1 << 32) - 2:
+                    raise _native.SgrError(rc, "more than 2^32 (Gaussian, tile) instances in one call; split the batch")
+                per = _est_per_render[key]
+                del state, scratch
+        ctx.save_for_backward(means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg, alpha, radii, state)
+        ctx.dims = (B, V, N, H, W, float(tanfovx), float(tanfovy), cap, flags, renders_per_chunk, state_bytes)
+        ctx.want_means2D = means2D is not None and means2D.requires_grad
+        ctx.mark_non_differentiable(radii)
+        return color, radii, depth, alpha
+
+    @staticmethod
+    def backward(ctx, g_color, g_radii, g_depth, g_alpha):
+        L = _native.lib()
+        means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg, alpha, radii, state = ctx.saved_tensors
+        B, V, N, H, W, tanfovx, tanfovy, cap, flags, rpc, state_bytes = ctx.dims
+        dev = means3D.device
+        _drain_pending(block=True)       # a deferred overflow of the forward surfaces here
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            if g_color is None:
+                g_color = torch.zeros((B, V, 3, H, W), dtype=torch.float32, device=dev)
+            g_color = g_color.contiguous().float()
+            g_depth = None if g_depth is None else g_depth.contiguous().float()
+            g_alpha = None if g_alpha is None else g_alpha.contiguous().float()
+            d_means3D = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+            d_cov3D = torch.empty((B, N, 6), dtype=torch.float32, device=dev)
+            d_colors = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+            d_opac = torch.empty((B, N), dtype=torch.float32, device=dev)
+            d_means2D = torch.empty((B, V, N, 3), dtype=torch.float32, device=dev) if ctx.want_means2D else None
+            scratch_bytes = int(L.sgr_scratch_bytes(B, V, N, H, W, cap, rpc))
+            scratch = torch.empty((scratch_bytes,), dtype=torch.uint8, device=dev)
+            a = _native.SgrBackwardArgs()
+            _fill_problem(a.p, B, V, N, H, W, tanfovx, tanfovy, means3D, cov3D, colors, opacities, viewmatrix,
+                          projmatrix, bg, cap, flags, rpc)
+            a.out_alpha, a.radii = _ptr(alpha), _ptr(radii)
+            a.dL_dcolor, a.dL_ddepth, a.dL_dalpha = _ptr(g_color), _ptr(g_depth), _ptr(g_alpha)
+            a.dL_dmeans3D, a.dL_dcov3D, a.dL_dcolors, a.dL_dopacities = (_ptr(d_means3D), _ptr(d_cov3D),
+                                                                        _ptr(d_colors), _ptr(d_opac))
+            a.dL_dmeans2D = _ptr(d_means2D)
+            a.state, a.state_bytes = _ptr(state), state_bytes
+            a.scratch, a.scratch_bytes = _ptr(scratch), scratch_bytes
+            a.stream = ctypes.c_void_p(stream.cuda_stream)
+            _native.check(L.sgr_backward(ctypes.byref(a)))
+        return (d_means3D, d_cov3D, d_colors, d_opac, d_means2D, None, None, None, None, None, None, None, None, None)
+
+
+def rasterize_batch(means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg, image_height, image_width,
+                    tanfovx, tanfovy, means2D=None, clamp_color=False, simple_blend=False, renders_per_chunk=0):
+    """Render B subjects x V views in one launch set.
+
+    means3D [B,N,3], cov3D [B,N,6] (xx,xy,xz,yy,yz,zz — gs.py:32-37), colors [B,N,3], opacities [B,N] or [B,N,1],
+    viewmatrix / projmatrix [B,V,4,4] in the layout of gs.py:89-90 (``cam_view``, ``cam_view_proj``), bg [3].
+    Returns ``(color [B,V,3,H,W], radii [B,V,N] int32, depth [B,V,1,H,W], alpha [B,V,1,H,W])``; differentiable
+    w.r.t. means3D, cov3D, colors, opacities (gradients summed over a subject's views) and, if given, the per-render
+    gradient slot ``means2D [B,V,N,3]``.  ``clamp_color`` fuses gs.py:107's ``clamp(0, 1)``.
+    """
+    if means3D.dim() != 3 or means3D.shape[-1] != 3:
+        raise ValueError("means3D must be [B,N,3]")
+    B, N = int(means3D.shape[0]), int(means3D.shape[1])
+    if viewmatrix.dim() != 4 or tuple(viewmatrix.shape[2:]) != (4, 4) or int(viewmatrix.shape[0]) != B:
+        raise ValueError("viewmatrix must be [B,V,4,4]")
+    V = int(viewmatrix.shape[1])
+    if opacities.dim() == 3:
+        opacities = opacities.reshape(B, N)
+    means3D = _check_input("means3D", means3D, (B, N, 3))
+    cov3D = _check_input("cov3D", cov3D, (B, N, 6))
+    colors = _check_input("colors", colors, (B, N, 3))
+    opacities = _check_input("opacities", opacities, (B, N))
+    viewmatrix = _check_input("viewmatrix", viewmatrix, (B, V, 4, 4))
+    projmatrix = _check_input("projmatrix", projmatrix, (B, V, 4, 4))
+    bg = _check_input("bg", bg, (3,))
+    if means2D is not None and tuple(means2D.shape) != (B, V, N, 3):
+        raise ValueError("means2D must be [B,V,N,3]")
+    flags = (_native.FLAG_CLAMP_COLOR if clamp_color else 0) | (_native.FLAG_SIMPLE_BLEND if simple_blend else 0)
+    return _RasterizeBatch.apply(means3D, cov3D, colors, opacities, means2D, viewmatrix, projmatrix, bg,
+                                 int(image_height), int(image_width), float(tanfovx), float(tanfovy), flags,
+                                 int(renders_per_chunk))
+
+
+# ------------------------------------------------------------------------------------------------ optional inputs
+class _Cov3DFromScaleRot(torch.autograd.Function):
+    """upstream computeCov3D (+ backward): Sigma = R diag((mod*s)^2) R^T from scales [N,3], quaternions [N,4]."""
+
+    @staticmethod
+    def forward(ctx, scales, rotations, scale_modifier):
+        L = _native.lib()
+        N = int(scales.shape[0])
+        cov = torch.empty((N, 6), dtype=torch.float32, device=scales.device)
+        with torch.cuda.device(scales.device):
+            s = torch.cuda.current_stream(scales.device)
+            _native.check(L.sgr_cov3d_from_scale_rot(_ptr(scales), _ptr(rotations), float(scale_modifier), N,
+                                                     _ptr(cov), ctypes.c_void_p(s.cuda_stream)))
+        ctx.save_for_backward(scales, rotations)
+        ctx.mod = float(scale_modifier)
+        return cov
+
+    @staticmethod
+    def backward(ctx, g_cov):
+        L = _native.lib()
+        scales, rotations = ctx.saved_tensors
+        N = int(scales.shape[0])
+        g_cov = g_cov.contiguous().float()
+        ds = torch.empty_like(scales)
+        dr = torch.empty_like(rotations)
+        with torch.cuda.device(scales.device):
+            s = torch.cuda.current_stream(scales.device)
+            _native.check(L.sgr_cov3d_from_scale_rot_backward(_ptr(scales), _ptr(rotations), ctx.mod, N, _ptr(g_cov),
+                                                              _ptr(ds), _ptr(dr), ctypes.c_void_p(s.cuda_stream)))
+        return ds, dr, None
+
+
+def cov3d_from_scale_rot(scales, rotations, scale_modifier=1.0):
+    N = int(scales.shape[0])
+    scales = _check_input("scales", scales, (N, 3))
+    rotations = _check_input("rotations", rotations, (N, 4))
+    return _Cov3DFromScaleRot.apply(scales, rotations, float(scale_modifier))
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings: GaussianRasterizationSettings):
+    """One view of one Gaussian set — upstream ``rasterize_gaussians`` (same argument order)."""
+    if sh is not None and sh.numel() > 0:
+        raise NotImplementedError(
+            "spherical-harmonics colours are not on the SIGMAN path (sh_degree=0, shs=None, "
+            "/root/reference/core/gaussians/gs.py:91,102); pass colors_precomp")
+    N = int(means3D.shape[0])
+    if cov3Ds_precomp is None or cov3Ds_precomp.numel() == 0:
+        cov3D = cov3d_from_scale_rot(scales, rotations, raster_settings.scale_modifier)
+    else:
+        cov3D = cov3Ds_precomp
+    s = raster_settings
+    H, W = int(s.image_height), int(s.image_width)
+    dev = means3D.device
+    m2 = None
+    if means2D is not None and means2D.requires_grad:
+        m2 = means2D.reshape(1, 1, N, 3)
+    color, radii, depth, alpha = rasterize_batch(
+        means3D.reshape(1, N, 3), cov3D.reshape(1, N, 6), colors_precomp.reshape(1, N, 3), opacities.reshape(1, N),
+        s.viewmatrix.to(dev, torch.float32).reshape(1, 1, 4, 4), s.projmatrix.to(dev, torch.float32).reshape(1, 1, 4, 4),
+        s.bg.to(dev, torch.float32).reshape(3), H, W, float(s.tanfovx), float(s.tanfovy), means2D=m2)
+    return color[0, 0], radii[0, 0], depth[0, 0], alpha[0, 0]
+
+
+class GaussianRasterizer(torch.nn.Module):
+    """Same constructor, ``forward`` keywords, return tuple and exceptions as upstream's module
+    (call site gs.py:96-106)."""
+
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions: torch.Tensor) -> torch.Tensor:
+        """upstream ``_C.mark_visible``: boolean [N], True where the view-space depth exceeds 0.2."""
+        L = _native.lib()
+        s = self.raster_settings
+        with torch.no_grad():
+            pos = positions.detach().contiguous().float()
+            N = int(pos.shape[0])
+            vis = torch.empty((N,), dtype=torch.uint8, device=pos.device)
+            vm = s.viewmatrix.to(pos.device, torch.float32).contiguous()
+            pm = s.projmatrix.to(pos.device, torch.float32).contiguous()
+            with torch.cuda.device(pos.device):
+                st = torch.cuda.current_stream(pos.device)
+                _native.check(L.sgr_mark_visible(_ptr(pos), N, _ptr(vm), _ptr(pm), _ptr(vis),
+                                                 ctypes.c_void_p(st.cuda_stream)))
+        return vis.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or (
+                (scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                   self.raster_settings)

@@ -1,0 +1,87 @@
+"""Batched drop-in for ``GaussianRenderer`` of ``/root/reference/core/gaussians/gs.py:41-117`` and for
+``simple_knn._C.distCUDA2`` (gs.py:6,70).
+
+Same constructor argument (an options object with ``output_size_h``, ``output_size_w``, ``FoVy``), same
+``render(gaussians, cam_view, cam_view_proj, cam_pos, bg_color=None, scale_modifier=0.5)`` signature and the same
+``{"image": [B,V,3,H,W], "alpha": [B,V,1,H,W]}`` result — but the B x V Python double loop (one full rasteriser
+pipeline, one host sync and >= 8 launches per view) is replaced by ONE batched launch set of the sm_100a library.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native
+from .rasterizer import _ptr, rasterize_batch
+
+__all__ = ["GaussianRenderer", "distCUDA2", "get_covariance", "strip_lowerdiag"]
+
+
+def distCUDA2(points: torch.Tensor) -> torch.Tensor:
+    """Mean squared distance to the 3 nearest other points, float32 [N] (``simple_knn._C.distCUDA2``, gs.py:70)."""
+    L = _native.lib()
+    if not points.is_cuda:
+        raise ValueError("distCUDA2 needs a CUDA tensor (no CPU path)")
+    pts = points.detach().contiguous().float()
+    if pts.dim() != 2 or pts.shape[1] != 3:
+        raise ValueError("points must be [N,3]")
+    N = int(pts.shape[0])
+    out = torch.empty((N,), dtype=torch.float32, device=pts.device)
+    nbytes = int(L.sgr_knn_scratch_bytes(N))
+    with torch.cuda.device(pts.device):
+        scratch = torch.empty((nbytes,), dtype=torch.uint8, device=pts.device)
+        st = torch.cuda.current_stream(pts.device)
+        _native.check(L.sgr_knn_mean_dist2(_ptr(pts), N, _ptr(out), _ptr(scratch), nbytes,
+                                           ctypes.c_void_p(st.cuda_stream)))
+    return out
+
+
+def strip_lowerdiag(L: torch.Tensor) -> torch.Tensor:
+    """[..., 3, 3] -> [..., 6] in the order (xx, xy, xz, yy, yz, zz) of gs.py:29-38."""
+    return torch.stack([L[..., 0, 0], L[..., 0, 1], L[..., 0, 2], L[..., 1, 1], L[..., 1, 2], L[..., 2, 2]], dim=-1)
+
+
+def get_covariance(scaling: torch.Tensor, rotation: torch.Tensor, scaling_modifier: float = 1) -> torch.Tensor:
+    """R diag(s)^2 R^T packed to 6 values (gs.py:17-23); works on [N,...] and [B,N,...]."""
+    RS = rotation * (scaling * scaling).unsqueeze(-2)            # R diag(s^2)
+    return strip_lowerdiag(RS @ rotation.transpose(-1, -2))
+
+
+class GaussianRenderer:
+    def __init__(self, opt):
+        self.opt = opt
+        self.bg_color = torch.tensor([1, 1, 1], dtype=torch.float32, device="cuda")
+        self.tan_half_fov = np.tan(0.5 * self.opt.FoVy)
+
+    def prepare(self, gaussians):
+        """Per-subject preparation of gs.py:64-73, batched over B: returns (means3D, cov3D [B,N,6], rgb, opacity)."""
+        means3D = gaussians["position"].contiguous().float()
+        opacity = gaussians["opacity"].contiguous().float()
+        scales = gaussians["scale"].contiguous().float()
+        rot = gaussians["cov3d"].contiguous().float()
+        rgbs = gaussians["rgb"].contiguous().float()
+        B = means3D.shape[0]
+        with torch.no_grad():
+            dist2 = torch.stack([torch.clamp_min(distCUDA2(means3D[b]), 0.0000001) for b in range(B)])
+            base = torch.sqrt(dist2)[..., None]                 # detached kNN factor (gs.py:71)
+        scale = (scales + 1) * base
+        cov3D = get_covariance(scale, rot)
+        return means3D, cov3D, rgbs, opacity
+
+    def render(self, gaussians, cam_view, cam_view_proj, cam_pos, bg_color=None, scale_modifier=0.5):
+        device = gaussians["position"].device
+        B, V = cam_view.shape[:2]
+        H, W = int(self.opt.output_size_h), int(self.opt.output_size_w)
+        means3D, cov3D, rgbs, opacity = self.prepare(gaussians)
+        bg = self.bg_color if bg_color is None else bg_color
+        bg = bg.to(device=device, dtype=torch.float32)
+        needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (means3D, cov3D, rgbs, opacity))
+        # scale_modifier and cam_pos do not enter the cov3D_precomp / colors_precomp path
+        image, _radii, _depth, alpha = rasterize_batch(
+            means3D, cov3D, rgbs, opacity, cam_view.float(), cam_view_proj.float(), bg, H, W,
+            self.tan_half_fov, self.tan_half_fov, clamp_color=not needs_grad)
+        if needs_grad:
+            image = image.clamp(0, 1)                           # gs.py:107 (keeps torch's clamp gradient mask)
+        return {"image": image, "alpha": alpha}

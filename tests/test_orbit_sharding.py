@@ -1,0 +1,57 @@
+"""World-size-2 gloo test (CPU) of the multi-GPU orbit sharding: round-robin view shards + one all-gather give the
+same stack as a single-process render."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from sigman_release_b200.orbit import render_orbit_sharded, shard_views
+
+
+def _fake_render(views):
+    # an "image" that encodes its view id: [len, 5, 4, 6]  (RGB + depth + alpha planes)
+    return torch.stack([torch.full((5, 4, 6), float(v)) + torch.arange(5.0).view(5, 1, 1) * 0.01 for v in views])
+
+
+def _worker(rank, world, port, num_views, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        out = render_orbit_sharded(_fake_render, num_views)
+        ret[rank] = out
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_shard_views_partition():
+    for world in (1, 2, 4, 8):
+        for n in (1, 7, 90, 91):
+            shards = [shard_views(n, r, world) for r in range(world)]
+            assert sorted(sum(shards, [])) == list(range(n))
+            assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 1
+    with pytest.raises(ValueError):
+        shard_views(4, 2, 2)
+
+
+@pytest.mark.parametrize("num_views", [7, 90])
+def test_two_rank_gather_equals_single_process(num_views):
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), num_views, ret), nprocs=world, join=True)
+    expect = _fake_render(range(num_views))
+    for r in range(world):
+        assert torch.equal(ret[r], expect)
+
+
+def test_single_process_passthrough():
+    assert torch.equal(render_orbit_sharded(_fake_render, 5), _fake_render(range(5)))
