@@ -24,9 +24,9 @@ def test_config2_forward_bit_exact_all_views(body):
     for v in range(len(VIEWS)):
         r, ora = oracle_forward(body, vm[v], pm[v], 512, 512)
         np.testing.assert_array_equal(radii[0, v].cpu().numpy(), ora.radii)
-        np.testing.assert_array_equal(color[0, v].cpu().numpy(), ora.color)
-        np.testing.assert_array_equal(depth[0, v].cpu().numpy(), ora.depth)
-        np.testing.assert_array_equal(alpha[0, v].cpu().numpy(), ora.alpha)
+        np.testing.assert_array_equal(color[0, v].detach().cpu().numpy(), ora.color)
+        np.testing.assert_array_equal(depth[0, v].detach().cpu().numpy(), ora.depth)
+        np.testing.assert_array_equal(alpha[0, v].detach().cpu().numpy(), ora.alpha)
         if v in (0, 5):
             ranges, ncon, pl = debug_state(state, 1, len(VIEWS), 100_000, 512, 512, dims[7], v)
             b = r.binning()

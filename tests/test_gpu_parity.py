@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 def _assert_forward_equal(gpu_out, ora, render=0, exact=True):
     color, radii, depth, alpha = gpu_out
-    c = color[0, render].cpu().numpy(); d = depth[0, render].cpu().numpy(); a = alpha[0, render].cpu().numpy()
+    c = color[0, render].detach().cpu().numpy(); d = depth[0, render].detach().cpu().numpy(); a = alpha[0, render].detach().cpu().numpy()
     np.testing.assert_array_equal(radii[0, render].cpu().numpy(), ora.radii)
     if exact:
         np.testing.assert_array_equal(c, ora.color)
