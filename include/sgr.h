@@ -167,11 +167,13 @@ uint64_t sgr_launch_count(void);
  *   n_contrib    uint32[H*W]       upstream's per-pixel n_contrib
  *   point_list   uint32[point_list_capacity]  Gaussian index of every instance of the render in sorted order —
  *                                  upstream's binningState.point_list restricted to the render
+ *   tile_timing  uint32[tiles][2]  (start, duration) of the tile's forward blend in ns of the GPU global timer
+ *                                  (low 32 bits; load-balance diagnostics)
  * The shape arguments must be those of the forward that filled `state`. */
 int sgr_debug_copy_state(const void* state, int32_t num_subjects, int32_t views_per_subject, int32_t num_gaussians,
                          int32_t image_height, int32_t image_width, uint64_t max_instances, int32_t render,
                          uint32_t* tile_ranges, uint32_t* n_contrib, uint32_t* point_list,
-                         uint64_t point_list_capacity, void* stream);
+                         uint64_t point_list_capacity, uint32_t* tile_timing, void* stream);
 
 #ifdef __cplusplus
 }

@@ -112,7 +112,7 @@ SYMBOLS = {
     "sgr_profile_enable": (None, [ctypes.c_int]),
     "sgr_profile_collect": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint32)]),
     "sgr_launch_count": (_u64, []),
-    "sgr_debug_copy_state": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _u64, _i32, _vp, _vp, _vp, _u64, _vp]),
+    "sgr_debug_copy_state": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _u64, _i32, _vp, _vp, _vp, _u64, _vp, _vp]),
 }
 
 STAGES = ("preprocess", "scan", "scatter", "sort", "worklist", "blend_forward", "blend_backward",

@@ -96,6 +96,7 @@ void fill_ctx(ChunkCtx& c, const SgrProblem& p, void* state, void* scratch, cuda
     c.header = reinterpret_cast<StateHeader*>(s + S.header);
     c.tile_off = reinterpret_cast<unsigned int*>(s + S.tile_off);
     c.tile_cnt = reinterpret_cast<unsigned int*>(s + S.tile_cnt);
+    c.tile_time = reinterpret_cast<uint2*>(s + S.tile_time);
     c.n_contrib = reinterpret_cast<unsigned int*>(s + S.n_contrib);
     c.sorted_ids = reinterpret_cast<unsigned int*>(s + S.sorted_ids);
     c.rec0 = reinterpret_cast<float4*>(s + S.rec0);
@@ -191,6 +192,7 @@ int sgr_forward(const SgrForwardArgs* args) {
     SGR_CUDA(cudaGetLastError());
     g_launches += 1;
     SGR_CUDA(cudaMemsetAsync(c.tile_cnt, 0, size_t(R) * c.g.num_tiles * 4, stream));
+    SGR_CUDA(cudaMemsetAsync(c.tile_time, 0, size_t(R) * c.g.num_tiles * 8, stream));
     const size_t P = size_t(p.image_height) * p.image_width;
     for (int r0 = 0; r0 < R; r0 += rpc) {
         c.render_base = r0;
@@ -313,7 +315,7 @@ int sgr_cov3d_from_scale_rot_backward(const float* scales, const float* rotation
 
 int sgr_debug_copy_state(const void* state, int32_t B, int32_t V, int32_t N, int32_t H, int32_t W,
                          uint64_t max_instances, int32_t render, uint32_t* tile_ranges, uint32_t* n_contrib,
-                         uint32_t* point_list, uint64_t point_list_capacity, void* stream) {
+                         uint32_t* point_list, uint64_t point_list_capacity, uint32_t* tile_timing, void* stream) {
     if (!state || B <= 0 || V <= 0 || N < 0 || H <= 0 || W <= 0 || render < 0 || render >= B * V)
         return fail(SGR_E_INVALID_ARGUMENT, "bad debug_copy_state arguments");
     const StateLayout S = make_state_layout(B, V, N, H, W, max_instances);
@@ -329,6 +331,9 @@ int sgr_debug_copy_state(const void* state, int32_t B, int32_t V, int32_t N, int
     if (n_contrib)
         SGR_CUDA(cudaMemcpyAsync(n_contrib, reinterpret_cast<const unsigned int*>(s + S.n_contrib) + size_t(render) * H * W,
                                  size_t(H) * W * 4, cudaMemcpyDeviceToDevice, st));
+    if (tile_timing)
+        SGR_CUDA(cudaMemcpyAsync(tile_timing, reinterpret_cast<const uint2*>(s + S.tile_time) + size_t(render) * T,
+                                 size_t(T) * 8, cudaMemcpyDeviceToDevice, st));
     if (point_list && point_list_capacity) {
         debug_point_list_kernel<<<256, 256, 0, st>>>(off, cnt, T, reinterpret_cast<const unsigned int*>(s + S.sorted_ids),
                                                      point_list, point_list_capacity);

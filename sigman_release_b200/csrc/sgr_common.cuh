@@ -28,7 +28,7 @@ static_assert(sizeof(SgrStatus) == 32, "SgrStatus layout is part of the ABI");
 
 // Layout of `state` (kept forward -> backward) for a problem shape.
 struct StateLayout {
-    uint64_t header, tile_off, tile_cnt, n_contrib, sorted_ids, rec0, rec1, rec2, total;
+    uint64_t header, tile_off, tile_cnt, tile_time, n_contrib, sorted_ids, rec0, rec1, rec2, total;
 };
 // Layout of `scratch` (valid only inside one call).
 struct ScratchLayout {
@@ -48,6 +48,7 @@ inline StateLayout make_state_layout(int B, int V, int N, int H, int W, uint64_t
     L.header = o;      o = align_up(o + sizeof(StateHeader));
     L.tile_off = o;    o = align_up(o + R * T * 4);
     L.tile_cnt = o;    o = align_up(o + R * T * 4);
+    L.tile_time = o;   o = align_up(o + R * T * 8);     // (start ns, duration ns) of the forward blend per tile
     L.n_contrib = o;   o = align_up(o + R * P * 4);
     L.sorted_ids = o;  o = align_up(o + cap * 4);
     L.rec0 = o;        o = align_up(o + cap * 16);
@@ -108,12 +109,13 @@ struct RenderGeom {
 
 // ------------------------------------------------------------------------------------------------
 // exp_spec: bit-identical to oracle/sgr_oracle.cpp::exp_spec (fixed sequence of IEEE fp32 ops).
-__device__ __forceinline__ float exp_spec(float x) {
-    if (x != x) return x;
-    if (x < -87.0f) return 0.0f;
-    if (x > 88.0f) return __int_as_float(0x7f800000);
+// exp_core is the same sequence without the range / NaN checks, valid for x in [-87, 88] (and NaN -> NaN):
+// rint() and the float->int conversion are done with the 1.5 * 2^23 magic constant, which yields the identical
+// round-half-even integer n for |x * log2(e)| < 2^22 and leaves n in the low mantissa bits of `tn`.
+__device__ __forceinline__ float exp_core(float x) {
     const float t = __fmul_rn(x, 1.44269502162933349609375f);
-    const float n = rintf(t);
+    const float tn = __fadd_rn(t, 12582912.0f);
+    const float n = __fsub_rn(tn, 12582912.0f);
     float r = __fmaf_rn(n, -0.693145751953125f, x);
     r = __fmaf_rn(n, -1.428606765330187045e-06f, r);
     float p = 1.98412701e-4f;
@@ -124,7 +126,14 @@ __device__ __forceinline__ float exp_spec(float x) {
     p = __fmaf_rn(p, r, 0.5f);
     p = __fmaf_rn(p, r, 1.0f);
     p = __fmaf_rn(p, r, 1.0f);
-    return __int_as_float(__float_as_int(p) + (static_cast<int>(n) << 23));
+    return __int_as_float(__float_as_int(p) + (__float_as_int(tn) << 23));
+}
+
+__device__ __forceinline__ float exp_spec(float x) {
+    if (x != x) return x;
+    if (x < -87.0f) return 0.0f;
+    if (x > 88.0f) return __int_as_float(0x7f800000);
+    return exp_core(x);
 }
 
 // power = -0.5f * (A*dx*dx + C*dy*dy) - B*dx*dy evaluated in source order without contraction
@@ -153,6 +162,7 @@ struct ChunkCtx {
     StateHeader* header;
     unsigned int* tile_off;   // [R*T]
     unsigned int* tile_cnt;   // [R*T]
+    uint2* tile_time;         // [R*T]
     unsigned int* n_contrib;  // [R*P]
     unsigned int* sorted_ids; // [cap]
     float4 *rec0, *rec1, *rec2;   // [cap]

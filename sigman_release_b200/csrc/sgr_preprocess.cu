@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(PreArgs a) {
                     }
                 }
                 // rec0 = (x, y, half2(ex, ey) rounded up, pthr): power < pthr can never reach alpha >= 1/255
-                const float pthr = (opac >= kAlphaMin) ? -(logf(255.0f * opac) + 1.0e-3f) : 1.0e30f;
+                // (clamped to -87 so that exp_core's argument range holds: below it exp_spec returns 0 anyway)
+                const float pthr = (opac >= kAlphaMin) ? fmaxf(-(logf(255.0f * opac) + 1.0e-3f), -87.0f) : 1.0e30f;
                 const unsigned int exy = uint32_t(__half_as_ushort(__float2half_ru(ex))) |
                                          (uint32_t(__half_as_ushort(__float2half_ru(ey))) << 16);
                 a.g0[oi] = make_float4(px, py, __uint_as_float(exy), pthr);

@@ -177,6 +177,7 @@ class _RasterizeBatch(torch.autograd.Function):
         ctx.save_for_backward(means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg, alpha, radii, state)
         ctx.dims = (B, V, N, H, W, float(tanfovx), float(tanfovy), cap, flags, renders_per_chunk, state_bytes)
         ctx.want_means2D = means2D is not None and means2D.requires_grad
+        ctx.set_materialize_grads(False)     # unused depth / alpha outputs arrive as None, not as zero tensors
         ctx.mark_non_differentiable(radii)
         return color, radii, depth, alpha
 

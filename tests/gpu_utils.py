@@ -56,7 +56,8 @@ def debug_state(fn_ctx_state, B, V, N, H, W, cap, render):
     st = torch.cuda.current_stream()
     _native.check(L.sgr_debug_copy_state(ctypes.c_void_p(fn_ctx_state.data_ptr()), B, V, N, H, W, int(cap), render,
                                          ctypes.c_void_p(ranges.data_ptr()), ctypes.c_void_p(ncon.data_ptr()),
-                                         ctypes.c_void_p(pl.data_ptr()), cap_pl, ctypes.c_void_p(st.cuda_stream)))
+                                         ctypes.c_void_p(pl.data_ptr()), cap_pl, None,
+                                         ctypes.c_void_p(st.cuda_stream)))
     torch.cuda.synchronize()
     ranges = ranges.cpu().numpy().astype(np.uint32)
     n = int(ranges[:, 1].max()) if T else 0
