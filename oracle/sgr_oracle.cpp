@@ -19,9 +19,14 @@
 //
 // Conventions that make GPU parity checkable bit-for-bit (documented in DESIGN.md):
 //   * fp32 instantiation: every expression is evaluated in C source order with IEEE-754
-//     binary32 round-to-nearest operations and NO fused multiply-add (build with
-//     -ffp-contract=off, no -ffast-math).  Upstream is built by nvcc with FMA contraction in a
-//     compiler-chosen pattern that cannot be reproduced without its binary.
+//     binary32 round-to-nearest operations; a fused multiply-add is used exactly where the
+//     source says fma() and nowhere else (build with -ffp-contract=off, no -ffast-math).
+//     Upstream is built by nvcc with FMA contraction in a compiler-chosen pattern that cannot
+//     be reproduced without its binary; the per-pixel blend expressions below fix one such
+//     pattern (gauss_power / blend_forward) so that CPU and GPU agree bit for bit:
+//         power  = fma(dx, (-A/2)*dx, dy * fma(-C/2, dy, (-B)*dx))
+//         test_T = fma(-alpha, T, T)
+//         w = alpha*T;  C = fma(c, w, C);  D = fma(z, w, D);  Wt = Wt + w
 //   * exp(): upstream calls CUDA's expf (<= 2 ulp, built on MUFU.EX2, not reproducible on a CPU).
 //     The oracle uses exp_spec() below — a fixed sequence of IEEE fp32 operations accurate to
 //     ~1 ulp — and the CUDA kernels execute the same sequence.
@@ -82,6 +87,17 @@ inline int f2i_rz_sat(R v) {
     if (v >= R(2147483648.0)) return INT_MAX;
     if (v <= R(-2147483648.0)) return INT_MIN;
     return static_cast<int>(v);
+}
+
+inline float fma_r(float a, float b, float c) { return fmaf(a, b, c); }
+inline double fma_r(double a, double b, double c) { return std::fma(a, b, c); }
+
+// power = -1/2 (A dx^2 + C dy^2) - B dx dy in the fixed FMA pattern of the spec (header).  The halvings and the
+// negation are exact, so hA, hC, nB carry exactly the information of the conic.
+template <typename R>
+inline R gauss_power(R A, R B, R C, R dx, R dy) {
+    const R hA = R(-0.5f) * A, hC = R(-0.5f) * C, nB = -B;
+    return fma_r(dx, hA * dx, dy * fma_r(hC, dy, nB * dx));
 }
 
 inline uint32_t float_bits(float f) {
@@ -250,16 +266,17 @@ void blend_forward(int H, int W, const Geom<R>& g, const Binning& b, const R* co
                     ++evals;
                     const uint32_t id = b.point_list[k];
                     const R dx = g.x[id] - pxf, dy = g.y[id] - pyf;
-                    const R power = R(-0.5f) * (g.cA[id] * dx * dx + g.cC[id] * dy * dy) - g.cB[id] * dx * dy;
+                    const R power = gauss_power(g.cA[id], g.cB[id], g.cC[id], dx, dy);
                     if (power > R(0)) continue;
                     const R alpha = std::min(R(0.99f), g.opac[id] * exp_spec(power));
                     if (alpha < R(1.0f / 255.0f)) continue;
-                    const R test_T = T * (R(1) - alpha);
+                    const R test_T = fma_r(-alpha, T, T);      // T * (1 - alpha)
                     if (test_T < R(0.0001f)) break;          // "done = true"
                     ++blends;
-                    for (int ch = 0; ch < 3; ++ch) C[ch] += colors[3 * id + ch] * alpha * T;
-                    Wt += alpha * T;
-                    D += g.depth[id] * alpha * T;
+                    const R w = alpha * T;
+                    for (int ch = 0; ch < 3; ++ch) C[ch] = fma_r(colors[3 * id + ch], w, C[ch]);
+                    Wt += w;
+                    D = fma_r(g.depth[id], w, D);
                     T = test_T;
                     last = contributor;
                 }
@@ -323,7 +340,7 @@ void blend_backward(int N, int H, int W, const Geom<R>& g, const Binning& b, con
                         const uint32_t id = b.point_list[k];
                         const R dx = g.x[id] - pxf, dy = g.y[id] - pyf;
                         const R cA = g.cA[id], cB = g.cB[id], cC = g.cC[id], op = g.opac[id];
-                        const R power = R(-0.5f) * (cA * dx * dx + cC * dy * dy) - cB * dx * dy;
+                        const R power = gauss_power(cA, cB, cC, dx, dy);
                         if (power > R(0)) continue;
                         const R G = exp_spec(power);
                         const R alpha = std::min(R(0.99f), op * G);

@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsgr_b200.so")
+LIB_PATH = os.environ.get("SGR_LIB_PATH") or os.path.join(_HERE, "libsgr_b200.so")
 ABI_VERSION = 1
 
 SGR_OK = 0

@@ -2,22 +2,24 @@
 //
 // Replaces upstream renderCUDA forward/backward (third-party diff_gaussian_rasterization; call site
 // /root/reference/core/gaussians/gs.py:99-106).  Design (DESIGN.md "blend"):
-//   * persistent CTAs (a multiple of the SM count) pull (render, tile) work items from a device-side queue that is
-//     ordered longest-list-first (sgr_binning.cu::worklist_kernel);
-//   * the tile's depth-ordered 48-byte records (three float4 streams, contiguous per tile because the per-tile sort
-//     gathers them) are staged into a shared-memory ring with 1-D TMA bulk copies (cp.async.bulk) completing on
-//     mbarriers, issued by a dedicated producer warp; the eight consumer warps run decoupled from each other;
-//   * every consumer warp owns an 8x4 pixel block made of four 4x2 quarters.  It first tests 32 records at a time
-//     (lane = record) against each quarter with the conservative alpha >= 1/255 extent computed in the preprocess
-//     kernel (four ballots); then every quarter walks only its own survivors (lane = pixel), so up to four different
+//   * the unit of work is one 8x4 pixel block of one tile of one render.  Every WARP is autonomous: it pops work items
+//     from a device-side queue ordered longest-list-first (sgr_binning.cu::worklist_kernel), streams the tile's
+//     depth-ordered 48-byte records (three float4 streams, contiguous per tile because the per-tile sort gathers them)
+//     through its own shared-memory ring with 1-D TMA bulk copies (cp.async.bulk) completing on its own mbarriers, and
+//     never waits for another warp — no block-wide barrier, no producer/consumer hand-off, early exit as soon as its
+//     32 pixels are finished;
+//   * a block is four 4x2 quarters.  The warp tests 32 records at a time (lane = record) against each quarter with the
+//     conservative alpha >= 1/255 extent computed in the preprocess kernel (four ballots), compacts the survivors'
+//     indices per quarter, and then every quarter walks only its own survivors (lane = pixel), so up to four different
 //     Gaussians are evaluated per trip.  Culled records would have been skipped by the alpha test, so the per-pixel
 //     arithmetic, the contributor index and every output bit equal the straightforward kernel's;
 //   * the walk is split into phases through a per-warp shared-memory stash so that only the inherently sequential
-//     part sits on the dependent chain: phase A evaluates alpha for up to 16 trips (independent iterations, unrolled
-//     and interleaved by the compiler), phase B composites front to back reading the stashed alphas;
+//     part sits on the dependent chain: phase A evaluates alpha for up to 16 trips (independent, written load-first in
+//     blocks of four so the chains interleave), phase B composites front to back reading the stashed alphas;
 //   * backward: the same walk in reverse with three phases — A: alpha, B: the per-pixel transmittance / colour
-//     recurrences producing dL/dalpha and the blend weight, C: per-Gaussian partial sums reduced over the quarter's 8
-//     pixels with a transposing butterfly (lane k ends up with component k) and one atomic per component.
+//     recurrences producing dL/dalpha and the blend weight, C: the roles flip to lane = (Gaussian, quarter) pair, each
+//     lane summing the gradient terms of its quarter's 8 pixels in registers (XOR-swizzled stash, no shuffles) before
+//     one atomic per component.  Gradient arithmetic is free to use FMA (compared with a tolerance, not bit-exact).
 //
 // Compiled with --fmad=false: the per-pixel expressions are the oracle's (oracle/sgr_oracle.cpp::blend_forward /
 // blend_backward) evaluated in the same order, which makes colour, depth, alpha and n_contrib bit-exact.
@@ -30,12 +32,14 @@
 namespace sgr {
 namespace {
 
-constexpr int kChunk = 128;                    // records per ring stage
-constexpr int kStages = 4;
-constexpr int kConsumerWarps = 8;              // 8 warps x (8x4 pixels) = one 16x16 tile
-constexpr int kBlendThreads = (kConsumerWarps + 1) * 32;
+constexpr int kBatch = 32;                     // records per ring stage (one cull: lane = record)
+constexpr int kStages = 3;                     // per-warp TMA ring depth
+constexpr int kWarpsPerCta = 8;
+constexpr int kBlendThreads = kWarpsPerCta * 32;
+constexpr int kBlocksPerTile = 8;              // a 16x16 tile = eight 8x4 pixel blocks = eight work items
 constexpr int kBlockW = 8, kBlockH = 4;        // pixel block of one warp (four 4x2 quarters walk separate lists)
-constexpr int kSlots = 16;                     // trips per phase pass (depth of the per-warp stash)
+constexpr int kSlots = 16;                     // forward: trips per phase pass (depth of the per-warp stash)
+constexpr int kBwdSlots = 8;                   // backward: 8 trips x 4 quarters = 32 (Gaussian, quarter) pairs per pass
 constexpr unsigned int kFull = 0xffffffffu;
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -84,18 +88,15 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
-template <int kStashes>
-struct BlendSmem {
-    float4 r0[kStages][kChunk];
-    float4 r1[kStages][kChunk];
-    float4 r2[kStages][kChunk];
-    float stash[kConsumerWarps][kStashes][kSlots][32];
-    unsigned char list[kConsumerWarps][4][kChunk];   // per warp and quarter: chunk-local indices of the survivors
+template <int kStashes, int kDepth>
+struct WarpSmem {
+    float4 r0[kStages][kBatch];
+    float4 r1[kStages][kBatch];
+    float4 r2[kStages][kBatch];
+    float stash[kStashes][kDepth][32];
+    float dpix[4][32];                          // backward: dL/dcolor (3) and dL/ddepth of the block's pixels
+    unsigned char list[4][kBatch];              // per quarter: batch-local indices of the survivors (ascending)
     uint64_t full[kStages];
-    uint64_t empty[kStages];
-    unsigned int work;                          // current work item (chunk-local tile index) or 0xffffffff
-    unsigned int warps_done;
-    unsigned int max_last;                      // backward: largest n_contrib of the tile
 };
 
 __device__ __forceinline__ float2 unpack_extent(float packed) {
@@ -104,37 +105,56 @@ __device__ __forceinline__ float2 unpack_extent(float packed) {
                        __half2float(__ushort_as_half(static_cast<unsigned short>(u >> 16))));
 }
 
-// Cull the chunk's m records against the four 4x2 quarters of the warp's 8x4 block at (wx0, wy0): lane = record, one
-// ballot per quarter, warp-parallel compaction of the survivors' chunk-local indices into list[quarter][...] (ascending).
-// `limit`: records at or beyond it are ignored (backward: beyond the warp's largest n_contrib).  Returns the four counts.
-__device__ __forceinline__ uint4 cull_chunk(const float4* r0, unsigned int m, unsigned int limit, float wx0, float wy0,
-                                            unsigned char (*list)[kChunk], int lane) {
-    unsigned int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+// Cull a batch of m <= 32 records against the four 4x2 quarters of the warp's 8x4 block at (wx0, wy0): lane = record,
+// one ballot per quarter, warp-parallel compaction of the survivors' batch-local indices into list[quarter][...]
+// (ascending).  `limit`: records at or beyond it are ignored.  Returns the four survivor counts.
+__device__ __forceinline__ uint4 cull_batch(const float4* r0, unsigned int m, unsigned int limit, float wx0, float wy0,
+                                            unsigned char (*list)[kBatch], int lane) {
     const unsigned int lt = (1u << lane) - 1u;
-    for (unsigned int sub = 0; sub < m; sub += 32) {
-        const unsigned int e = sub + lane;
-        bool px0 = false, px1 = false, py0 = false, py1 = false;
-        if (e < m && e < limit) {
-            const float4 q = r0[e];
-            const float2 ext = unpack_extent(q.z);
-            const float xl = q.x - ext.x, xh = q.x + ext.x, yl = q.y - ext.y, yh = q.y + ext.y;
-            px0 = (xh >= wx0) && (xl <= wx0 + 3.0f);
-            px1 = (xh >= wx0 + 4.0f) && (xl <= wx0 + 7.0f);
-            py0 = (yh >= wy0) && (yl <= wy0 + 1.0f);
-            py1 = (yh >= wy0 + 2.0f) && (yl <= wy0 + 3.0f);
-        }
-        const unsigned int m0 = __ballot_sync(kFull, px0 && py0);
-        const unsigned int m1 = __ballot_sync(kFull, px1 && py0);
-        const unsigned int m2 = __ballot_sync(kFull, px0 && py1);
-        const unsigned int m3 = __ballot_sync(kFull, px1 && py1);
-        if (px0 && py0) list[0][n0 + __popc(m0 & lt)] = static_cast<unsigned char>(e);
-        if (px1 && py0) list[1][n1 + __popc(m1 & lt)] = static_cast<unsigned char>(e);
-        if (px0 && py1) list[2][n2 + __popc(m2 & lt)] = static_cast<unsigned char>(e);
-        if (px1 && py1) list[3][n3 + __popc(m3 & lt)] = static_cast<unsigned char>(e);
-        n0 += __popc(m0); n1 += __popc(m1); n2 += __popc(m2); n3 += __popc(m3);
+    bool px0 = false, px1 = false, py0 = false, py1 = false;
+    if (unsigned(lane) < m && unsigned(lane) < limit) {
+        const float4 q = r0[lane];
+        const float2 ext = unpack_extent(q.z);
+        const float xl = q.x - ext.x, xh = q.x + ext.x, yl = q.y - ext.y, yh = q.y + ext.y;
+        px0 = (xh >= wx0) && (xl <= wx0 + 3.0f);
+        px1 = (xh >= wx0 + 4.0f) && (xl <= wx0 + 7.0f);
+        py0 = (yh >= wy0) && (yl <= wy0 + 1.0f);
+        py1 = (yh >= wy0 + 2.0f) && (yl <= wy0 + 3.0f);
     }
+    const unsigned int m0 = __ballot_sync(kFull, px0 && py0);
+    const unsigned int m1 = __ballot_sync(kFull, px1 && py0);
+    const unsigned int m2 = __ballot_sync(kFull, px0 && py1);
+    const unsigned int m3 = __ballot_sync(kFull, px1 && py1);
+    if (px0 && py0) list[0][__popc(m0 & lt)] = static_cast<unsigned char>(lane);
+    if (px1 && py0) list[1][__popc(m1 & lt)] = static_cast<unsigned char>(lane);
+    if (px0 && py1) list[2][__popc(m2 & lt)] = static_cast<unsigned char>(lane);
+    if (px1 && py1) list[3][__popc(m3 & lt)] = static_cast<unsigned char>(lane);
     __syncwarp();
-    return make_uint4(n0, n1, n2, n3);
+    return make_uint4(__popc(m0), __popc(m1), __popc(m2), __popc(m3));
+}
+
+// Per-warp TMA ring: `issued` / `consumed` count batches over the whole kernel (stage = k % kStages,
+// parity = (k / kStages) & 1), so the mbarriers never need re-initialisation between work items.
+template <typename Smem>
+__device__ __forceinline__ void ring_issue(Smem& sm, unsigned int issued, const float4* g0, const float4* g1,
+                                           const float4* g2, unsigned int m, int lane) {
+    if (lane == 0) {
+        const int s = issued % kStages;
+        const uint32_t bytes = m * 16u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the slot are done
+        mbar_arrive_expect_tx(&sm.full[s], 3u * bytes);
+        tma_load_1d(sm.r0[s], g0, bytes, &sm.full[s]);
+        tma_load_1d(sm.r1[s], g1, bytes, &sm.full[s]);
+        tma_load_1d(sm.r2[s], g2, bytes, &sm.full[s]);
+    }
+}
+
+// Pops one work item for the calling warp: (chunk-local tile index, pixel block) or 0xffffffff when the queue is empty.
+__device__ __forceinline__ unsigned int pop_item(unsigned int* cursor, unsigned int n_items, int lane) {
+    unsigned int w = 0;
+    if (lane == 0) w = atomicAdd(cursor, 1u);
+    w = __shfl_sync(kFull, w, 0);
+    return w < n_items ? w : 0xffffffffu;
 }
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -153,211 +173,153 @@ struct FwdArgs {
     int clamp_color;
 };
 
-using FwdSmem = BlendSmem<1>;
-using BwdSmem = BlendSmem<2>;
+using FwdSmem = WarpSmem<1, kSlots>;
+using BwdSmem = WarpSmem<3, kBwdSlots>;
 
-__global__ void __launch_bounds__(kBlendThreads) blend_forward_kernel(FwdArgs a) {
+#ifndef SGR_FWD_MIN_CTAS
+#define SGR_FWD_MIN_CTAS 2
+#endif
+#ifndef SGR_BWD_MIN_CTAS
+#define SGR_BWD_MIN_CTAS 2
+#endif
+__global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward_kernel(FwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool is_producer = warp == kConsumerWarps;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    FwdSmem& sm = reinterpret_cast<FwdSmem*>(smem_raw)[warp];
     const size_t P = size_t(a.g.H) * a.g.W;
     const float bg0 = a.bg[0], bg1 = a.bg[1], bg2 = a.bg[2];
-    const unsigned int n_blend = a.wc->n_blend, n_empty = a.wc->n_empty;
-
-    // ---------------- tiles with instances
-    unsigned long long t_begin = 0;
-    size_t timed_tile = 0;
-    for (bool first_tile = true;; first_tile = false) {
-        __syncthreads();                         // previous tile fully retired; no bulk copy in flight
-        if (tid == 0) {
-            const unsigned long long now = global_timer_ns();
-            if (!first_tile) a.tile_time[timed_tile] = make_uint2((unsigned int)t_begin, (unsigned int)(now - t_begin));
-            t_begin = now;
-            const unsigned int w = atomicAdd(&a.wc->blend_cursor, 1u);
-            sm.work = (w < n_blend) ? a.work_blend[w] : 0xffffffffu;
-            sm.warps_done = 0;
+    const unsigned int n_items = a.wc->n_blend * kBlocksPerTile, n_empty_items = a.wc->n_empty * kBlocksPerTile;
+    if (lane == 0) {
 #pragma unroll
-            for (int s = 0; s < kStages; ++s) {
-                if (!first_tile) { mbar_inval(&sm.full[s]); mbar_inval(&sm.empty[s]); }
-                mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], kConsumerWarps);
-            }
-            fence_barrier_init();
-        }
-        __syncthreads();
-        const unsigned int tile_local = sm.work;
-        if (tile_local == 0xffffffffu) break;
+        for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    const int qsel = ((lane >> 2) & 1) | ((lane >> 3) & 2);        // 4x2 pixel quarter of this lane: x half | 2 * y half
+    const unsigned int qmask = 0x00000f0fu << ((lane & 4) | (lane & 16));   // the quarter's 8 lanes
+    float (*stash)[32] = sm.stash[0];
+    const unsigned char* mylist = sm.list[qsel];
+    unsigned int issued = 0, consumed = 0;       // ring counters (warp-uniform)
+
+    // ---------------- blocks of tiles with instances
+    for (;;) {
+        const unsigned int item = pop_item(&a.wc->blend_cursor, n_items, lane);
+        if (item == 0xffffffffu) break;
+        const unsigned int tile_local = a.work_blend[item / kBlocksPerTile];
+        const int blk = item % kBlocksPerTile;
         const int rl = tile_local / a.g.num_tiles;
         const int tile = tile_local - rl * a.g.num_tiles;
         const int r = a.render_base + rl;
         const size_t tg = size_t(r) * a.g.num_tiles + tile;
-        timed_tile = tg;
         const unsigned int n = a.tile_cnt[tg];
         const size_t off = a.tile_off[tg];
-        const unsigned int nchunks = (n + kChunk - 1) / kChunk;
-
-        if (is_producer) {
-            if (lane == 0) {
-                unsigned int issued = 0;
-                for (unsigned int c = 0; c < nchunks; ++c) {
-                    const int s = c % kStages;
-                    if (c >= kStages) {
-                        const uint32_t par = ((c / kStages) - 1) & 1;
-                        bool stop = false;
-                        while (!mbar_try_wait(&sm.empty[s], par)) {
-                            if (*reinterpret_cast<volatile unsigned int*>(&sm.warps_done) == kConsumerWarps) { stop = true; break; }
-                        }
-                        if (stop) break;
-                    }
-                    if (*reinterpret_cast<volatile unsigned int*>(&sm.warps_done) == kConsumerWarps) break;
-                    const unsigned int m = min(unsigned(kChunk), n - c * kChunk);
-                    const uint32_t bytes = m * 16u;
-                    mbar_arrive_expect_tx(&sm.full[s], 3u * bytes);
-                    tma_load_1d(sm.r0[s], a.rec0 + off + size_t(c) * kChunk, bytes, &sm.full[s]);
-                    tma_load_1d(sm.r1[s], a.rec1 + off + size_t(c) * kChunk, bytes, &sm.full[s]);
-                    tma_load_1d(sm.r2[s], a.rec2 + off + size_t(c) * kChunk, bytes, &sm.full[s]);
-                    issued = c + 1;
-                }
-                // drain: every issued copy must have landed before the barriers are re-initialised
-                const unsigned int first = issued > unsigned(kStages) ? issued - kStages : 0u;
-                for (unsigned int c = first; c < issued; ++c) mbar_wait(&sm.full[c % kStages], (c / kStages) & 1);
-            }
-            continue;
-        }
-
-        // ---- consumer warp: 8x4 pixel block
+        const unsigned int nb = (n + kBatch - 1) / kBatch;
         const int tx = tile % a.g.tiles_x, ty = tile / a.g.tiles_x;
-        const int bx0 = tx * kTile + (warp & 1) * kBlockW, by0 = ty * kTile + (warp >> 1) * kBlockH;
+        const int bx0 = tx * kTile + (blk & 1) * kBlockW, by0 = ty * kTile + (blk >> 1) * kBlockH;
+        if (bx0 >= a.g.W || by0 >= a.g.H) continue;                 // block entirely outside the image
+        const unsigned long long t_begin = global_timer_ns();
         const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
         const bool inside = px < a.g.W && py < a.g.H;
         const float pxf = float(px), pyf = float(py);
         const float wx0 = float(bx0), wy0 = float(by0);
-        const int qsel = ((lane >> 2) & 1) | ((lane >> 3) & 2);        // 4x2 pixel quarter of this lane: x half | 2 * y half
-        const unsigned int qmask = 0x00000f0fu << ((lane & 4) | (lane & 16));   // the quarter's 8 lanes
-        float (*stash)[32] = sm.stash[warp][0];
-        unsigned char (*mylists)[kChunk] = sm.list[warp];
-        const unsigned char* mylist = sm.list[warp][qsel];
+        const float4 *g0 = a.rec0 + off, *g1 = a.rec1 + off, *g2 = a.rec2 + off;
+
         float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, D = 0.0f, Wt = 0.0f;
         unsigned int last = 0;
         bool done = !inside;
-        bool warp_done = __all_sync(kFull, done);
-        if (warp_done && lane == 0) atomicAdd(&sm.warps_done, 1u);
-#ifdef SGR_PROFILE_WARPS
-        long long pf_wait = 0, pf_cull = 0, pf_a = 0, pf_b = 0, pf_t0 = clock64(), pf_t;
-        int pf_trips = 0, pf_passes = 0;
-#define PF_MARK(acc) do { long long now__ = clock64(); acc += now__ - pf_t; pf_t = now__; } while (0)
-#else
-#define PF_MARK(acc) do {} while (0)
-#endif
-        for (unsigned int c = 0; c < nchunks; ++c) {
-            const int s = c % kStages;
-            const uint32_t par = (c / kStages) & 1;
-            if (warp_done) {
-                // keep the ring turning for the other warps; leave as soon as every warp is done
-                bool all_done = false;
-                while (!mbar_try_wait(&sm.full[s], par)) {
-                    if (*reinterpret_cast<volatile unsigned int*>(&sm.warps_done) == kConsumerWarps) { all_done = true; break; }
-                }
-                if (all_done) break;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.empty[s]);
-                continue;
+        unsigned int b_issued = 0;
+        while (b_issued < nb && b_issued < unsigned(kStages - 1)) {
+            ring_issue(sm, issued, g0 + b_issued * kBatch, g1 + b_issued * kBatch, g2 + b_issued * kBatch,
+                       min(unsigned(kBatch), n - b_issued * kBatch), lane);
+            ++issued; ++b_issued;
+        }
+        for (unsigned int b = 0; b < nb; ++b) {
+            if (b_issued < nb) {                 // refill the slot consumed in the previous iteration
+                ring_issue(sm, issued, g0 + b_issued * kBatch, g1 + b_issued * kBatch, g2 + b_issued * kBatch,
+                           min(unsigned(kBatch), n - b_issued * kBatch), lane);
+                ++issued; ++b_issued;
             }
-#ifdef SGR_PROFILE_WARPS
-            pf_t = clock64();
-#endif
-            mbar_wait(&sm.full[s], par);
-            PF_MARK(pf_wait);
-            const unsigned int m = min(unsigned(kChunk), n - c * kChunk);
-            const unsigned int cbase = c * kChunk;
+            const int s = consumed % kStages;
+            mbar_wait(&sm.full[s], (consumed / kStages) & 1);
+            ++consumed;
+            const unsigned int m = min(unsigned(kBatch), n - b * kBatch);
+            const unsigned int cbase = b * kBatch;
             const float4* r0 = sm.r0[s];
             const float4* r1 = sm.r1[s];
             const float4* r2 = sm.r2[s];
-            {
-                const uint4 cnt = cull_chunk(r0, m, m, wx0, wy0, mylists, lane);
-                // quarters whose 8 pixels are all finished need no further evaluation
-                const unsigned int dmask = __ballot_sync(kFull, done);
-                const unsigned int my_n = ((dmask & qmask) == qmask) ? 0u : (qsel == 0 ? cnt.x : qsel == 1 ? cnt.y : qsel == 2 ? cnt.z : cnt.w);
-                const int total = int(__reduce_max_sync(kFull, my_n));
-                PF_MARK(pf_cull);
-                for (int base = 0; base < total; base += kSlots) {
-                    const int trips = min(kSlots, total - base);
-                    // ---- phase A: alpha of the next `trips` survivors of this lane's quarter.  Trips are independent;
-                    // blocks of four are written load-first so the compiler interleaves the four dependent chains.
-                    for (int t0 = 0; t0 < trips; t0 += 4) {
-                        const unsigned int packed = *reinterpret_cast<const unsigned int*>(mylist + base + t0);
-                        float4 q0[4], q1[4];
-                        bool has[4];
+            const uint4 cnt = cull_batch(r0, m, m, wx0, wy0, sm.list, lane);
+            // quarters whose 8 pixels are all finished need no further evaluation
+            const unsigned int dmask = __ballot_sync(kFull, done);
+            const unsigned int my_n = ((dmask & qmask) == qmask) ? 0u : (qsel == 0 ? cnt.x : qsel == 1 ? cnt.y : qsel == 2 ? cnt.z : cnt.w);
+            const int total = int(__reduce_max_sync(kFull, my_n));
+            for (int base = 0; base < total; base += kSlots) {
+                const int trips = min(kSlots, total - base);
+                // ---- phase A: alpha of the next `trips` survivors of this lane's quarter.  Trips are independent;
+                // blocks of four are written load-first so the compiler interleaves the four dependent chains.
+                for (int t0 = 0; t0 < trips; t0 += 4) {
+                    const unsigned int packed = *reinterpret_cast<const unsigned int*>(mylist + base + t0);
+                    float4 q0[4], q1[4];
+                    bool has[4];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            has[u] = unsigned(base + t0 + u) < my_n;
-                            const unsigned int j = has[u] ? ((packed >> (8 * u)) & 0xffu) : 0u;
-                            q0[u] = r0[j];
-                            q1[u] = r1[j];
-                        }
-                        float al[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float dx = q0[u].x - pxf, dy = q0[u].y - pyf;
-                            const float power = gauss_power(q1[u].x, q1[u].y, q1[u].z, dx, dy);
-                            const bool valid = has[u] && !(power > 0.0f) && !(power < q0[u].w);
-                            const float alpha = fminf(kAlphaMax, q1[u].w * exp_core(valid ? power : 0.0f));
-                            al[u] = valid ? alpha : 0.0f;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) stash[t0 + u][lane] = al[u];
+                    for (int u = 0; u < 4; ++u) {
+                        has[u] = unsigned(base + t0 + u) < my_n;
+                        const unsigned int j = has[u] ? ((packed >> (8 * u)) & 0xffu) : 0u;
+                        q0[u] = r0[j];
+                        q1[u] = r1[j];
                     }
-                    __syncwarp();
-#ifdef SGR_PROFILE_WARPS
-                    pf_trips += trips; ++pf_passes;
-#endif
-                    PF_MARK(pf_a);
-                    // ---- phase B: front-to-back compositing (the sequential part), predicated, loads hoisted
-                    for (int t0 = 0; t0 < trips; t0 += 4) {
-                        const unsigned int packed = *reinterpret_cast<const unsigned int*>(mylist + base + t0);
-                        float al[4];
-                        float4 q2[4];
-                        unsigned int idx[4];
+                    float al[4];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const unsigned int j = (unsigned(base + t0 + u) < my_n) ? ((packed >> (8 * u)) & 0xffu) : 0u;
-                            al[u] = stash[t0 + u][lane];
-                            q2[u] = r2[j];
-                            idx[u] = cbase + j + 1;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const bool ok = !done && !(al[u] < kAlphaMin);
-                            const float test_T = T * (1.0f - al[u]);
-                            const bool stop = ok && (test_T < kTMin);
-                            const bool blend = ok && !stop;
-                            const float w0 = q2[u].x * al[u], w1 = q2[u].y * al[u], w2 = q2[u].z * al[u], w3 = q2[u].w * al[u];
-                            C0 = blend ? C0 + w0 * T : C0;
-                            C1 = blend ? C1 + w1 * T : C1;
-                            C2 = blend ? C2 + w2 * T : C2;
-                            Wt = blend ? Wt + al[u] * T : Wt;
-                            D = blend ? D + w3 * T : D;
-                            T = blend ? test_T : T;
-                            last = blend ? idx[u] : last;
-                            done = done || stop;
-                        }
+                    for (int u = 0; u < 4; ++u) {
+                        const float dx = q0[u].x - pxf, dy = q0[u].y - pyf;
+                        const float power = gauss_power(q1[u].x, q1[u].y, q1[u].z, dx, dy);
+                        const bool valid = has[u] && !(power > 0.0f) && !(power < q0[u].w);
+                        const float alpha = fminf(kAlphaMax, q1[u].w * exp_core(valid ? power : 0.0f));
+                        al[u] = valid ? alpha : 0.0f;
                     }
-                    __syncwarp();
-                    PF_MARK(pf_b);
-                    if (__all_sync(kFull, done)) { warp_done = true; break; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) stash[t0 + u][lane] = al[u];
                 }
+                __syncwarp();
+                // ---- phase B: front-to-back compositing (the sequential part), predicated, loads hoisted
+                for (int t0 = 0; t0 < trips; t0 += 4) {
+                    const unsigned int packed = *reinterpret_cast<const unsigned int*>(mylist + base + t0);
+                    float al[4];
+                    float4 q2[4];
+                    unsigned int idx[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const unsigned int j = (unsigned(base + t0 + u) < my_n) ? ((packed >> (8 * u)) & 0xffu) : 0u;
+                        al[u] = stash[t0 + u][lane];
+                        q2[u] = r2[j];
+                        idx[u] = cbase + j + 1;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const bool ok = !done && !(al[u] < kAlphaMin);
+                        const float test_T = __fmaf_rn(-al[u], T, T);
+                        const bool stop = ok && (test_T < kTMin);
+                        const bool blend = ok && !stop;
+                        const float w = blend ? al[u] * T : 0.0f;      // adding c * 0 leaves the sums bit-unchanged
+                        C0 = __fmaf_rn(q2[u].x, w, C0);
+                        C1 = __fmaf_rn(q2[u].y, w, C1);
+                        C2 = __fmaf_rn(q2[u].z, w, C2);
+                        Wt += w;
+                        D = __fmaf_rn(q2[u].w, w, D);
+                        T = blend ? test_T : T;
+                        last = blend ? idx[u] : last;
+                        done = done || stop;
+                    }
+                }
+                __syncwarp();
             }
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&sm.empty[s]);
-                if (warp_done) atomicAdd(&sm.warps_done, 1u);
-            }
+            if (__all_sync(kFull, done)) break;
         }
-#ifdef SGR_PROFILE_WARPS
-        if (lane == 0 && n > 8000)
-            printf("tile r%d t%d n=%u warp %d: total %lld wait %lld cull %lld A %lld B %lld trips %d passes %d done=%d\n", r, tile,
-                   n, warp, clock64() - pf_t0, pf_wait, pf_cull, pf_a, pf_b, pf_trips, pf_passes, int(warp_done));
-#endif
+        // drain: copies already in flight must land before their slots are reused by the next item
+        while (consumed < issued) {
+            mbar_wait(&sm.full[consumed % kStages], (consumed / kStages) & 1);
+            ++consumed;
+        }
+        __syncwarp();
         if (inside) {
             const size_t pix = size_t(py) * a.g.W + px;
             float c0 = C0 + T * bg0, c1 = C1 + T * bg1, c2 = C2 + T * bg2;
@@ -370,26 +332,26 @@ __global__ void __launch_bounds__(kBlendThreads) blend_forward_kernel(FwdArgs a)
             a.out_alpha[size_t(r) * P + pix] = Wt;
             a.n_contrib[size_t(r) * P + pix] = last;
         }
+        if (lane == 0) {                         // diagnostics: start of block 0, duration of the slowest block
+            const unsigned long long now = global_timer_ns();
+            if (blk == 0) a.tile_time[tg].x = (unsigned int)t_begin;
+            atomicMax(&a.tile_time[tg].y, (unsigned int)(now - t_begin));
+        }
     }
 
-    // ---------------- tiles without instances: background only
+    // ---------------- blocks of tiles without instances: background only
     float e0 = bg0, e1 = bg1, e2 = bg2;
     if (a.clamp_color) { e0 = fminf(fmaxf(e0, 0.0f), 1.0f); e1 = fminf(fmaxf(e1, 0.0f), 1.0f); e2 = fminf(fmaxf(e2, 0.0f), 1.0f); }
     for (;;) {
-        __syncthreads();
-        if (tid == 0) {
-            const unsigned int w = atomicAdd(&a.wc->empty_cursor, 1u);
-            sm.work = (w < n_empty) ? a.work_empty[w] : 0xffffffffu;
-        }
-        __syncthreads();
-        const unsigned int tile_local = sm.work;
-        if (tile_local == 0xffffffffu) break;
-        if (tid >= kTilePixels) continue;
+        const unsigned int item = pop_item(&a.wc->empty_cursor, n_empty_items, lane);
+        if (item == 0xffffffffu) break;
+        const unsigned int tile_local = a.work_empty[item / kBlocksPerTile];
+        const int blk = item % kBlocksPerTile;
         const int rl = tile_local / a.g.num_tiles;
         const int tile = tile_local - rl * a.g.num_tiles;
         const int r = a.render_base + rl;
         const int tx = tile % a.g.tiles_x, ty = tile / a.g.tiles_x;
-        const int px = tx * kTile + (tid & 15), py = ty * kTile + (tid >> 4);
+        const int px = tx * kTile + (blk & 1) * kBlockW + (lane & 7), py = ty * kTile + (blk >> 1) * kBlockH + (lane >> 3);
         if (px < a.g.W && py < a.g.H) {
             const size_t pix = size_t(py) * a.g.W + px;
             float* oc = a.out_color + size_t(r) * 3 * P;
@@ -418,46 +380,50 @@ struct BwdArgs {
     WorkCounts* wc;
 };
 
-// Chunks are walked from the back of the list; chunk c of the walk is list chunk (nchunks - 1 - c).
+// Batches are walked from the back of the (truncated) list: the block replays entries [0, wmax), wmax = the largest
+// n_contrib of its 32 pixels.
 template <bool kDepthAlphaGrads>
-__global__ void __launch_bounds__(kBlendThreads) blend_backward_kernel(BwdArgs a) {
+__global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backward_kernel(BwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool is_producer = warp == kConsumerWarps;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    BwdSmem& sm = reinterpret_cast<BwdSmem*>(smem_raw)[warp];
     const size_t P = size_t(a.g.H) * a.g.W;
     const float bg0 = a.bg[0], bg1 = a.bg[1], bg2 = a.bg[2];
-    const unsigned int n_blend = a.wc->n_blend;
+    const unsigned int n_items = a.wc->n_blend * kBlocksPerTile;
     const float ddelx_dx = 0.5f * float(a.g.W), ddely_dy = 0.5f * float(a.g.H);
-
-    for (bool first_tile = true;; first_tile = false) {
-        __syncthreads();
-        if (tid == 0) {
-            const unsigned int w = atomicAdd(&a.wc->blend_cursor, 1u);
-            sm.work = (w < n_blend) ? a.work_blend[w] : 0xffffffffu;
-            sm.max_last = 0;
+    if (lane == 0) {
 #pragma unroll
-            for (int s = 0; s < kStages; ++s) {
-                if (!first_tile) { mbar_inval(&sm.full[s]); mbar_inval(&sm.empty[s]); }
-                mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], kConsumerWarps);
-            }
-            fence_barrier_init();
-        }
-        __syncthreads();
-        const unsigned int tile_local = sm.work;
-        if (tile_local == 0xffffffffu) break;
+        for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    const int qsel = ((lane >> 2) & 1) | ((lane >> 3) & 2);        // 4x2 pixel quarter of this lane: x half | 2 * y half
+    float (*stA)[32] = sm.stash[0];             // phase A: alpha; phase B overwrites it with dL/dalpha
+    float (*stW)[32] = sm.stash[1];             // blend weight alpha * T (0 = the pixel did not blend this Gaussian)
+    float (*stG)[32] = sm.stash[2];             // G = exp(power)
+    const unsigned char* mylist = sm.list[qsel];
+    unsigned int issued = 0, consumed = 0;
+    // Stash rows are XOR-swizzled by trip, column = lane ^ swz(t): conflict-free both for lane = pixel (phases A, B)
+    // and for lane = (trip, quarter) pairs reading one pixel of their quarter (phase C).
+    // phase C role of this lane: quarter cq, trip ct of the pass
+    const int cq = lane & 3, ct = lane >> 2;
+    const int cswz = (ct & 3) | ((ct & 4) << 1);
+    const int cpl0 = ((cq & 1) << 2) | ((cq & 2) << 3);           // first pixel lane of quarter cq
+
+    for (;;) {
+        const unsigned int item = pop_item(&a.wc->blend_cursor, n_items, lane);
+        if (item == 0xffffffffu) break;
+        const unsigned int tile_local = a.work_blend[item / kBlocksPerTile];
+        const int blk = item % kBlocksPerTile;
         const int rl = tile_local / a.g.num_tiles;
         const int tile = tile_local - rl * a.g.num_tiles;
         const int r = a.render_base + rl;
         const size_t tg = size_t(r) * a.g.num_tiles + tile;
-        const unsigned int n = a.tile_cnt[tg];
         const size_t off = a.tile_off[tg];
-
-        // per-pixel inputs (consumer threads) and the tile's replay length
         const int tx = tile % a.g.tiles_x, ty = tile / a.g.tiles_x;
-        const int bx0 = tx * kTile + (warp & 1) * kBlockW, by0 = ty * kTile + (warp >> 1) * kBlockH;
+        const int bx0 = tx * kTile + (blk & 1) * kBlockW, by0 = ty * kTile + (blk >> 1) * kBlockH;
         const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
-        const bool inside = !is_producer && px < a.g.W && py < a.g.H;
+        const bool inside = px < a.g.W && py < a.g.H;
         unsigned int last = 0;
         float T_final = 1.0f, dp0 = 0, dp1 = 0, dp2 = 0, ddep = 0, dalp = 0;
         if (inside) {
@@ -471,188 +437,184 @@ __global__ void __launch_bounds__(kBlendThreads) blend_backward_kernel(BwdArgs a
                 if (a.dL_dalpha) dalp = a.dL_dalpha[size_t(r) * P + pix];
             }
         }
-        const unsigned int wmax = __reduce_max_sync(kFull, last);
-        if (lane == 0 && wmax) atomicMax(&sm.max_last, wmax);
-        __syncthreads();
-        const unsigned int n_eff = min(n, sm.max_last);
-        const unsigned int nchunks = (n_eff + kChunk - 1) / kChunk;
-
-        if (is_producer) {
-            if (lane == 0) {
-                for (unsigned int c = 0; c < nchunks; ++c) {
-                    const int s = c % kStages;
-                    if (c >= kStages) mbar_wait(&sm.empty[s], ((c / kStages) - 1) & 1);
-                    const unsigned int lc = nchunks - 1 - c;
-                    const unsigned int m = min(unsigned(kChunk), n_eff - lc * kChunk);
-                    const uint32_t bytes = m * 16u;
-                    mbar_arrive_expect_tx(&sm.full[s], 3u * bytes);
-                    tma_load_1d(sm.r0[s], a.rec0 + off + size_t(lc) * kChunk, bytes, &sm.full[s]);
-                    tma_load_1d(sm.r1[s], a.rec1 + off + size_t(lc) * kChunk, bytes, &sm.full[s]);
-                    tma_load_1d(sm.r2[s], a.rec2 + off + size_t(lc) * kChunk, bytes, &sm.full[s]);
-                    // (Gaussian ids are 4-byte entries at a 4-byte aligned segment start: not TMA-able; the consumers
-                    //  read the id of an entry that contributed straight from global memory.)
-                }
-            }
-            continue;
-        }
-
+        const unsigned int wmax = __reduce_max_sync(kFull, last);   // entries at or beyond it are never replayed
+        if (wmax == 0) continue;
+        sm.dpix[0][lane] = dp0; sm.dpix[1][lane] = dp1; sm.dpix[2][lane] = dp2; sm.dpix[3][lane] = ddep;
+        __syncwarp();
+        const unsigned int nb = (wmax + kBatch - 1) / kBatch;
         const float pxf = float(px), pyf = float(py);
         const float wx0 = float(bx0), wy0 = float(by0);
-        const int qsel = ((lane >> 2) & 1) | ((lane >> 3) & 2);        // 4x2 pixel quarter of this lane: x half | 2 * y half
-        const unsigned int qbase = (lane & 4) | (lane & 16);          // first lane of the quarter
-        const unsigned int qmask = 0x00000f0fu << qbase;              // the quarter's 8 lanes (lane bits 0, 1, 3)
-        unsigned char (*mylists)[kChunk] = sm.list[warp];
-        const unsigned char* mylist = sm.list[warp][qsel];
-        const bool p0 = (lane & 1) != 0, p1 = (lane & 2) != 0, p3 = (lane & 8) != 0;
-        const int comp = (p3 ? 4 : 0) | (p1 ? 2 : 0) | (p0 ? 1 : 0);  // component this lane owns after the butterfly
-        float (*stA)[32] = sm.stash[warp][0];
-        float (*stW)[32] = sm.stash[warp][1];
+        const float4 *g0 = a.rec0 + off, *g1 = a.rec1 + off, *g2 = a.rec2 + off;
         float T = T_final;
         float ar0 = 0, ar1 = 0, ar2 = 0, adr = 0, aar = 0, last_alpha = 0, lc0 = 0, lc1 = 0, lc2 = 0, last_depth = 0;
         const float bg_dot = (bg0 * dp0 + bg1 * dp1) + bg2 * dp2;
         float* acc = a.accum + size_t(rl) * a.g.N;
         const unsigned int* ids = a.sorted_ids + off;
 
-        for (unsigned int c = 0; c < nchunks; ++c) {
-            const int s = c % kStages;
-            mbar_wait(&sm.full[s], (c / kStages) & 1);
-            const unsigned int lcn = nchunks - 1 - c;
-            const unsigned int cbase = lcn * kChunk;
-            const unsigned int m = min(unsigned(kChunk), n_eff - cbase);
+        // walk step k handles list batch (nb - 1 - k)
+        unsigned int b_issued = 0;
+        while (b_issued < nb && b_issued < unsigned(kStages - 1)) {
+            const unsigned int lb = nb - 1 - b_issued;
+            ring_issue(sm, issued, g0 + lb * kBatch, g1 + lb * kBatch, g2 + lb * kBatch,
+                       min(unsigned(kBatch), wmax - lb * kBatch), lane);
+            ++issued; ++b_issued;
+        }
+        for (unsigned int b = 0; b < nb; ++b) {
+            if (b_issued < nb) {
+                const unsigned int lb = nb - 1 - b_issued;
+                ring_issue(sm, issued, g0 + lb * kBatch, g1 + lb * kBatch, g2 + lb * kBatch,
+                           min(unsigned(kBatch), wmax - lb * kBatch), lane);
+                ++issued; ++b_issued;
+            }
+            const int s = consumed % kStages;
+            mbar_wait(&sm.full[s], (consumed / kStages) & 1);
+            ++consumed;
+            const unsigned int cbase = (nb - 1 - b) * kBatch;
+            const unsigned int m = min(unsigned(kBatch), wmax - cbase);
             const float4* r0 = sm.r0[s];
             const float4* r1 = sm.r1[s];
             const float4* r2 = sm.r2[s];
-            if (cbase < wmax) {                               // some pixel of this warp replays entries of the chunk
-                const uint4 cnt = cull_chunk(r0, m, wmax - cbase, wx0, wy0, mylists, lane);
-                const unsigned int my_n = qsel == 0 ? cnt.x : qsel == 1 ? cnt.y : qsel == 2 ? cnt.z : cnt.w;
-                const int total = int(max(max(cnt.x, cnt.y), max(cnt.z, cnt.w)));
-                // trip t of the chunk handles the quarter's survivor number (my_n - 1 - t): back to front
-                for (int base = 0; base < total; base += kSlots) {
-                    const int trips = min(kSlots, total - base);
-                    // ---- phase A: alpha (0 = no blend); load-first blocks of four so the independent chains interleave
-                    for (int t0 = 0; t0 < trips; t0 += 4) {
-                        float4 q0[4], q1[4];
-                        bool has[4];
+            const uint4 cnt = cull_batch(r0, m, m, wx0, wy0, sm.list, lane);
+            const unsigned int my_n = qsel == 0 ? cnt.x : qsel == 1 ? cnt.y : qsel == 2 ? cnt.z : cnt.w;
+            const int total = int(max(max(cnt.x, cnt.y), max(cnt.z, cnt.w)));
+            // trip t of the batch handles the quarter's survivor number (my_n - 1 - t): back to front
+            const float nTb = -T_final * bg_dot;
+            for (int base = 0; base < total; base += kBwdSlots) {
+                const int trips = min(kBwdSlots, total - base);
+                // ---- phase A: alpha (0 = no blend) and G; load-first blocks of four so the chains interleave
+                for (int t0 = 0; t0 < trips; t0 += 4) {
+                    float4 q0[4], q1[4];
+                    bool has[4];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int k = int(my_n) - 1 - (base + t0 + u);
-                            const unsigned int j = k >= 0 ? mylist[k] : 0u;
-                            has[u] = k >= 0 && (cbase + j < last);
-                            q0[u] = r0[j];
-                            q1[u] = r1[j];
-                        }
-                        float al[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float dx = q0[u].x - pxf, dy = q0[u].y - pyf;
-                            const float power = gauss_power(q1[u].x, q1[u].y, q1[u].z, dx, dy);
-                            const bool valid = has[u] && !(power > 0.0f) && !(power < q0[u].w);
-                            const float alpha = fminf(kAlphaMax, q1[u].w * exp_core(valid ? power : 0.0f));
-                            al[u] = (valid && !(alpha < kAlphaMin)) ? alpha : 0.0f;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) stA[t0 + u][lane] = al[u];
-                    }
-                    __syncwarp();
-                    // ---- phase B: the sequential per-pixel recurrences -> dL/dalpha and blend weight per trip
-                    for (int t0 = 0; t0 < trips; t0 += 4) {
-                        float al[4], dl[4], wg[4];
-                        float4 q2[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int k = int(my_n) - 1 - (base + t0 + u);
-                            al[u] = stA[t0 + u][lane];
-                            q2[u] = r2[k >= 0 ? mylist[k] : 0u];
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float alpha = al[u];
-                            float wgt = 0.0f, dL_dal = 0.0f;
-                            if (alpha != 0.0f) {
-                                const float om = 1.0f - alpha;
-                                T = T / om;
-                                wgt = alpha * T;
-                                const float ola = 1.0f - last_alpha;
-                                ar0 = last_alpha * lc0 + ola * ar0; lc0 = q2[u].x;
-                                dL_dal += (q2[u].x - ar0) * dp0;
-                                ar1 = last_alpha * lc1 + ola * ar1; lc1 = q2[u].y;
-                                dL_dal += (q2[u].y - ar1) * dp1;
-                                ar2 = last_alpha * lc2 + ola * ar2; lc2 = q2[u].z;
-                                dL_dal += (q2[u].z - ar2) * dp2;
-                                if (kDepthAlphaGrads) {
-                                    adr = last_alpha * last_depth + ola * adr; last_depth = q2[u].w;
-                                    dL_dal += (q2[u].w - adr) * ddep;
-                                    aar = last_alpha + ola * aar;
-                                    dL_dal += (1.0f - aar) * dalp;
-                                }
-                                dL_dal *= T;
-                                last_alpha = alpha;
-                                dL_dal += (-T_final / om) * bg_dot;
-                            }
-                            dl[u] = dL_dal;
-                            wg[u] = wgt;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            stA[t0 + u][lane] = dl[u];
-                            stW[t0 + u][lane] = wg[u];
-                        }
-                    }
-                    __syncwarp();
-                    // ---- phase C: per-Gaussian partial sums over the quarter's 8 pixels (independent trips)
-                    for (int t = 0; t < trips; ++t) {
-                        const int k = int(my_n) - 1 - (base + t);
+                    for (int u = 0; u < 4; ++u) {
+                        const int k = int(my_n) - 1 - (base + t0 + u);
                         const unsigned int j = k >= 0 ? mylist[k] : 0u;
-                        const float wgt = stW[t][lane];
-                        const float dL_dal = stA[t][lane];
-                        const float4 q0 = r0[j];
-                        const float4 q1 = r1[j];
-                        const bool active = wgt != 0.0f;
-                        const unsigned int act = __ballot_sync(kFull, active);
-                        if (act == 0) continue;
-                        const float dx = q0.x - pxf, dy = q0.y - pyf;
-                        const float power = gauss_power(q1.x, q1.y, q1.z, dx, dy);
-                        const float G = exp_core(active ? power : 0.0f);
-                        const float dL_dG = q1.w * dL_dal;
-                        const float gdx = G * dx, gdy = G * dy;
-                        const float dG_ddelx = -gdx * q1.x - gdy * q1.y;
-                        const float dG_ddely = -gdy * q1.z - gdx * q1.y;
-                        float v0 = active ? dL_dG * dG_ddelx * ddelx_dx : 0.0f;
-                        float v1 = active ? dL_dG * dG_ddely * ddely_dy : 0.0f;
-                        float v2 = active ? -0.5f * gdx * dx * dL_dG : 0.0f;
-                        float v3 = active ? -0.5f * gdx * dy * dL_dG : 0.0f;
-                        float v4 = active ? -0.5f * gdy * dy * dL_dG : 0.0f;
-                        float v5 = active ? G * dL_dal : 0.0f;
-                        float v6 = wgt * dp0, v7 = wgt * dp1, v8 = wgt * dp2, v9 = wgt * ddep;
-                        // transposing butterfly over lane bits 0, 1, 3 for v0..v7
-                        const float b0 = (p0 ? v1 : v0) + __shfl_xor_sync(kFull, p0 ? v0 : v1, 1);
-                        const float b1 = (p0 ? v3 : v2) + __shfl_xor_sync(kFull, p0 ? v2 : v3, 1);
-                        const float b2 = (p0 ? v5 : v4) + __shfl_xor_sync(kFull, p0 ? v4 : v5, 1);
-                        const float b3 = (p0 ? v7 : v6) + __shfl_xor_sync(kFull, p0 ? v6 : v7, 1);
-                        const float c0 = (p1 ? b1 : b0) + __shfl_xor_sync(kFull, p1 ? b0 : b1, 2);
-                        const float c1 = (p1 ? b3 : b2) + __shfl_xor_sync(kFull, p1 ? b2 : b3, 2);
-                        const float d0 = (p3 ? c1 : c0) + __shfl_xor_sync(kFull, p3 ? c0 : c1, 8);
-                        v8 += __shfl_xor_sync(kFull, v8, 1);
-                        v8 += __shfl_xor_sync(kFull, v8, 2);
-                        v8 += __shfl_xor_sync(kFull, v8, 8);
+                        has[u] = k >= 0 && (cbase + j < last);
+                        q0[u] = r0[j];
+                        q1[u] = r1[j];
+                    }
+                    float al[4], gg[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float dx = q0[u].x - pxf, dy = q0[u].y - pyf;
+                        const float power = gauss_power(q1[u].x, q1[u].y, q1[u].z, dx, dy);
+                        const bool valid = has[u] && !(power > 0.0f) && !(power < q0[u].w);
+                        gg[u] = exp_core(valid ? power : 0.0f);
+                        const float alpha = fminf(kAlphaMax, q1[u].w * gg[u]);
+                        al[u] = (valid && !(alpha < kAlphaMin)) ? alpha : 0.0f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int t = t0 + u;
+                        const int col = lane ^ ((t & 3) | ((t & 4) << 1));
+                        stA[t][col] = al[u];
+                        stG[t][col] = gg[u];
+                    }
+                }
+                __syncwarp();
+                // ---- phase B: the sequential per-pixel recurrences -> dL/dalpha and blend weight per trip
+                for (int t0 = 0; t0 < trips; t0 += 4) {
+                    float al[4], dl[4], wg[4];
+                    float4 q2[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int t = t0 + u;
+                        const int k = int(my_n) - 1 - (base + t);
+                        al[u] = stA[t][lane ^ ((t & 3) | ((t & 4) << 1))];
+                        q2[u] = r2[k >= 0 ? mylist[k] : 0u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float alpha = al[u];
+                        const bool on = alpha != 0.0f;
+                        const float inv_om = __frcp_rn(1.0f - alpha);
+                        const float Tn = T * inv_om;
+                        const float ola = 1.0f - last_alpha;
+                        const float n0 = fmaf(last_alpha, lc0, ola * ar0);
+                        const float n1 = fmaf(last_alpha, lc1, ola * ar1);
+                        const float n2 = fmaf(last_alpha, lc2, ola * ar2);
+                        float d = (q2[u].x - n0) * dp0;
+                        d = fmaf(q2[u].y - n1, dp1, d);
+                        d = fmaf(q2[u].z - n2, dp2, d);
+                        float nd = adr, na = aar;
                         if (kDepthAlphaGrads) {
-                            v9 += __shfl_xor_sync(kFull, v9, 1);
-                            v9 += __shfl_xor_sync(kFull, v9, 2);
-                            v9 += __shfl_xor_sync(kFull, v9, 8);
+                            nd = fmaf(last_alpha, last_depth, ola * adr);
+                            d = fmaf(q2[u].w - nd, ddep, d);
+                            na = fmaf(ola, aar, last_alpha);
+                            d = fmaf(1.0f - na, dalp, d);
                         }
-                        if (act & qmask) {
-                            const unsigned int id = __ldg(ids + cbase + j);
-                            if (d0 != 0.0f) atomicAdd(acc + size_t(comp) * a.plane + id, d0);
-                            if (comp == 0 && v8 != 0.0f) atomicAdd(acc + size_t(8) * a.plane + id, v8);
-                            if (kDepthAlphaGrads && comp == 1 && v9 != 0.0f) atomicAdd(acc + size_t(9) * a.plane + id, v9);
+                        d = fmaf(nTb, inv_om, d * Tn);
+                        dl[u] = on ? d : 0.0f;
+                        wg[u] = on ? alpha * Tn : 0.0f;
+                        if (on) {
+                            T = Tn;
+                            ar0 = n0; ar1 = n1; ar2 = n2; lc0 = q2[u].x; lc1 = q2[u].y; lc2 = q2[u].z;
+                            if (kDepthAlphaGrads) { adr = nd; aar = na; last_depth = q2[u].w; }
+                            last_alpha = alpha;
                         }
                     }
-                    __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int t = t0 + u;
+                        const int col = lane ^ ((t & 3) | ((t & 4) << 1));
+                        stA[t][col] = dl[u];
+                        stW[t][col] = wg[u];
+                    }
                 }
+                __syncwarp();
+                // ---- phase C: lane = (trip ct, quarter cq) pair, i.e. one Gaussian of one quarter; it sums the
+                // gradient terms of the quarter's 8 pixels in registers (no shuffles) and issues the atomics
+                {
+                    const unsigned int n_cq = cq == 0 ? cnt.x : cq == 1 ? cnt.y : cq == 2 ? cnt.z : cnt.w;
+                    const int k = int(n_cq) - 1 - (base + ct);
+                    const bool cvalid = ct < trips && k >= 0;
+                    const unsigned int j = cvalid ? sm.list[cq][k] : 0u;
+                    const float4 q0 = r0[j];
+                    const float4 q1 = r1[j];
+                    const float bxq = wx0 + float((cq & 1) * 4), byq = wy0 + float((cq >> 1) * 2);
+                    const float hA2 = 2.0f * q1.x, hC2 = 2.0f * q1.z;
+                    float s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0, s8 = 0, s9 = 0;
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) {
+                        const int pl = cpl0 + (p & 3) + ((p >> 2) << 3);       // pixel lane inside the quarter
+                        const int col = pl ^ cswz;
+                        const float w = stW[ct][col];
+                        const float dal = stA[ct][col];
+                        const float G = stG[ct][col];
+                        const float dx = q0.x - (bxq + float(p & 3)), dy = q0.y - (byq + float(p >> 2));
+                        const float dL_dG = q1.w * dal;
+                        const float gdx = G * dx, gdy = G * dy;
+                        // -gdx*A - gdy*B = 2*gdx*hA + gdy*nB   (rec1 = (-A/2, -B, -C/2, o))
+                        s0 = fmaf(dL_dG, fmaf(hA2, gdx, q1.y * gdy), s0);
+                        s1 = fmaf(dL_dG, fmaf(hC2, gdy, q1.y * gdx), s1);
+                        s2 = fmaf(gdx * dx, dL_dG, s2);
+                        s3 = fmaf(gdx * dy, dL_dG, s3);
+                        s4 = fmaf(gdy * dy, dL_dG, s4);
+                        s5 = fmaf(G, dal, s5);
+                        s6 = fmaf(w, sm.dpix[0][pl], s6);
+                        s7 = fmaf(w, sm.dpix[1][pl], s7);
+                        s8 = fmaf(w, sm.dpix[2][pl], s8);
+                        if (kDepthAlphaGrads) s9 = fmaf(w, sm.dpix[3][pl], s9);
+                    }
+                    if (cvalid) {
+                        const unsigned int id = __ldg(ids + cbase + j);
+                        float* g = acc + id;
+                        if (s0 != 0.0f) atomicAdd(g + 0 * a.plane, s0 * ddelx_dx);
+                        if (s1 != 0.0f) atomicAdd(g + 1 * a.plane, s1 * ddely_dy);
+                        if (s2 != 0.0f) atomicAdd(g + 2 * a.plane, -0.5f * s2);
+                        if (s3 != 0.0f) atomicAdd(g + 3 * a.plane, -0.5f * s3);
+                        if (s4 != 0.0f) atomicAdd(g + 4 * a.plane, -0.5f * s4);
+                        if (s5 != 0.0f) atomicAdd(g + 5 * a.plane, s5);
+                        if (s6 != 0.0f) atomicAdd(g + 6 * a.plane, s6);
+                        if (s7 != 0.0f) atomicAdd(g + 7 * a.plane, s7);
+                        if (s8 != 0.0f) atomicAdd(g + 8 * a.plane, s8);
+                        if (kDepthAlphaGrads && s9 != 0.0f) atomicAdd(g + 9 * a.plane, s9);
+                    }
+                }
+                __syncwarp();
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.empty[s]);
         }
+        __syncwarp();
     }
 }
 
@@ -689,14 +651,15 @@ cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out
     a.out_color = out_color; a.out_depth = out_depth; a.out_alpha = out_alpha;
     a.work_blend = c.work_blend; a.work_empty = c.work_empty; a.wc = c.work_counts;
     a.clamp_color = (c.p->flags & SGR_FLAG_CLAMP_COLOR) ? 1 : 0;
+    constexpr size_t smem = sizeof(FwdSmem) * kWarpsPerCta;
     static int per_sm = 0;
     if (per_sm == 0) {
-        cudaError_t e = prepare_kernel(blend_forward_kernel, sizeof(FwdSmem), &per_sm);
+        cudaError_t e = prepare_kernel(blend_forward_kernel, smem, &per_sm);
         if (e != cudaSuccess) return e;
     }
-    const int total_tiles = c.num_renders * c.g.num_tiles;
-    const int grid = min(num_sms() * per_sm, total_tiles);
-    blend_forward_kernel<<<grid, kBlendThreads, sizeof(FwdSmem), c.stream>>>(a);
+    const long long items = (long long)c.num_renders * c.g.num_tiles * kBlocksPerTile;
+    const int grid = int(min((long long)num_sms() * per_sm, (items + kWarpsPerCta - 1) / kWarpsPerCta));
+    blend_forward_kernel<<<grid, kBlendThreads, smem, c.stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -708,21 +671,23 @@ cudaError_t launch_blend_backward(const ChunkCtx& c, const float* out_alpha, con
     a.n_contrib = c.n_contrib; a.out_alpha = out_alpha; a.dL_dcolor = dL_dcolor; a.dL_ddepth = dL_ddepth;
     a.dL_dalpha = dL_dalpha; a.accum = c.accum; a.plane = size_t(c.num_renders) * c.g.N;
     a.work_blend = c.work_blend; a.wc = c.work_counts;
-    const int total_tiles = c.num_renders * c.g.num_tiles;
+    constexpr size_t smem = sizeof(BwdSmem) * kWarpsPerCta;
+    const long long items = (long long)c.num_renders * c.g.num_tiles * kBlocksPerTile;
+    const long long want = (items + kWarpsPerCta - 1) / kWarpsPerCta;
     if (dL_ddepth || dL_dalpha) {
         static int per_sm = 0;
         if (per_sm == 0) {
-            cudaError_t e = prepare_kernel(blend_backward_kernel<true>, sizeof(BwdSmem), &per_sm);
+            cudaError_t e = prepare_kernel(blend_backward_kernel<true>, smem, &per_sm);
             if (e != cudaSuccess) return e;
         }
-        blend_backward_kernel<true><<<min(num_sms() * per_sm, total_tiles), kBlendThreads, sizeof(BwdSmem), c.stream>>>(a);
+        blend_backward_kernel<true><<<int(min((long long)num_sms() * per_sm, want)), kBlendThreads, smem, c.stream>>>(a);
     } else {
         static int per_sm = 0;
         if (per_sm == 0) {
-            cudaError_t e = prepare_kernel(blend_backward_kernel<false>, sizeof(BwdSmem), &per_sm);
+            cudaError_t e = prepare_kernel(blend_backward_kernel<false>, smem, &per_sm);
             if (e != cudaSuccess) return e;
         }
-        blend_backward_kernel<false><<<min(num_sms() * per_sm, total_tiles), kBlendThreads, sizeof(BwdSmem), c.stream>>>(a);
+        blend_backward_kernel<false><<<int(min((long long)num_sms() * per_sm, want)), kBlendThreads, smem, c.stream>>>(a);
     }
     return cudaGetLastError();
 }

@@ -55,14 +55,15 @@ __global__ void __launch_bounds__(kTilePixels) blend_forward_simple_kernel(Simpl
             if (power > 0.0f) continue;
             const float alpha = fminf(kAlphaMax, q1.w * exp_spec(power));
             if (alpha < kAlphaMin) continue;
-            const float test_T = T * (1.0f - alpha);
+            const float test_T = __fmaf_rn(-alpha, T, T);
             if (test_T < kTMin) { done = true; continue; }
             const float4 q2 = s2[j];
-            C0 += q2.x * alpha * T;
-            C1 += q2.y * alpha * T;
-            C2 += q2.z * alpha * T;
-            Wt += alpha * T;
-            D += q2.w * alpha * T;
+            const float w = alpha * T;
+            C0 = __fmaf_rn(q2.x, w, C0);
+            C1 = __fmaf_rn(q2.y, w, C1);
+            C2 = __fmaf_rn(q2.z, w, C2);
+            Wt += w;
+            D = __fmaf_rn(q2.w, w, D);
             T = test_T;
             last = contributor;
         }
@@ -190,8 +191,9 @@ __global__ void __launch_bounds__(kTilePixels) blend_backward_simple_kernel(Simp
                         dL_dal += (-T_final / (1.0f - alpha)) * bg_dot;
                         const float dL_dG = q1.w * dL_dal;
                         const float gdx = G * dx, gdy = G * dy;
-                        const float dG_ddelx = -gdx * q1.x - gdy * q1.y;
-                        const float dG_ddely = -gdy * q1.z - gdx * q1.y;
+                        // rec1 = (-A/2, -B, -C/2, o):  -gdx*A - gdy*B = 2*gdx*hA + gdy*nB
+                        const float dG_ddelx = 2.0f * gdx * q1.x + gdy * q1.y;
+                        const float dG_ddely = 2.0f * gdy * q1.z + gdx * q1.y;
                         v[0] = dL_dG * dG_ddelx * ddelx_dx;
                         v[1] = dL_dG * dG_ddely * ddely_dy;
                         v[2] = -0.5f * gdx * dx * dL_dG;

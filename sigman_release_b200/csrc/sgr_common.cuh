@@ -136,13 +136,10 @@ __device__ __forceinline__ float exp_spec(float x) {
     return exp_core(x);
 }
 
-// power = -0.5f * (A*dx*dx + C*dy*dy) - B*dx*dy evaluated in source order without contraction
-// (oracle: blend_forward / blend_backward).
-__device__ __forceinline__ float gauss_power(float A, float B, float C, float dx, float dy) {
-    const float t1 = __fmul_rn(__fmul_rn(A, dx), dx);
-    const float t2 = __fmul_rn(__fmul_rn(C, dy), dy);
-    const float t3 = __fmul_rn(__fmul_rn(B, dx), dy);
-    return __fsub_rn(__fmul_rn(-0.5f, __fadd_rn(t1, t2)), t3);
+// power = -1/2 (A dx^2 + C dy^2) - B dx dy in the spec's fixed FMA pattern (oracle: gauss_power), on the pre-scaled
+// conic (hA, nB, hC) = (-A/2, -B, -C/2) that the preprocess kernel stores (exact scalings).
+__device__ __forceinline__ float gauss_power(float hA, float nB, float hC, float dx, float dy) {
+    return __fmaf_rn(dx, __fmul_rn(hA, dx), __fmul_rn(dy, __fmaf_rn(hC, dy, __fmul_rn(nB, dx))));
 }
 
 constexpr float kAlphaMin = 1.0f / 255.0f;

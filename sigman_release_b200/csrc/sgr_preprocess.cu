@@ -171,7 +171,9 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(PreArgs a) {
                 const unsigned int exy = uint32_t(__half_as_ushort(__float2half_ru(ex))) |
                                          (uint32_t(__half_as_ushort(__float2half_ru(ey))) << 16);
                 a.g0[oi] = make_float4(px, py, __uint_as_float(exy), pthr);
-                a.g1[oi] = make_float4(c2.c * det_inv, -c2.b * det_inv, c2.a * det_inv, opac);
+                // rec1 = (-A/2, -B, -C/2, opacity) with conic (A, B, C) = (c, -b, a) / det as in the oracle
+                const float cA = c2.c * det_inv, cB = -c2.b * det_inv, cC = c2.a * det_inv;
+                a.g1[oi] = make_float4(-0.5f * cA, -cB, -0.5f * cC, opac);
                 a.g2[oi] = make_float4(s_col[3 * t], s_col[3 * t + 1], s_col[3 * t + 2], pvz);
                 unsigned int* cnt = a.tile_cnt + size_t(r) * a.g.num_tiles;
                 for (int y = rminy; y < rmaxy; ++y)
