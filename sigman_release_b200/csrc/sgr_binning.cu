@@ -354,16 +354,28 @@ cudaError_t launch_sort_tiles(const ChunkCtx& c) {
         attr_set = true;
     }
     const int total_tiles = c.num_renders * c.g.num_tiles;
-    // big lists first (longest processing time first), one persistent CTA per SM
+    // The few long lists (one 1024-thread CTA each, latency bound) run on a side stream concurrently with the many
+    // short ones: fork after the scatter, join before the blend.
+    static cudaStream_t side = nullptr;
+    static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaError_t e;
+    if (!side) {
+        if ((e = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    if ((e = cudaEventRecord(ev_fork, c.stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(side, ev_fork, 0)) != cudaSuccess) return e;
     a.work = c.work_big;
     a.work_count = &c.work_counts->n_big;
-    sort_big_kernel<<<min(num_sms, total_tiles), kBigSortThreads, big_smem, c.stream>>>(a);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    sort_big_kernel<<<min(num_sms, total_tiles), kBigSortThreads, big_smem, side>>>(a);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(ev_join, side)) != cudaSuccess) return e;
     a.work = c.work_small;
     a.work_count = &c.work_counts->n_small;
     sort_small_kernel<<<min(num_sms * 5, total_tiles), kSmallSortThreads, 0, c.stream>>>(a);
-    return cudaGetLastError();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    return cudaStreamWaitEvent(c.stream, ev_join, 0);
 }
 
 }  // namespace sgr

@@ -88,23 +88,38 @@ struct PreArgs {
 };
 
 constexpr int kPreThreads = 256;
+constexpr int kPreIters = 8;                 // sub-batches of 256 Gaussians per CTA (amortises the histogram flush)
+constexpr int kHistTiles = 4096;             // tiles per render whose counters fit the shared-memory histogram
 
+// Tile counters: the (Gaussian, tile) instances of the CTA's 2048 Gaussians are first counted in shared memory and
+// flushed with one global atomic per touched tile — the dense head / hand tiles otherwise serialise tens of thousands
+// of same-address atomics in L2.
 __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(PreArgs a) {
     __shared__ float s_view[16], s_proj[16];
     __shared__ __align__(16) float s_mean[kPreThreads * 3];
     __shared__ __align__(16) float s_cov[kPreThreads * 6];
     __shared__ __align__(16) float s_col[kPreThreads * 3];
     __shared__ __align__(16) float s_op[kPreThreads];
+    extern __shared__ unsigned int s_hist[];     // [num_tiles] when num_tiles <= kHistTiles
 
     const int rl = blockIdx.y;
     const int r = a.render_base + rl;
     const int b = r / a.g.V;
     const int N = a.g.N;
-    const int i0 = blockIdx.x * kPreThreads;
-    const int nblk = min(kPreThreads, N - i0);
+    const bool use_hist = a.g.num_tiles <= kHistTiles;
     if (threadIdx.x < 16) s_view[threadIdx.x] = __ldg(a.view + size_t(r) * 16 + threadIdx.x);
     else if (threadIdx.x < 32) s_proj[threadIdx.x - 16] = __ldg(a.proj + size_t(r) * 16 + threadIdx.x - 16);
+    if (use_hist)
+        for (int k = threadIdx.x; k < a.g.num_tiles; k += kPreThreads) s_hist[k] = 0;
+    unsigned int* gcnt = a.tile_cnt + size_t(r) * a.g.num_tiles;
+    unsigned int* cnt = use_hist ? s_hist : gcnt;
+
+  for (int it = 0; it < kPreIters; ++it) {
+    const int i0 = (blockIdx.x * kPreIters + it) * kPreThreads;
+    if (i0 >= N) break;
+    const int nblk = min(kPreThreads, N - i0);
     const size_t gbase = size_t(b) * N + i0;
+    __syncthreads();                             // previous sub-batch fully consumed (and s_view / s_hist ready)
     stage_floats(a.means + gbase * 3, s_mean, nblk * 3);
     stage_floats(a.cov + gbase * 6, s_cov, nblk * 6);
     stage_floats(a.colors + gbase * 3, s_col, nblk * 3);
@@ -112,7 +127,7 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(PreArgs a) {
     __syncthreads();
 
     const int t = threadIdx.x;
-    if (t >= nblk) return;
+    if (t >= nblk) continue;
     const int i = i0 + t;
     const size_t oi = size_t(rl) * N + i;          // chunk-local record index
     const int W = a.g.W, H = a.g.H;
@@ -175,7 +190,6 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(PreArgs a) {
                 const float cA = c2.c * det_inv, cB = -c2.b * det_inv, cC = c2.a * det_inv;
                 a.g1[oi] = make_float4(-0.5f * cA, -cB, -0.5f * cC, opac);
                 a.g2[oi] = make_float4(s_col[3 * t], s_col[3 * t + 1], s_col[3 * t + 2], pvz);
-                unsigned int* cnt = a.tile_cnt + size_t(r) * a.g.num_tiles;
                 for (int y = rminy; y < rmaxy; ++y)
                     for (int x = rminx; x < rmaxx; ++x) atomicAdd(cnt + y * gx + x, 1u);
             }
@@ -183,6 +197,14 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(PreArgs a) {
     }
     a.radii[size_t(r) * N + i] = radius_i;
     a.rect[oi] = rect;
+  }
+    if (use_hist) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < a.g.num_tiles; k += kPreThreads) {
+            const unsigned int c = s_hist[k];
+            if (c) atomicAdd(gcnt + k, c);
+        }
+    }
 }
 
 struct ScatterArgs {
@@ -197,25 +219,55 @@ struct ScatterArgs {
 };
 
 // duplicateWithKeys: one (depth bits << 32 | gaussian id) key per covered tile, appended to the tile's segment.
+// A CTA handles kPreIters * 256 Gaussians of one render: it counts its instances per tile in shared memory, reserves a
+// contiguous range per touched tile with ONE global atomic, and then places its keys with shared-memory atomics.
 __global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs a) {
+    extern __shared__ unsigned int s_sc[];       // cnt[num_tiles], base[num_tiles] when num_tiles <= kHistTiles
     if (a.wc->chunk_dropped) return;
     const int rl = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.g.N) return;
-    const size_t oi = size_t(rl) * a.g.N + i;
-    const uint2 rc = a.rect[oi];
-    const int rminx = rc.x & 0xffff, rminy = rc.x >> 16, rmaxx = rc.y & 0xffff, rmaxy = rc.y >> 16;
-    if (rmaxx <= rminx || rmaxy <= rminy) return;
-    const unsigned long long key =
-        (static_cast<unsigned long long>(__float_as_uint(a.g2[oi].w)) << 32) | static_cast<unsigned int>(i);
-    const size_t tb = size_t(a.render_base + rl) * a.g.num_tiles;
-    unsigned int* cur = a.cursor + size_t(rl) * a.g.num_tiles;
-    for (int y = rminy; y < rmaxy; ++y)
-        for (int x = rminx; x < rmaxx; ++x) {
-            const int t = y * a.g.tiles_x + x;
-            const unsigned int slot = atomicAdd(cur + t, 1u);
-            a.keys[size_t(a.tile_off[tb + t]) + slot] = key;
+    const int T = a.g.num_tiles;
+    const bool use_hist = T <= kHistTiles;
+    unsigned int* s_cnt = s_sc;
+    unsigned int* s_base = s_sc + T;
+    const size_t tb = size_t(a.render_base + rl) * T;
+    unsigned int* cur = a.cursor + size_t(rl) * T;
+    const int i_lo = blockIdx.x * kPreIters * 256;
+    if (use_hist) {
+        for (int k = threadIdx.x; k < T; k += 256) s_cnt[k] = 0;
+        __syncthreads();
+        for (int it = 0; it < kPreIters; ++it) {
+            const int i = i_lo + it * 256 + threadIdx.x;
+            if (i >= a.g.N) break;
+            const uint2 rc = a.rect[size_t(rl) * a.g.N + i];
+            const int rminx = rc.x & 0xffff, rminy = rc.x >> 16, rmaxx = rc.y & 0xffff, rmaxy = rc.y >> 16;
+            for (int y = rminy; y < rmaxy; ++y)
+                for (int x = rminx; x < rmaxx; ++x) atomicAdd(&s_cnt[y * a.g.tiles_x + x], 1u);
         }
+        __syncthreads();
+        for (int k = threadIdx.x; k < T; k += 256) {
+            const unsigned int c = s_cnt[k];
+            if (c) s_base[k] = a.tile_off[tb + k] + atomicAdd(cur + k, c);
+            s_cnt[k] = 0;
+        }
+        __syncthreads();
+    }
+    for (int it = 0; it < kPreIters; ++it) {
+        const int i = i_lo + it * 256 + threadIdx.x;
+        if (i >= a.g.N) break;
+        const size_t oi = size_t(rl) * a.g.N + i;
+        const uint2 rc = a.rect[oi];
+        const int rminx = rc.x & 0xffff, rminy = rc.x >> 16, rmaxx = rc.y & 0xffff, rmaxy = rc.y >> 16;
+        if (rmaxx <= rminx || rmaxy <= rminy) continue;
+        const unsigned long long key =
+            (static_cast<unsigned long long>(__float_as_uint(a.g2[oi].w)) << 32) | static_cast<unsigned int>(i);
+        for (int y = rminy; y < rmaxy; ++y)
+            for (int x = rminx; x < rmaxx; ++x) {
+                const int t = y * a.g.tiles_x + x;
+                const size_t slot = use_hist ? size_t(s_base[t]) + atomicAdd(&s_cnt[t], 1u)
+                                             : size_t(a.tile_off[tb + t]) + atomicAdd(cur + t, 1u);
+                a.keys[slot] = key;
+            }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -410,8 +462,10 @@ cudaError_t launch_preprocess(const ChunkCtx& c, int32_t* radii) {
     a.means = c.p->means3D; a.cov = c.p->cov3D; a.colors = c.p->colors; a.opac = c.p->opacities;
     a.view = c.p->viewmatrix; a.proj = c.p->projmatrix;
     a.g0 = c.g0; a.g1 = c.g1; a.g2 = c.g2; a.rect = c.rect; a.radii = radii; a.tile_cnt = c.tile_cnt;
-    dim3 grid((c.g.N + kPreThreads - 1) / kPreThreads, c.num_renders);
-    preprocess_kernel<<<grid, kPreThreads, 0, c.stream>>>(a);
+    const int per_cta = kPreThreads * kPreIters;
+    dim3 grid((c.g.N + per_cta - 1) / per_cta, c.num_renders);
+    const size_t smem = c.g.num_tiles <= kHistTiles ? size_t(c.g.num_tiles) * 4 : 0;
+    preprocess_kernel<<<grid, kPreThreads, smem, c.stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -419,8 +473,10 @@ cudaError_t launch_scatter(const ChunkCtx& c) {
     ScatterArgs a;
     a.g = c.g; a.render_base = c.render_base; a.g2 = c.g2; a.rect = c.rect; a.tile_off = c.tile_off;
     a.cursor = c.cursor; a.keys = c.keys; a.wc = c.work_counts;
-    dim3 grid((c.g.N + 255) / 256, c.num_renders);
-    scatter_kernel<<<grid, 256, 0, c.stream>>>(a);
+    const int per_cta = 256 * kPreIters;
+    dim3 grid((c.g.N + per_cta - 1) / per_cta, c.num_renders);
+    const size_t smem = c.g.num_tiles <= kHistTiles ? size_t(c.g.num_tiles) * 8 : 0;
+    scatter_kernel<<<grid, 256, smem, c.stream>>>(a);
     return cudaGetLastError();
 }
 
