@@ -217,7 +217,8 @@ __device__ __forceinline__ void block_exclusive_scan(unsigned int* hist, unsigne
 // Sorts the n keys of one tile, writes ids + gathered records.  kb: n-element key buffer (shared or global).
 template <int THREADS, int NB>
 __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local, unsigned long long* kb,
-                                              unsigned int* hist, unsigned int* s_warp, unsigned long long* s_red) {
+                                              bool kb_in_rec0, unsigned int* hist, unsigned int* s_warp,
+                                              unsigned long long* s_red) {
     const int t = threadIdx.x;
     const int rl = tile_local / a.num_tiles;
     const size_t tg = size_t(a.render_base) * a.num_tiles + tile_local;      // global tile index
@@ -254,8 +255,12 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
         kb[pos] = key;
     }
     __syncthreads();
-    // 4. exact rank inside the bucket -> final position
+    // 4. exact rank inside the bucket -> final position; the owner of an element immediately gathers its 48-byte
+    //    record into depth order (the stream the blend kernels read).  Unrolled so that several independent
+    //    key -> record -> store chains are in flight per thread (the step is L2-latency bound).
     unsigned int* ids = a.sorted_ids + off;
+    const size_t gb = size_t(rl) * a.N;
+#pragma unroll 4
     for (unsigned int p = t; p < n; p += THREADS) {
         const unsigned long long key = kb[p];
         const unsigned int b = static_cast<unsigned int>((key - mn) >> shift);
@@ -263,18 +268,30 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
         const unsigned int e = hist[b];
         unsigned int cnt = 0;
         for (unsigned int j = s; j < e; ++j) cnt += (kb[j] < key) ? 1u : 0u;
-        ids[s + cnt] = static_cast<unsigned int>(key & 0xffffffffull);
+        const unsigned int id = static_cast<unsigned int>(key & 0xffffffffull);
+        const size_t pos = off + s + cnt;
+        const float4 v0 = __ldg(a.g0 + gb + id);
+        const float4 v1 = __ldg(a.g1 + gb + id);
+        const float4 v2 = __ldg(a.g2 + gb + id);
+        a.sorted_ids[pos] = id;
+        if (!kb_in_rec0) {
+            a.rec0[pos] = v0;
+            a.rec1[pos] = v1;
+            a.rec2[pos] = v2;
+        }
     }
     __syncthreads();
-    // 5. gather the 48-byte records into depth order (the stream the blend kernels read)
-    const size_t gb = size_t(rl) * a.N;
-    for (unsigned int q = t; q < n; q += THREADS) {
-        const unsigned int id = ids[q];
-        a.rec0[off + q] = __ldg(a.g0 + gb + id);
-        a.rec1[off + q] = __ldg(a.g1 + gb + id);
-        a.rec2[off + q] = __ldg(a.g2 + gb + id);
+    if (kb_in_rec0) {
+        // the key buffer lives in the tile's own rec0 segment (lists beyond the shared-memory capacity): records are
+        // gathered in a second sweep once no thread reads the keys any more
+        for (unsigned int q = t; q < n; q += THREADS) {
+            const unsigned int id = ids[q];
+            a.rec0[off + q] = __ldg(a.g0 + gb + id);
+            a.rec1[off + q] = __ldg(a.g1 + gb + id);
+            a.rec2[off + q] = __ldg(a.g2 + gb + id);
+        }
+        __syncthreads();
     }
-    __syncthreads();
 }
 
 __global__ void __launch_bounds__(kSmallSortThreads) sort_small_kernel(SortArgs a) {
@@ -284,7 +301,7 @@ __global__ void __launch_bounds__(kSmallSortThreads) sort_small_kernel(SortArgs 
     __shared__ unsigned long long s_red[2 * (kSmallSortThreads / 32)];
     const unsigned int nw = *a.work_count;
     for (unsigned int w = blockIdx.x; w < nw; w += gridDim.x)
-        sort_one_tile<kSmallSortThreads, kSmallSortBuckets>(a, a.work[w], kb, hist, s_warp, s_red);
+        sort_one_tile<kSmallSortThreads, kSmallSortBuckets>(a, a.work[w], kb, false, hist, s_warp, s_red);
 }
 
 __global__ void __launch_bounds__(kBigSortThreads) sort_big_kernel(SortArgs a) {
@@ -299,10 +316,9 @@ __global__ void __launch_bounds__(kBigSortThreads) sort_big_kernel(SortArgs a) {
         const size_t tg = size_t(a.render_base) * a.num_tiles + tile_local;
         const unsigned int n = a.tile_cnt[tg];
         // lists that do not fit in shared memory borrow the tile's own rec0 segment (16 B/instance, not yet written)
-        unsigned long long* kb = (n <= static_cast<unsigned int>(kBigSortSmemCap))
-                                     ? kb_s
-                                     : reinterpret_cast<unsigned long long*>(a.rec0 + a.tile_off[tg]);
-        sort_one_tile<kBigSortThreads, kBigSortBuckets>(a, tile_local, kb, hist, s_warp, s_red);
+        const bool spill = n > static_cast<unsigned int>(kBigSortSmemCap);
+        unsigned long long* kb = spill ? reinterpret_cast<unsigned long long*>(a.rec0 + a.tile_off[tg]) : kb_s;
+        sort_one_tile<kBigSortThreads, kBigSortBuckets>(a, tile_local, kb, spill, hist, s_warp, s_red);
     }
 }
 

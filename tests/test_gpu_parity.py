@@ -90,11 +90,11 @@ def test_background_and_empty_inputs():
     np.testing.assert_array_equal(color[0, 0, 0].cpu().numpy(), np.ones((H, W), np.float32))
 
 
-def test_long_tile_lists_and_early_termination():
-    """Many opaque Gaussians stacked on a few tiles: lists of thousands of entries (multi-chunk ring, big-tile sort)
-    and per-pixel early termination."""
+@pytest.mark.parametrize("n,min_longest", [(30_000, 4096), (70_000, 26_624)])
+def test_long_tile_lists_and_early_termination(n, min_longest):
+    """Many opaque Gaussians stacked on a few tiles: lists of thousands of entries (multi-batch ring, big-tile sort,
+    and beyond 26,624 entries the sort's key buffer spills out of shared memory) and per-pixel early termination."""
     rng = np.random.default_rng(5)
-    n = 30_000
     xyz = rng.normal(scale=(0.03, 0.03, 0.2), size=(n, 3))
     scale = rng.uniform(0.002, 0.02, (n, 3))
     rot = scenes.quat_to_rotmat(rng.normal(size=(n, 4)))
@@ -107,7 +107,7 @@ def test_long_tile_lists_and_early_termination():
         state, dims = saved_state(out[0])
         ranges, ncon, pl = debug_state(state, 1, 1, n, 96, 96, dims[7], 0)
         b = r.binning()
-        assert int((b["ranges"][:, 1] - b["ranges"][:, 0]).max()) > 4096        # exercises the big-tile sort
+        assert int((b["ranges"][:, 1] - b["ranges"][:, 0]).max()) > min_longest  # exercises the big-tile sort paths
         np.testing.assert_array_equal(pl, b["point_list"])
         np.testing.assert_array_equal(ncon, b["n_contrib"])
 
