@@ -32,14 +32,15 @@
 namespace sgr {
 namespace {
 
-constexpr int kBatch = 32;                     // records per ring stage (one cull: lane = record)
-constexpr int kStages = 3;                     // per-warp TMA ring depth
+constexpr int kBatch = 64;                     // records per ring stage (culled 32 at a time: lane = record)
+constexpr int kFwdStages = 3;                  // per-warp TMA ring depth, forward
+constexpr int kBwdStages = 2;                  // backward (larger stash; keeps two CTAs per SM)
 constexpr int kWarpsPerCta = 8;
 constexpr int kBlendThreads = kWarpsPerCta * 32;
 constexpr int kBlocksPerTile = 8;              // a 16x16 tile = eight 8x4 pixel blocks = eight work items
 constexpr int kBlockW = 8, kBlockH = 4;        // pixel block of one warp (four 4x2 quarters walk separate lists)
 constexpr int kSlots = 16;                     // forward: trips per phase pass (depth of the per-warp stash)
-constexpr int kBwdSlots = 8;                   // backward: 8 trips x 4 quarters = 32 (Gaussian, quarter) pairs per pass
+constexpr int kBwdSlots = 16;                  // backward: trips per phase pass
 constexpr unsigned int kFull = 0xffffffffu;
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -88,15 +89,16 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
-template <int kStashes, int kDepth>
+template <int kStashes, int kDepth, int kNumStages>
 struct WarpSmem {
-    float4 r0[kStages][kBatch];
-    float4 r1[kStages][kBatch];
-    float4 r2[kStages][kBatch];
+    static constexpr int stages = kNumStages;
+    float4 r0[kNumStages][kBatch];
+    float4 r1[kNumStages][kBatch];
+    float4 r2[kNumStages][kBatch];
     float stash[kStashes][kDepth][32];
     float dpix[4][32];                          // backward: dL/dcolor (3) and dL/ddepth of the block's pixels
     unsigned char list[4][kBatch];              // per quarter: batch-local indices of the survivors (ascending)
-    uint64_t full[kStages];
+    uint64_t full[kNumStages];
 };
 
 __device__ __forceinline__ float2 unpack_extent(float packed) {
@@ -105,41 +107,48 @@ __device__ __forceinline__ float2 unpack_extent(float packed) {
                        __half2float(__ushort_as_half(static_cast<unsigned short>(u >> 16))));
 }
 
-// Cull a batch of m <= 32 records against the four 4x2 quarters of the warp's 8x4 block at (wx0, wy0): lane = record,
-// one ballot per quarter, warp-parallel compaction of the survivors' batch-local indices into list[quarter][...]
-// (ascending).  `limit`: records at or beyond it are ignored.  Returns the four survivor counts.
-__device__ __forceinline__ uint4 cull_batch(const float4* r0, unsigned int m, unsigned int limit, float wx0, float wy0,
+// Cull a batch of m <= kBatch records against the four 4x2 quarters of the warp's 8x4 block at (wx0, wy0): 32 records
+// per round (lane = record), one ballot per quarter, warp-parallel compaction of the survivors' batch-local indices
+// into list[quarter][...] (ascending).  Returns the four survivor counts.
+__device__ __forceinline__ uint4 cull_batch(const float4* r0, unsigned int m, float wx0, float wy0,
                                             unsigned char (*list)[kBatch], int lane) {
     const unsigned int lt = (1u << lane) - 1u;
-    bool px0 = false, px1 = false, py0 = false, py1 = false;
-    if (unsigned(lane) < m && unsigned(lane) < limit) {
-        const float4 q = r0[lane];
-        const float2 ext = unpack_extent(q.z);
-        const float xl = q.x - ext.x, xh = q.x + ext.x, yl = q.y - ext.y, yh = q.y + ext.y;
-        px0 = (xh >= wx0) && (xl <= wx0 + 3.0f);
-        px1 = (xh >= wx0 + 4.0f) && (xl <= wx0 + 7.0f);
-        py0 = (yh >= wy0) && (yl <= wy0 + 1.0f);
-        py1 = (yh >= wy0 + 2.0f) && (yl <= wy0 + 3.0f);
+    unsigned int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+#pragma unroll
+    for (unsigned int sub = 0; sub < unsigned(kBatch); sub += 32) {
+        if (sub >= m) break;
+        const unsigned int e = sub + lane;
+        bool px0 = false, px1 = false, py0 = false, py1 = false;
+        if (e < m) {
+            const float4 q = r0[e];
+            const float2 ext = unpack_extent(q.z);
+            const float xl = q.x - ext.x, xh = q.x + ext.x, yl = q.y - ext.y, yh = q.y + ext.y;
+            px0 = (xh >= wx0) && (xl <= wx0 + 3.0f);
+            px1 = (xh >= wx0 + 4.0f) && (xl <= wx0 + 7.0f);
+            py0 = (yh >= wy0) && (yl <= wy0 + 1.0f);
+            py1 = (yh >= wy0 + 2.0f) && (yl <= wy0 + 3.0f);
+        }
+        const unsigned int m0 = __ballot_sync(kFull, px0 && py0);
+        const unsigned int m1 = __ballot_sync(kFull, px1 && py0);
+        const unsigned int m2 = __ballot_sync(kFull, px0 && py1);
+        const unsigned int m3 = __ballot_sync(kFull, px1 && py1);
+        if (px0 && py0) list[0][n0 + __popc(m0 & lt)] = static_cast<unsigned char>(e);
+        if (px1 && py0) list[1][n1 + __popc(m1 & lt)] = static_cast<unsigned char>(e);
+        if (px0 && py1) list[2][n2 + __popc(m2 & lt)] = static_cast<unsigned char>(e);
+        if (px1 && py1) list[3][n3 + __popc(m3 & lt)] = static_cast<unsigned char>(e);
+        n0 += __popc(m0); n1 += __popc(m1); n2 += __popc(m2); n3 += __popc(m3);
     }
-    const unsigned int m0 = __ballot_sync(kFull, px0 && py0);
-    const unsigned int m1 = __ballot_sync(kFull, px1 && py0);
-    const unsigned int m2 = __ballot_sync(kFull, px0 && py1);
-    const unsigned int m3 = __ballot_sync(kFull, px1 && py1);
-    if (px0 && py0) list[0][__popc(m0 & lt)] = static_cast<unsigned char>(lane);
-    if (px1 && py0) list[1][__popc(m1 & lt)] = static_cast<unsigned char>(lane);
-    if (px0 && py1) list[2][__popc(m2 & lt)] = static_cast<unsigned char>(lane);
-    if (px1 && py1) list[3][__popc(m3 & lt)] = static_cast<unsigned char>(lane);
     __syncwarp();
-    return make_uint4(__popc(m0), __popc(m1), __popc(m2), __popc(m3));
+    return make_uint4(n0, n1, n2, n3);
 }
 
-// Per-warp TMA ring: `issued` / `consumed` count batches over the whole kernel (stage = k % kStages,
-// parity = (k / kStages) & 1), so the mbarriers never need re-initialisation between work items.
+// Per-warp TMA ring: `issued` / `consumed` count batches over the whole kernel (stage = k % stages,
+// parity = (k / stages) & 1), so the mbarriers never need re-initialisation between work items.
 template <typename Smem>
 __device__ __forceinline__ void ring_issue(Smem& sm, unsigned int issued, const float4* g0, const float4* g1,
                                            const float4* g2, unsigned int m, int lane) {
     if (lane == 0) {
-        const int s = issued % kStages;
+        const int s = issued % Smem::stages;
         const uint32_t bytes = m * 16u;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the slot are done
         mbar_arrive_expect_tx(&sm.full[s], 3u * bytes);
@@ -173,8 +182,8 @@ struct FwdArgs {
     int clamp_color;
 };
 
-using FwdSmem = WarpSmem<1, kSlots>;
-using BwdSmem = WarpSmem<3, kBwdSlots>;
+using FwdSmem = WarpSmem<1, kSlots, kFwdStages>;
+using BwdSmem = WarpSmem<3, kBwdSlots, kBwdStages>;
 
 #ifndef SGR_FWD_MIN_CTAS
 #define SGR_FWD_MIN_CTAS 2
@@ -191,7 +200,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
     const unsigned int n_items = a.wc->n_blend * kBlocksPerTile, n_empty_items = a.wc->n_empty * kBlocksPerTile;
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
+        for (int s = 0; s < kFwdStages; ++s) mbar_init(&sm.full[s], 1);
         fence_barrier_init();
     }
     __syncwarp();
@@ -228,7 +237,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
         unsigned int last = 0;
         bool done = !inside;
         unsigned int b_issued = 0;
-        while (b_issued < nb && b_issued < unsigned(kStages - 1)) {
+        while (b_issued < nb && b_issued < unsigned(kFwdStages - 1)) {
             ring_issue(sm, issued, g0 + b_issued * kBatch, g1 + b_issued * kBatch, g2 + b_issued * kBatch,
                        min(unsigned(kBatch), n - b_issued * kBatch), lane);
             ++issued; ++b_issued;
@@ -239,15 +248,15 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
                            min(unsigned(kBatch), n - b_issued * kBatch), lane);
                 ++issued; ++b_issued;
             }
-            const int s = consumed % kStages;
-            mbar_wait(&sm.full[s], (consumed / kStages) & 1);
+            const int s = consumed % kFwdStages;
+            mbar_wait(&sm.full[s], (consumed / kFwdStages) & 1);
             ++consumed;
             const unsigned int m = min(unsigned(kBatch), n - b * kBatch);
             const unsigned int cbase = b * kBatch;
             const float4* r0 = sm.r0[s];
             const float4* r1 = sm.r1[s];
             const float4* r2 = sm.r2[s];
-            const uint4 cnt = cull_batch(r0, m, m, wx0, wy0, sm.list, lane);
+            const uint4 cnt = cull_batch(r0, m, wx0, wy0, sm.list, lane);
             // quarters whose 8 pixels are all finished need no further evaluation
             const unsigned int dmask = __ballot_sync(kFull, done);
             const unsigned int my_n = ((dmask & qmask) == qmask) ? 0u : (qsel == 0 ? cnt.x : qsel == 1 ? cnt.y : qsel == 2 ? cnt.z : cnt.w);
@@ -316,7 +325,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
         }
         // drain: copies already in flight must land before their slots are reused by the next item
         while (consumed < issued) {
-            mbar_wait(&sm.full[consumed % kStages], (consumed / kStages) & 1);
+            mbar_wait(&sm.full[consumed % kFwdStages], (consumed / kFwdStages) & 1);
             ++consumed;
         }
         __syncwarp();
@@ -393,7 +402,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
     const float ddelx_dx = 0.5f * float(a.g.W), ddely_dy = 0.5f * float(a.g.H);
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
+        for (int s = 0; s < kBwdStages; ++s) mbar_init(&sm.full[s], 1);
         fence_barrier_init();
     }
     __syncwarp();
@@ -405,10 +414,6 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
     unsigned int issued = 0, consumed = 0;
     // Stash rows are XOR-swizzled by trip, column = lane ^ swz(t): conflict-free both for lane = pixel (phases A, B)
     // and for lane = (trip, quarter) pairs reading one pixel of their quarter (phase C).
-    // phase C role of this lane: quarter cq, trip ct of the pass
-    const int cq = lane & 3, ct = lane >> 2;
-    const int cswz = (ct & 3) | ((ct & 4) << 1);
-    const int cpl0 = ((cq & 1) << 2) | ((cq & 2) << 3);           // first pixel lane of quarter cq
 
     for (;;) {
         const unsigned int item = pop_item(&a.wc->blend_cursor, n_items, lane);
@@ -453,7 +458,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
 
         // walk step k handles list batch (nb - 1 - k)
         unsigned int b_issued = 0;
-        while (b_issued < nb && b_issued < unsigned(kStages - 1)) {
+        while (b_issued < nb && b_issued < unsigned(kBwdStages - 1)) {
             const unsigned int lb = nb - 1 - b_issued;
             ring_issue(sm, issued, g0 + lb * kBatch, g1 + lb * kBatch, g2 + lb * kBatch,
                        min(unsigned(kBatch), wmax - lb * kBatch), lane);
@@ -466,15 +471,15 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
                            min(unsigned(kBatch), wmax - lb * kBatch), lane);
                 ++issued; ++b_issued;
             }
-            const int s = consumed % kStages;
-            mbar_wait(&sm.full[s], (consumed / kStages) & 1);
+            const int s = consumed % kBwdStages;
+            mbar_wait(&sm.full[s], (consumed / kBwdStages) & 1);
             ++consumed;
             const unsigned int cbase = (nb - 1 - b) * kBatch;
             const unsigned int m = min(unsigned(kBatch), wmax - cbase);
             const float4* r0 = sm.r0[s];
             const float4* r1 = sm.r1[s];
             const float4* r2 = sm.r2[s];
-            const uint4 cnt = cull_batch(r0, m, m, wx0, wy0, sm.list, lane);
+            const uint4 cnt = cull_batch(r0, m, wx0, wy0, sm.list, lane);
             const unsigned int my_n = qsel == 0 ? cnt.x : qsel == 1 ? cnt.y : qsel == 2 ? cnt.z : cnt.w;
             const int total = int(max(max(cnt.x, cnt.y), max(cnt.z, cnt.w)));
             // trip t of the batch handles the quarter's survivor number (my_n - 1 - t): back to front
@@ -562,53 +567,64 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
                     }
                 }
                 __syncwarp();
-                // ---- phase C: lane = (trip ct, quarter cq) pair, i.e. one Gaussian of one quarter; it sums the
-                // gradient terms of the quarter's 8 pixels in registers (no shuffles) and issues the atomics
+                // ---- phase C: the roles flip to lane = (trip, quarter) pair, i.e. one Gaussian of one quarter; the
+                // lane sums the gradient terms of the quarter's 8 pixels in registers (no shuffles) and issues the
+                // atomics.  The pass's pairs are enumerated quarter by quarter and taken 32 at a time.
                 {
-                    const unsigned int n_cq = cq == 0 ? cnt.x : cq == 1 ? cnt.y : cq == 2 ? cnt.z : cnt.w;
-                    const int k = int(n_cq) - 1 - (base + ct);
-                    const bool cvalid = ct < trips && k >= 0;
-                    const unsigned int j = cvalid ? sm.list[cq][k] : 0u;
-                    const float4 q0 = r0[j];
-                    const float4 q1 = r1[j];
-                    const float bxq = wx0 + float((cq & 1) * 4), byq = wy0 + float((cq >> 1) * 2);
-                    const float hA2 = 2.0f * q1.x, hC2 = 2.0f * q1.z;
-                    float s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0, s8 = 0, s9 = 0;
+                    const int c0n = min(max(int(cnt.x) - base, 0), kBwdSlots), c1n = min(max(int(cnt.y) - base, 0), kBwdSlots);
+                    const int c2n = min(max(int(cnt.z) - base, 0), kBwdSlots), c3n = min(max(int(cnt.w) - base, 0), kBwdSlots);
+                    const int e1 = c0n + c1n, e2 = e1 + c2n, npairs = e2 + c3n;
+                    for (int pbase = 0; pbase < npairs; pbase += 32) {
+                        const int pi = pbase + lane;
+                        const bool cvalid = pi < npairs;
+                        const int cq = pi < c0n ? 0 : pi < e1 ? 1 : pi < e2 ? 2 : 3;
+                        const int ct = cvalid ? pi - (cq == 0 ? 0 : cq == 1 ? c0n : cq == 2 ? e1 : e2) : 0;
+                        const unsigned int n_cq = cq == 0 ? cnt.x : cq == 1 ? cnt.y : cq == 2 ? cnt.z : cnt.w;
+                        const int k = int(n_cq) - 1 - (base + ct);
+                        const unsigned int j = cvalid ? sm.list[cq][k] : 0u;
+                        const float4 q0 = r0[j];
+                        const float4 q1 = r1[j];
+                        const int cswz = (ct & 3) | ((ct & 4) << 1);
+                        const int cpl0 = ((cq & 1) << 2) | ((cq & 2) << 3);           // first pixel lane of quarter cq
+                        const float bxq = wx0 + float((cq & 1) * 4), byq = wy0 + float((cq >> 1) * 2);
+                        const float hA2 = 2.0f * q1.x, hC2 = 2.0f * q1.z;
+                        float s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0, s8 = 0, s9 = 0;
 #pragma unroll
-                    for (int p = 0; p < 8; ++p) {
-                        const int pl = cpl0 + (p & 3) + ((p >> 2) << 3);       // pixel lane inside the quarter
-                        const int col = pl ^ cswz;
-                        const float w = stW[ct][col];
-                        const float dal = stA[ct][col];
-                        const float G = stG[ct][col];
-                        const float dx = q0.x - (bxq + float(p & 3)), dy = q0.y - (byq + float(p >> 2));
-                        const float dL_dG = q1.w * dal;
-                        const float gdx = G * dx, gdy = G * dy;
-                        // -gdx*A - gdy*B = 2*gdx*hA + gdy*nB   (rec1 = (-A/2, -B, -C/2, o))
-                        s0 = fmaf(dL_dG, fmaf(hA2, gdx, q1.y * gdy), s0);
-                        s1 = fmaf(dL_dG, fmaf(hC2, gdy, q1.y * gdx), s1);
-                        s2 = fmaf(gdx * dx, dL_dG, s2);
-                        s3 = fmaf(gdx * dy, dL_dG, s3);
-                        s4 = fmaf(gdy * dy, dL_dG, s4);
-                        s5 = fmaf(G, dal, s5);
-                        s6 = fmaf(w, sm.dpix[0][pl], s6);
-                        s7 = fmaf(w, sm.dpix[1][pl], s7);
-                        s8 = fmaf(w, sm.dpix[2][pl], s8);
-                        if (kDepthAlphaGrads) s9 = fmaf(w, sm.dpix[3][pl], s9);
-                    }
-                    if (cvalid) {
-                        const unsigned int id = __ldg(ids + cbase + j);
-                        float* g = acc + id;
-                        if (s0 != 0.0f) atomicAdd(g + 0 * a.plane, s0 * ddelx_dx);
-                        if (s1 != 0.0f) atomicAdd(g + 1 * a.plane, s1 * ddely_dy);
-                        if (s2 != 0.0f) atomicAdd(g + 2 * a.plane, -0.5f * s2);
-                        if (s3 != 0.0f) atomicAdd(g + 3 * a.plane, -0.5f * s3);
-                        if (s4 != 0.0f) atomicAdd(g + 4 * a.plane, -0.5f * s4);
-                        if (s5 != 0.0f) atomicAdd(g + 5 * a.plane, s5);
-                        if (s6 != 0.0f) atomicAdd(g + 6 * a.plane, s6);
-                        if (s7 != 0.0f) atomicAdd(g + 7 * a.plane, s7);
-                        if (s8 != 0.0f) atomicAdd(g + 8 * a.plane, s8);
-                        if (kDepthAlphaGrads && s9 != 0.0f) atomicAdd(g + 9 * a.plane, s9);
+                        for (int p = 0; p < 8; ++p) {
+                            const int pl = cpl0 + (p & 3) + ((p >> 2) << 3);       // pixel lane inside the quarter
+                            const int col = pl ^ cswz;
+                            const float w = cvalid ? stW[ct][col] : 0.0f;
+                            const float dal = cvalid ? stA[ct][col] : 0.0f;
+                            const float G = stG[ct][col];
+                            const float dx = q0.x - (bxq + float(p & 3)), dy = q0.y - (byq + float(p >> 2));
+                            const float dL_dG = q1.w * dal;
+                            const float gdx = G * dx, gdy = G * dy;
+                            // -gdx*A - gdy*B = 2*gdx*hA + gdy*nB   (rec1 = (-A/2, -B, -C/2, o))
+                            s0 = fmaf(dL_dG, fmaf(hA2, gdx, q1.y * gdy), s0);
+                            s1 = fmaf(dL_dG, fmaf(hC2, gdy, q1.y * gdx), s1);
+                            s2 = fmaf(gdx * dx, dL_dG, s2);
+                            s3 = fmaf(gdx * dy, dL_dG, s3);
+                            s4 = fmaf(gdy * dy, dL_dG, s4);
+                            s5 = fmaf(G, dal, s5);
+                            s6 = fmaf(w, sm.dpix[0][pl], s6);
+                            s7 = fmaf(w, sm.dpix[1][pl], s7);
+                            s8 = fmaf(w, sm.dpix[2][pl], s8);
+                            if (kDepthAlphaGrads) s9 = fmaf(w, sm.dpix[3][pl], s9);
+                        }
+                        if (cvalid) {
+                            const unsigned int id = __ldg(ids + cbase + j);
+                            float* g = acc + id;
+                            if (s0 != 0.0f) atomicAdd(g + 0 * a.plane, s0 * ddelx_dx);
+                            if (s1 != 0.0f) atomicAdd(g + 1 * a.plane, s1 * ddely_dy);
+                            if (s2 != 0.0f) atomicAdd(g + 2 * a.plane, -0.5f * s2);
+                            if (s3 != 0.0f) atomicAdd(g + 3 * a.plane, -0.5f * s3);
+                            if (s4 != 0.0f) atomicAdd(g + 4 * a.plane, -0.5f * s4);
+                            if (s5 != 0.0f) atomicAdd(g + 5 * a.plane, s5);
+                            if (s6 != 0.0f) atomicAdd(g + 6 * a.plane, s6);
+                            if (s7 != 0.0f) atomicAdd(g + 7 * a.plane, s7);
+                            if (s8 != 0.0f) atomicAdd(g + 8 * a.plane, s8);
+                            if (kDepthAlphaGrads && s9 != 0.0f) atomicAdd(g + 9 * a.plane, s9);
+                        }
                     }
                 }
                 __syncwarp();
