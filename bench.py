@@ -135,10 +135,12 @@ def run_reference(args):
     step = oracle_step_fn(sc, sample_views)
     for _ in range(max(1, min(args.warmup, 2))):
         step()
+    # every step is the same bounded sample; cap the repetitions so that the run ends within a few minutes
+    reps = max(1, min(args.steps, 100))
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(reps):
         step()
-    dt = (time.perf_counter() - t0) / args.steps
+    dt = (time.perf_counter() - t0) / reps
     value = N_GAUSS * sample_views / dt
     cores = oracle.num_threads()
     sample = (f"each step = forward+backward of {sample_views} of the 8 views of the same subject "
@@ -245,6 +247,7 @@ def run_ours(args):
         render_step(d)
     torch.cuda.synchronize()
     sampler.start()
+    time.sleep(0.25)                                          # let the sampler take a first reading under no load
     launches0 = int(L.sgr_launch_count())
     ms_step = timed(lambda: render_step(d), args.steps, 0)
     launches = int(L.sgr_launch_count()) - launches0         # kernels of libsgr_b200.so launched in the timed region
@@ -326,8 +329,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
