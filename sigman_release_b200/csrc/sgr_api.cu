@@ -102,6 +102,8 @@ void fill_ctx(ChunkCtx& c, const SgrProblem& p, void* state, void* scratch, cuda
     c.rec0 = reinterpret_cast<float4*>(s + S.rec0);
     c.rec1 = reinterpret_cast<float4*>(s + S.rec1);
     c.rec2 = reinterpret_cast<float4*>(s + S.rec2);
+    c.ck0 = reinterpret_cast<float4*>(s + S.ck0);
+    c.ck1 = reinterpret_cast<float*>(s + S.ck1);
     c.keys = reinterpret_cast<unsigned long long*>(x + X.keys);
     c.g0 = reinterpret_cast<float4*>(x + X.g0);
     c.g1 = reinterpret_cast<float4*>(x + X.g1);
@@ -112,6 +114,7 @@ void fill_ctx(ChunkCtx& c, const SgrProblem& p, void* state, void* scratch, cuda
     c.work_big = reinterpret_cast<unsigned int*>(x + X.work_big);
     c.work_blend = reinterpret_cast<unsigned int*>(x + X.work_blend);
     c.work_empty = reinterpret_cast<unsigned int*>(x + X.work_empty);
+    c.work_seg = reinterpret_cast<uint2*>(x + X.work_seg);
     c.work_counts = reinterpret_cast<WorkCounts*>(x + X.work_counts);
     c.accum = reinterpret_cast<float*>(x + X.accum);
     c.stream = stream;
@@ -250,7 +253,7 @@ int sgr_backward(const SgrBackwardArgs* args) {
         if (p.flags & SGR_FLAG_SIMPLE_BLEND) {
             SGR_STAGE(kStBlendBwd, launch_blend_backward_simple(c, args->out_alpha, args->dL_dcolor, args->dL_ddepth, args->dL_dalpha));
         } else {
-            SGR_STAGE(kStWorklist, launch_worklist(c));
+            SGR_STAGE(kStWorklist, launch_worklist_segments(c));
             SGR_STAGE(kStBlendBwd, launch_blend_backward(c, args->out_alpha, args->dL_dcolor, args->dL_ddepth, args->dL_dalpha));
         }
         SGR_STAGE(kStPreBwd, launch_preprocess_backward(c, *args));

@@ -146,9 +146,44 @@ __global__ void __launch_bounds__(kScanThreads) worklist_kernel(WorkArgs a) {
     }
 }
 
+// Backward work list: every tile list is cut into segments of kSegment records; items are (tile, segment) pairs
+// ordered by descending size class of the segment length (all full segments first).
+__global__ void __launch_bounds__(kScanThreads) worklist_segments_kernel(WorkArgs a, uint2* work_seg) {
+    __shared__ unsigned int s_hist[kSizeClasses], s_start[kSizeClasses];
+    const int t = threadIdx.x;
+    const int full_class = size_class(kSegment);
+    if (t < kSizeClasses) s_hist[t] = 0;
+    __syncthreads();
+    for (int k = t; k < a.n; k += kScanThreads) {
+        const unsigned int c = a.tile_cnt[k];
+        if (c == 0) continue;
+        const unsigned int nfull = c / kSegment, rem = c - nfull * kSegment;
+        if (nfull) atomicAdd(&s_hist[full_class], nfull);
+        if (rem) atomicAdd(&s_hist[size_class(rem)], 1u);
+    }
+    __syncthreads();
+    if (t == 0) {
+        unsigned int run = 0;
+        for (int c = kSizeClasses - 1; c >= 1; --c) { s_start[c] = run; run += s_hist[c]; }
+        a.wc->n_seg = run;
+        a.wc->seg_cursor = 0;
+    }
+    __syncthreads();
+    for (int k = t; k < a.n; k += kScanThreads) {
+        const unsigned int c = a.tile_cnt[k];
+        if (c == 0) continue;
+        const unsigned int nfull = c / kSegment, rem = c - nfull * kSegment;
+        if (nfull) {
+            const unsigned int pos = atomicAdd(&s_start[full_class], nfull);
+            for (unsigned int s = 0; s < nfull; ++s) work_seg[pos + s] = make_uint2(unsigned(k), s);
+        }
+        if (rem) work_seg[atomicAdd(&s_start[size_class(rem)], 1u)] = make_uint2(unsigned(k), nfull);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ sort
 struct SortArgs {
-    int N, num_tiles, render_base;
+    int N, num_tiles, tiles_x, render_base;
     const unsigned int* tile_off;    // global arrays
     const unsigned int* tile_cnt;
     const unsigned long long* keys;
@@ -260,6 +295,8 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
     //    key -> record -> store chains are in flight per thread (the step is L2-latency bound).
     unsigned int* ids = a.sorted_ids + off;
     const size_t gb = size_t(rl) * a.N;
+    const int tile = tile_local - rl * a.num_tiles;
+    const float X0 = float((tile % a.tiles_x) * kTile), Y0 = float((tile / a.tiles_x) * kTile);
 #pragma unroll 4
     for (unsigned int p = t; p < n; p += THREADS) {
         const unsigned long long key = kb[p];
@@ -270,9 +307,10 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
         for (unsigned int j = s; j < e; ++j) cnt += (kb[j] < key) ? 1u : 0u;
         const unsigned int id = static_cast<unsigned int>(key & 0xffffffffull);
         const size_t pos = off + s + cnt;
-        const float4 v0 = __ldg(a.g0 + gb + id);
+        float4 v0 = __ldg(a.g0 + gb + id);
         const float4 v1 = __ldg(a.g1 + gb + id);
         const float4 v2 = __ldg(a.g2 + gb + id);
+        v0.z = __uint_as_float(quarter_mask(v0.x, v0.y, v0.z, X0, Y0));   // the instance's cull mask for this tile
         a.sorted_ids[pos] = id;
         if (!kb_in_rec0) {
             a.rec0[pos] = v0;
@@ -286,7 +324,9 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
         // gathered in a second sweep once no thread reads the keys any more
         for (unsigned int q = t; q < n; q += THREADS) {
             const unsigned int id = ids[q];
-            a.rec0[off + q] = __ldg(a.g0 + gb + id);
+            float4 v0 = __ldg(a.g0 + gb + id);
+            v0.z = __uint_as_float(quarter_mask(v0.x, v0.y, v0.z, X0, Y0));
+            a.rec0[off + q] = v0;
             a.rec1[off + q] = __ldg(a.g1 + gb + id);
             a.rec2[off + q] = __ldg(a.g2 + gb + id);
         }
@@ -350,9 +390,20 @@ cudaError_t launch_worklist(const ChunkCtx& c) {
     return cudaGetLastError();
 }
 
+cudaError_t launch_worklist_segments(const ChunkCtx& c) {
+    WorkArgs a;
+    a.n = c.num_renders * c.g.num_tiles;
+    a.tile_cnt = c.tile_cnt + size_t(c.render_base) * c.g.num_tiles;
+    a.work_blend = nullptr;
+    a.work_empty = nullptr;
+    a.wc = c.work_counts;
+    worklist_segments_kernel<<<1, kScanThreads, 0, c.stream>>>(a, c.work_seg);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_sort_tiles(const ChunkCtx& c) {
     SortArgs a;
-    a.N = c.g.N; a.num_tiles = c.g.num_tiles; a.render_base = c.render_base;
+    a.N = c.g.N; a.num_tiles = c.g.num_tiles; a.tiles_x = c.g.tiles_x; a.render_base = c.render_base;
     a.tile_off = c.tile_off; a.tile_cnt = c.tile_cnt; a.keys = c.keys; a.sorted_ids = c.sorted_ids;
     a.rec0 = c.rec0; a.rec1 = c.rec1; a.rec2 = c.rec2; a.g0 = c.g0; a.g1 = c.g1; a.g2 = c.g2;
     static int num_sms = 0;

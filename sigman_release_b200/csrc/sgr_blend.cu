@@ -23,8 +23,6 @@
 //
 // Compiled with --fmad=false: the per-pixel expressions are the oracle's (oracle/sgr_oracle.cpp::blend_forward /
 // blend_backward) evaluated in the same order, which makes colour, depth, alpha and n_contrib bit-exact.
-#include <cuda_fp16.h>
-
 #include <cstdio>
 
 #include "sgr_common.cuh"
@@ -83,6 +81,11 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ float rcp_approx(float x) {       // MUFU.RCP, 1 ulp; gradients are compared with a tolerance
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -101,41 +104,29 @@ struct WarpSmem {
     uint64_t full[kNumStages];
 };
 
-__device__ __forceinline__ float2 unpack_extent(float packed) {
-    const unsigned int u = __float_as_uint(packed);
-    return make_float2(__half2float(__ushort_as_half(static_cast<unsigned short>(u & 0xffffu))),
-                       __half2float(__ushort_as_half(static_cast<unsigned short>(u >> 16))));
-}
-
-// Cull a batch of m <= kBatch records against the four 4x2 quarters of the warp's 8x4 block at (wx0, wy0): 32 records
-// per round (lane = record), one ballot per quarter, warp-parallel compaction of the survivors' batch-local indices
-// into list[quarter][...] (ascending).  Returns the four survivor counts.
-__device__ __forceinline__ uint4 cull_batch(const float4* r0, unsigned int m, float wx0, float wy0,
-                                            unsigned char (*list)[kBatch], int lane) {
+// Cull a batch of m <= kBatch records against the four 4x2 quarters of the warp's 8x4 pixel block `blk` of the tile:
+// 32 records per round (lane = record) read their precomputed quarter mask (rec0.z, built once per instance by the
+// tile sort, sgr_common.cuh::quarter_mask), one ballot per quarter, warp-parallel compaction of the survivors'
+// batch-local indices into list[quarter][...] (ascending).  Returns the four survivor counts.
+__device__ __forceinline__ uint4 cull_batch(const float4* r0, unsigned int m, int blk, unsigned char (*list)[kBatch],
+                                            int lane) {
     const unsigned int lt = (1u << lane) - 1u;
+    const unsigned int* words = reinterpret_cast<const unsigned int*>(r0);
     unsigned int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
 #pragma unroll
     for (unsigned int sub = 0; sub < unsigned(kBatch); sub += 32) {
         if (sub >= m) break;
         const unsigned int e = sub + lane;
-        bool px0 = false, px1 = false, py0 = false, py1 = false;
-        if (e < m) {
-            const float4 q = r0[e];
-            const float2 ext = unpack_extent(q.z);
-            const float xl = q.x - ext.x, xh = q.x + ext.x, yl = q.y - ext.y, yh = q.y + ext.y;
-            px0 = (xh >= wx0) && (xl <= wx0 + 3.0f);
-            px1 = (xh >= wx0 + 4.0f) && (xl <= wx0 + 7.0f);
-            py0 = (yh >= wy0) && (yl <= wy0 + 1.0f);
-            py1 = (yh >= wy0 + 2.0f) && (yl <= wy0 + 3.0f);
-        }
-        const unsigned int m0 = __ballot_sync(kFull, px0 && py0);
-        const unsigned int m1 = __ballot_sync(kFull, px1 && py0);
-        const unsigned int m2 = __ballot_sync(kFull, px0 && py1);
-        const unsigned int m3 = __ballot_sync(kFull, px1 && py1);
-        if (px0 && py0) list[0][n0 + __popc(m0 & lt)] = static_cast<unsigned char>(e);
-        if (px1 && py0) list[1][n1 + __popc(m1 & lt)] = static_cast<unsigned char>(e);
-        if (px0 && py1) list[2][n2 + __popc(m2 & lt)] = static_cast<unsigned char>(e);
-        if (px1 && py1) list[3][n3 + __popc(m3 & lt)] = static_cast<unsigned char>(e);
+        const unsigned int bits = (e < m) ? ((words[4 * e + 2] >> (4 * blk)) & 0xfu) : 0u;
+        if (__ballot_sync(kFull, bits != 0u) == 0u) continue;     // no record of the round touches this block
+        const unsigned int m0 = __ballot_sync(kFull, bits & 1u);
+        const unsigned int m1 = __ballot_sync(kFull, bits & 2u);
+        const unsigned int m2 = __ballot_sync(kFull, bits & 4u);
+        const unsigned int m3 = __ballot_sync(kFull, bits & 8u);
+        if (bits & 1u) list[0][n0 + __popc(m0 & lt)] = static_cast<unsigned char>(e);
+        if (bits & 2u) list[1][n1 + __popc(m1 & lt)] = static_cast<unsigned char>(e);
+        if (bits & 4u) list[2][n2 + __popc(m2 & lt)] = static_cast<unsigned char>(e);
+        if (bits & 8u) list[3][n3 + __popc(m3 & lt)] = static_cast<unsigned char>(e);
         n0 += __popc(m0); n1 += __popc(m1); n2 += __popc(m2); n3 += __popc(m3);
     }
     __syncwarp();
@@ -177,6 +168,8 @@ struct FwdArgs {
     unsigned int* n_contrib;
     uint2* tile_time;
     float *out_color, *out_depth, *out_alpha;
+    float4* ck0;                  // per-pixel checkpoints (T, C0, C1, C2) at segment boundaries of long lists
+    float* ck1;                   // ... and D
     const unsigned int *work_blend, *work_empty;
     WorkCounts* wc;
     int clamp_color;
@@ -230,7 +223,6 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
         const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
         const bool inside = px < a.g.W && py < a.g.H;
         const float pxf = float(px), pyf = float(py);
-        const float wx0 = float(bx0), wy0 = float(by0);
         const float4 *g0 = a.rec0 + off, *g1 = a.rec1 + off, *g2 = a.rec2 + off;
 
         float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, D = 0.0f, Wt = 0.0f;
@@ -256,7 +248,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
             const float4* r0 = sm.r0[s];
             const float4* r1 = sm.r1[s];
             const float4* r2 = sm.r2[s];
-            const uint4 cnt = cull_batch(r0, m, wx0, wy0, sm.list, lane);
+            const uint4 cnt = cull_batch(r0, m, blk, sm.list, lane);
             // quarters whose 8 pixels are all finished need no further evaluation
             const unsigned int dmask = __ballot_sync(kFull, done);
             const unsigned int my_n = ((dmask & qmask) == qmask) ? 0u : (qsel == 0 ? cnt.x : qsel == 1 ? cnt.y : qsel == 2 ? cnt.z : cnt.w);
@@ -321,7 +313,18 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
                 }
                 __syncwarp();
             }
+            // lists longer than one backward segment: checkpoint the running state at every segment boundary
+            if (n > unsigned(kSegment) && ((b + 1) * kBatch) % kSegment == 0 && (b + 1) * kBatch < n) {
+                const size_t ci = ((off / (kSegment / 2) + (b + 1) * kBatch / kSegment - 1) * kBlocksPerTile + blk) * 32 + lane;
+                a.ck0[ci] = make_float4(T, C0, C1, C2);
+                a.ck1[ci] = D;
+            }
             if (__all_sync(kFull, done)) break;
+        }
+        if (n > unsigned(kSegment)) {                 // final state, read by the backward's non-final segments
+            const size_t ci = ((off / (kSegment / 2) + (n + kSegment - 1) / kSegment - 1) * kBlocksPerTile + blk) * 32 + lane;
+            a.ck0[ci] = make_float4(T, C0, C1, C2);
+            a.ck1[ci] = D;
         }
         // drain: copies already in flight must land before their slots are reused by the next item
         while (consumed < issued) {
@@ -385,12 +388,19 @@ struct BwdArgs {
     const float *out_alpha, *dL_dcolor, *dL_ddepth, *dL_dalpha;
     float* accum;
     size_t plane;
-    const unsigned int* work_blend;
+    const float4* ck0;            // forward checkpoints (sgr_common.cuh::kSegment)
+    const float* ck1;
+    const uint2* work_seg;        // (chunk-local tile, segment) items, longest first
     WorkCounts* wc;
 };
 
-// Batches are walked from the back of the (truncated) list: the block replays entries [0, wmax), wmax = the largest
-// n_contrib of its 32 pixels.
+// Work item = (tile, segment, 8x4 pixel block): the block replays the list entries [lo, hi) of its segment back to
+// front, lo = segment * kSegment, hi = min(lo + kSegment, wmax), wmax = the largest n_contrib of its 32 pixels.
+// A pixel whose contributors end inside the segment starts from its final state exactly like the sequential
+// algorithm; a pixel that continues behind the segment starts from the forward's checkpoint at the segment end:
+//   T = T_ck * (T_final / T_fin)   (T_final = 1 - alpha_out as in A.5; T_ck / T_fin = the forward's running values)
+//   accumulated colour / depth / alpha behind = (X_fin - X_ck) / T_ck
+// so that the long face / hand lists no longer serialise on one warp.
 template <bool kDepthAlphaGrads>
 __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backward_kernel(BwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -398,7 +408,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
     BwdSmem& sm = reinterpret_cast<BwdSmem*>(smem_raw)[warp];
     const size_t P = size_t(a.g.H) * a.g.W;
     const float bg0 = a.bg[0], bg1 = a.bg[1], bg2 = a.bg[2];
-    const unsigned int n_items = a.wc->n_blend * kBlocksPerTile;
+    const unsigned int n_items = a.wc->n_seg * kBlocksPerTile;
     const float ddelx_dx = 0.5f * float(a.g.W), ddely_dy = 0.5f * float(a.g.H);
     if (lane == 0) {
 #pragma unroll
@@ -416,24 +426,28 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
     // and for lane = (trip, quarter) pairs reading one pixel of their quarter (phase C).
 
     for (;;) {
-        const unsigned int item = pop_item(&a.wc->blend_cursor, n_items, lane);
+        const unsigned int item = pop_item(&a.wc->seg_cursor, n_items, lane);
         if (item == 0xffffffffu) break;
-        const unsigned int tile_local = a.work_blend[item / kBlocksPerTile];
+        const uint2 ws = a.work_seg[item / kBlocksPerTile];
+        const unsigned int tile_local = ws.x;
+        const unsigned int lo = ws.y * unsigned(kSegment);
         const int blk = item % kBlocksPerTile;
         const int rl = tile_local / a.g.num_tiles;
         const int tile = tile_local - rl * a.g.num_tiles;
         const int r = a.render_base + rl;
         const size_t tg = size_t(r) * a.g.num_tiles + tile;
-        const size_t off = a.tile_off[tg];
         const int tx = tile % a.g.tiles_x, ty = tile / a.g.tiles_x;
         const int bx0 = tx * kTile + (blk & 1) * kBlockW, by0 = ty * kTile + (blk >> 1) * kBlockH;
         const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
         const bool inside = px < a.g.W && py < a.g.H;
-        unsigned int last = 0;
+        const size_t pix = size_t(py) * a.g.W + px;
+        const unsigned int last = inside ? a.n_contrib[size_t(r) * P + pix] : 0u;
+        const unsigned int wmax = __reduce_max_sync(kFull, last);   // entries at or beyond it are never replayed
+        if (wmax <= lo) continue;
+        const unsigned int hi = min(lo + unsigned(kSegment), wmax);
+        const size_t off = a.tile_off[tg];
         float T_final = 1.0f, dp0 = 0, dp1 = 0, dp2 = 0, ddep = 0, dalp = 0;
         if (inside) {
-            const size_t pix = size_t(py) * a.g.W + px;
-            last = a.n_contrib[size_t(r) * P + pix];
             T_final = 1.0f - a.out_alpha[size_t(r) * P + pix];
             const float* dc = a.dL_dcolor + size_t(r) * 3 * P;
             dp0 = dc[pix]; dp1 = dc[P + pix]; dp2 = dc[2 * P + pix];
@@ -442,16 +456,28 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
                 if (a.dL_dalpha) dalp = a.dL_dalpha[size_t(r) * P + pix];
             }
         }
-        const unsigned int wmax = __reduce_max_sync(kFull, last);   // entries at or beyond it are never replayed
-        if (wmax == 0) continue;
         sm.dpix[0][lane] = dp0; sm.dpix[1][lane] = dp1; sm.dpix[2][lane] = dp2; sm.dpix[3][lane] = ddep;
         __syncwarp();
-        const unsigned int nb = (wmax + kBatch - 1) / kBatch;
+        const unsigned int nb = (hi - lo + kBatch - 1) / kBatch;
         const float pxf = float(px), pyf = float(py);
         const float wx0 = float(bx0), wy0 = float(by0);
-        const float4 *g0 = a.rec0 + off, *g1 = a.rec1 + off, *g2 = a.rec2 + off;
+        const float4 *g0 = a.rec0 + off + lo, *g1 = a.rec1 + off + lo, *g2 = a.rec2 + off + lo;
         float T = T_final;
         float ar0 = 0, ar1 = 0, ar2 = 0, adr = 0, aar = 0, last_alpha = 0, lc0 = 0, lc1 = 0, lc2 = 0, last_depth = 0;
+        if (last > hi) {                         // contributors behind this segment: resume from the checkpoints
+            const unsigned int n = a.tile_cnt[tg];
+            const size_t slot0 = off / (kSegment / 2);
+            const size_t ci = ((slot0 + ws.y) * kBlocksPerTile + blk) * 32 + lane;
+            const size_t fi = ((slot0 + (n + kSegment - 1) / kSegment - 1) * kBlocksPerTile + blk) * 32 + lane;
+            const float4 ck = a.ck0[ci], fin = a.ck0[fi];
+            const float inv = 1.0f / ck.x;
+            T = ck.x * (T_final / fin.x);
+            ar0 = (fin.y - ck.y) * inv; ar1 = (fin.z - ck.z) * inv; ar2 = (fin.w - ck.w) * inv;
+            if (kDepthAlphaGrads) {
+                adr = (a.ck1[fi] - a.ck1[ci]) * inv;
+                aar = (ck.x - fin.x) * inv;
+            }
+        }
         const float bg_dot = (bg0 * dp0 + bg1 * dp1) + bg2 * dp2;
         float* acc = a.accum + size_t(rl) * a.g.N;
         const unsigned int* ids = a.sorted_ids + off;
@@ -461,25 +487,25 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
         while (b_issued < nb && b_issued < unsigned(kBwdStages - 1)) {
             const unsigned int lb = nb - 1 - b_issued;
             ring_issue(sm, issued, g0 + lb * kBatch, g1 + lb * kBatch, g2 + lb * kBatch,
-                       min(unsigned(kBatch), wmax - lb * kBatch), lane);
+                       min(unsigned(kBatch), hi - lo - lb * kBatch), lane);
             ++issued; ++b_issued;
         }
         for (unsigned int b = 0; b < nb; ++b) {
             if (b_issued < nb) {
                 const unsigned int lb = nb - 1 - b_issued;
                 ring_issue(sm, issued, g0 + lb * kBatch, g1 + lb * kBatch, g2 + lb * kBatch,
-                           min(unsigned(kBatch), wmax - lb * kBatch), lane);
+                           min(unsigned(kBatch), hi - lo - lb * kBatch), lane);
                 ++issued; ++b_issued;
             }
             const int s = consumed % kBwdStages;
             mbar_wait(&sm.full[s], (consumed / kBwdStages) & 1);
             ++consumed;
-            const unsigned int cbase = (nb - 1 - b) * kBatch;
-            const unsigned int m = min(unsigned(kBatch), wmax - cbase);
+            const unsigned int cbase = lo + (nb - 1 - b) * kBatch;     // list index of the batch's first record
+            const unsigned int m = min(unsigned(kBatch), hi - cbase);
             const float4* r0 = sm.r0[s];
             const float4* r1 = sm.r1[s];
             const float4* r2 = sm.r2[s];
-            const uint4 cnt = cull_batch(r0, m, wx0, wy0, sm.list, lane);
+            const uint4 cnt = cull_batch(r0, m, blk, sm.list, lane);
             const unsigned int my_n = qsel == 0 ? cnt.x : qsel == 1 ? cnt.y : qsel == 2 ? cnt.z : cnt.w;
             const int total = int(max(max(cnt.x, cnt.y), max(cnt.z, cnt.w)));
             // trip t of the batch handles the quarter's survivor number (my_n - 1 - t): back to front
@@ -532,7 +558,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
                     for (int u = 0; u < 4; ++u) {
                         const float alpha = al[u];
                         const bool on = alpha != 0.0f;
-                        const float inv_om = __frcp_rn(1.0f - alpha);
+                        const float inv_om = rcp_approx(1.0f - alpha);
                         const float Tn = T * inv_om;
                         const float ola = 1.0f - last_alpha;
                         const float n0 = fmaf(last_alpha, lc0, ola * ar0);
@@ -665,6 +691,7 @@ cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out
     a.rec0 = c.rec0; a.rec1 = c.rec1; a.rec2 = c.rec2; a.bg = c.p->bg; a.n_contrib = c.n_contrib;
     a.tile_time = c.tile_time;
     a.out_color = out_color; a.out_depth = out_depth; a.out_alpha = out_alpha;
+    a.ck0 = c.ck0; a.ck1 = c.ck1;
     a.work_blend = c.work_blend; a.work_empty = c.work_empty; a.wc = c.work_counts;
     a.clamp_color = (c.p->flags & SGR_FLAG_CLAMP_COLOR) ? 1 : 0;
     constexpr size_t smem = sizeof(FwdSmem) * kWarpsPerCta;
@@ -686,7 +713,7 @@ cudaError_t launch_blend_backward(const ChunkCtx& c, const float* out_alpha, con
     a.sorted_ids = c.sorted_ids; a.rec0 = c.rec0; a.rec1 = c.rec1; a.rec2 = c.rec2; a.bg = c.p->bg;
     a.n_contrib = c.n_contrib; a.out_alpha = out_alpha; a.dL_dcolor = dL_dcolor; a.dL_ddepth = dL_ddepth;
     a.dL_dalpha = dL_dalpha; a.accum = c.accum; a.plane = size_t(c.num_renders) * c.g.N;
-    a.work_blend = c.work_blend; a.wc = c.work_counts;
+    a.ck0 = c.ck0; a.ck1 = c.ck1; a.work_seg = c.work_seg; a.wc = c.work_counts;
     constexpr size_t smem = sizeof(BwdSmem) * kWarpsPerCta;
     const long long items = (long long)c.num_renders * c.g.num_tiles * kBlocksPerTile;
     const long long want = (items + kWarpsPerCta - 1) / kWarpsPerCta;

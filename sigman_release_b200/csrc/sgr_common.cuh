@@ -1,5 +1,6 @@
 // sgr_common.cuh — shared definitions of the sm_100a rasteriser kernels (internal; the public ABI is include/sgr.h).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -10,6 +11,12 @@ namespace sgr {
 constexpr int kTile = 16;                 // BLOCK_X = BLOCK_Y of the published algorithm
 constexpr int kTilePixels = kTile * kTile;
 constexpr int kDefaultRendersPerChunk = 16;
+// Backward work granularity: a tile's depth-ordered list is replayed in independent segments of kSegment records
+// (multiple of the blend kernels' 64-record batch).  The forward blend checkpoints every pixel's running state at the
+// segment boundaries of lists longer than one segment; slot (tile, s) = tile_off / (kSegment / 2) + s, s < #segments,
+// the last slot holding the final state (a list of n > kSegment records spans at least ceil(n / kSegment) slots).
+constexpr int kSegment = 1024;
+constexpr int kCkptPerSlot = kTilePixels;   // one entry per pixel of the tile: [8 blocks][32 lanes]
 
 // ------------------------------------------------------------------------------------------------
 // Device-resident status / counters at the start of `state`.
@@ -28,17 +35,18 @@ static_assert(sizeof(SgrStatus) == 32, "SgrStatus layout is part of the ABI");
 
 // Layout of `state` (kept forward -> backward) for a problem shape.
 struct StateLayout {
-    uint64_t header, tile_off, tile_cnt, tile_time, n_contrib, sorted_ids, rec0, rec1, rec2, total;
+    uint64_t header, tile_off, tile_cnt, tile_time, n_contrib, sorted_ids, rec0, rec1, rec2, ck0, ck1, total;
 };
 // Layout of `scratch` (valid only inside one call).
 struct ScratchLayout {
-    uint64_t keys, g0, g1, g2, rect, cursor, work_small, work_big, work_blend, work_empty, work_counts, accum, total;
+    uint64_t keys, g0, g1, g2, rect, cursor, work_small, work_big, work_blend, work_empty, work_seg, work_counts, accum, total;
 };
 
 __host__ __device__ inline uint64_t align_up(uint64_t x, uint64_t a = 256) { return (x + a - 1) / a * a; }
 
 inline int tiles_x(int W) { return (W + kTile - 1) / kTile; }
 inline int tiles_y(int H) { return (H + kTile - 1) / kTile; }
+inline uint64_t ckpt_slots(uint64_t cap) { return cap / (kSegment / 2) + 2; }
 
 inline StateLayout make_state_layout(int B, int V, int N, int H, int W, uint64_t cap) {
     (void)N;
@@ -54,6 +62,8 @@ inline StateLayout make_state_layout(int B, int V, int N, int H, int W, uint64_t
     L.rec0 = o;        o = align_up(o + cap * 16);
     L.rec1 = o;        o = align_up(o + cap * 16);
     L.rec2 = o;        o = align_up(o + cap * 16);
+    L.ck0 = o;         o = align_up(o + ckpt_slots(cap) * kCkptPerSlot * 16);   // (T, C0, C1, C2) per pixel and slot
+    L.ck1 = o;         o = align_up(o + ckpt_slots(cap) * kCkptPerSlot * 4);    // D
     L.total = o;
     return L;
 }
@@ -75,6 +85,7 @@ inline ScratchLayout make_scratch_layout(int B, int V, int N, int H, int W, uint
     L.work_big = o;    o = align_up(o + Rc * T * 4);
     L.work_blend = o;  o = align_up(o + Rc * T * 4);
     L.work_empty = o;  o = align_up(o + Rc * T * 4);
+    L.work_seg = o;    o = align_up(o + (Rc * T + cap / kSegment + 1) * 8);       // (tile, segment) backward items
     L.work_counts = o; o = align_up(o + 256);
     L.accum = o;       o = align_up(o + Rc * N * 4 * kAccumPlanes);
     L.total = o;
@@ -91,6 +102,8 @@ struct WorkCounts {
     unsigned int n_empty;      // tiles without instances (background only)
     unsigned int blend_cursor; // dynamic work queue heads of the persistent blend kernels
     unsigned int empty_cursor;
+    unsigned int n_seg;        // backward items: (tile, segment) pairs, longest first
+    unsigned int seg_cursor;
 };
 
 constexpr int kSmallSortCap = 4096;       // instances sorted in a 40 KB shared-memory CTA
@@ -142,6 +155,30 @@ __device__ __forceinline__ float gauss_power(float hA, float nB, float hC, float
     return __fmaf_rn(dx, __fmul_rn(hA, dx), __fmul_rn(dy, __fmaf_rn(hC, dy, __fmul_rn(nB, dx))));
 }
 
+// Conservative alpha >= 1/255 extent (|dx| <= ex, |dy| <= ey) packed as two halves by the preprocess kernel.
+__device__ __forceinline__ float2 unpack_extent(float packed) {
+    const unsigned int u = __float_as_uint(packed);
+    return make_float2(__half2float(__ushort_as_half(static_cast<unsigned short>(u & 0xffffu))),
+                       __half2float(__ushort_as_half(static_cast<unsigned short>(u >> 16))));
+}
+
+// Quarter mask of one (Gaussian, tile) instance: bit (blk * 4 + q) is set when the Gaussian's conservative extent
+// overlaps the pixel centres of 4x2 quarter q of 8x4 pixel block blk of the 16x16 tile at (X0, Y0).
+// blk = (y block 0..3) * 2 + (x block 0..1), q = (x half) | (y half) << 1 — the blend kernels' work decomposition.
+// NaN coordinates give an empty mask (all comparisons false): such a record can never pass the alpha test.
+__device__ __forceinline__ unsigned int quarter_mask(float x, float y, float packed_ext, float X0, float Y0) {
+    const float2 ext = unpack_extent(packed_ext);
+    const float xl = x - ext.x, xh = x + ext.x, yl = y - ext.y, yh = y + ext.y;
+    unsigned int row = 0, mask = 0;
+#pragma unroll
+    for (int qc = 0; qc < 4; ++qc)
+        if (xh >= X0 + float(4 * qc) && xl <= X0 + float(4 * qc + 3)) row |= 1u << ((qc & 1) | ((qc >> 1) << 2));
+#pragma unroll
+    for (int qr = 0; qr < 8; ++qr)
+        if (yh >= Y0 + float(2 * qr) && yl <= Y0 + float(2 * qr + 1)) mask |= row << ((qr >> 1) * 8 + (qr & 1) * 2);
+    return mask;
+}
+
 constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr float kAlphaMax = 0.99f;
 constexpr float kTMin = 0.0001f;
@@ -163,12 +200,15 @@ struct ChunkCtx {
     unsigned int* n_contrib;  // [R*P]
     unsigned int* sorted_ids; // [cap]
     float4 *rec0, *rec1, *rec2;   // [cap]
+    float4* ck0;              // [ckpt_slots][256] forward checkpoints (T, C0, C1, C2)
+    float* ck1;               // [ckpt_slots][256] forward checkpoints D
     // scratch
     unsigned long long* keys; // [cap]
     float4 *g0, *g1, *g2;     // [Rc*N]
     uint2* rect;              // [Rc*N] packed tile rectangle
     unsigned int* cursor;     // [Rc*T]
     unsigned int *work_small, *work_big, *work_blend, *work_empty;
+    uint2* work_seg;          // [Rc*T + cap/kSegment + 1]
     WorkCounts* work_counts;
     float* accum;             // [kAccumPlanes][Rc*N]
     cudaStream_t stream;
@@ -176,7 +216,8 @@ struct ChunkCtx {
 
 cudaError_t launch_preprocess(const ChunkCtx& c, int32_t* radii);
 cudaError_t launch_scan_tiles(const ChunkCtx& c);
-cudaError_t launch_worklist(const ChunkCtx& c);     // blend/empty work lists from tile_cnt (forward and backward)
+cudaError_t launch_worklist(const ChunkCtx& c);     // forward: blend/empty tile work lists from tile_cnt
+cudaError_t launch_worklist_segments(const ChunkCtx& c);   // backward: (tile, segment) work list from tile_cnt
 cudaError_t launch_scatter(const ChunkCtx& c);
 cudaError_t launch_sort_tiles(const ChunkCtx& c);
 cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out_depth, float* out_alpha);

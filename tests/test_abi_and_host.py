@@ -41,7 +41,8 @@ def test_buffer_size_queries(lib):
     a = lib.sgr_state_bytes(1, 8, 100_000, 512, 512, 2_000_000)
     b = lib.sgr_state_bytes(1, 8, 100_000, 512, 512, 4_000_000)
     assert 0 < a < b and a % 256 == 0
-    assert b - a == 2_000_000 * 52                       # 4-byte id + three 16-byte record streams per instance
+    # per instance: 4-byte id + three 16-byte record streams; per 512 instances one checkpoint slot of 256 pixels x 20 B
+    assert b - a == 2_000_000 * 52 + (4_000_000 // 512 - 2_000_000 // 512) * 256 * 20
     assert lib.sgr_state_bytes(0, 8, 10, 64, 64, 10) == 0
     s16 = lib.sgr_scratch_bytes(8, 10, 100_000, 512, 512, 20_000_000, 16)
     s80 = lib.sgr_scratch_bytes(8, 10, 100_000, 512, 512, 20_000_000, 80)
