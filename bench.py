@@ -40,13 +40,15 @@ def alg_bytes(n, p):
     return dict(forward=56 * n + 20 * p, backward=116 * n + 28 * p)
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, unfused=False):
     return {
         "workload": "BASELINE configs[1]: 1 subject x ~100K Gaussians (procedural SMPL-X-shaped body), 8 views "
                     "512x512, forward+backward, L1 on clamped RGB",
         "num_gaussians": N_GAUSS, "views": len(VIEWS), "image": [H, W], "subjects_per_gpu": 1,
         "parallelism": f"{n_gpus} rank(s), one subject each (independent renders, no data-path collective)",
         "l2": "256 MiB memset between steps (outside the per-step event pairs)",
+        "loss": ("torch elementwise ops on the rendered images (clamp, sub, abs, mean) + autograd" if unfused else
+                 "render_l1_loss: clamp + L1 + dL/dcolour evaluated in the blend epilogue (SURVEY 8f #4)"),
     }
 
 
@@ -193,9 +195,13 @@ def run_ours(args):
     def render_step(t):
         for v in t.values():
             v.grad = None
-        color, radii, depth, alpha = rasterizer.rasterize_batch(t["means3D"], t["cov3D"], t["colors"], t["opacities"],
-                                                                vmt, pmt, bg, H, W, tan, tan)
-        loss = (color.clamp(0, 1) - target).abs().mean()
+        if args.unfused_loss:
+            color, radii, depth, alpha = rasterizer.rasterize_batch(t["means3D"], t["cov3D"], t["colors"],
+                                                                    t["opacities"], vmt, pmt, bg, H, W, tan, tan)
+            loss = (color.clamp(0, 1) - target).abs().mean()
+        else:
+            loss = rasterizer.render_l1_loss(t["means3D"], t["cov3D"], t["colors"], t["opacities"], vmt, pmt, bg, H, W,
+                                             tan, tan, target)[0]
         loss.backward()
         if world > 1:
             dist.all_gather_into_tensor(gathered, loss.detach().reshape(1))
@@ -298,7 +304,7 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(world),
+        "data": "synthetic", "config": workload_config(world, args.unfused_loss),
         "views_per_sec": V * world / (ms_step * 1e-3),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e, "views_per_sec": V * world / (ms_e2e * 1e-3)},
@@ -333,6 +339,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--unfused-loss", action="store_true",
+                    help="compute the L1 loss with torch ops on the rendered images instead of the fused epilogue")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SGR_ABI_VERSION 1
+#define SGR_ABI_VERSION 2
 
 typedef enum SgrError {
     SGR_OK = 0,
@@ -42,7 +42,9 @@ typedef enum SgrError {
 
 enum {
     SGR_FLAG_SIMPLE_BLEND = 1,     /* use the straightforward (upstream-shaped) blend kernels: debugging aid */
-    SGR_FLAG_CLAMP_COLOR = 2       /* fuse gs.py:107 `rendered_image.clamp(0, 1)` into the blend epilogue */
+    SGR_FLAG_CLAMP_COLOR = 2,      /* fuse gs.py:107 `rendered_image.clamp(0, 1)` into the blend epilogue */
+    SGR_FLAG_FORWARD_ONLY = 4      /* no backward will follow: skip the forward's bookkeeping for it (the refinement
+                                      of the per-instance cull masks to the quarters that actually blended) */
 };
 
 /* Problem description shared by forward and backward.
@@ -79,6 +81,17 @@ typedef struct SgrForwardArgs {
     void* state;    uint64_t state_bytes;
     void* scratch;  uint64_t scratch_bytes;
     void* stream;
+    /* Optional fused reconstruction loss: replaces gs.py:107 `clamp(0, 1)` followed by
+     * /root/reference/core/loss/whole_loss.py:126-130 `l1(pred * mask, gt * mask)` (mean reduction) and its autograd
+     * backward.  When loss_target != NULL the blend epilogue writes the CLAMPED colour, accumulates
+     * sum |clamp(c) * m - t * m| * loss_scale into *loss_out (device scalar, deterministic summation order) and
+     * writes d loss / d colour (w.r.t. the unclamped colour: zero where the clamp saturated) to loss_dL_dcolor,
+     * which sgr_backward takes as its dL_dcolor.  Not available with SGR_FLAG_SIMPLE_BLEND. */
+    const float* loss_target;    /* [B,V,3,H,W] or NULL (no fused loss) */
+    const float* loss_mask;      /* [B,V,1,H,W] or NULL (mask of ones) */
+    float* loss_dL_dcolor;       /* [B,V,3,H,W] */
+    float* loss_out;             /* device scalar */
+    float loss_scale;            /* e.g. 1 / (B*V*3*H*W) for the mean */
 } SgrForwardArgs;
 
 /* Replaces `_C.rasterize_gaussians_backward`.  Gradient slots follow the tuple returned by upstream's
@@ -101,6 +114,8 @@ typedef struct SgrBackwardArgs {
     void* state;    uint64_t state_bytes;
     void* scratch;  uint64_t scratch_bytes;
     void* stream;
+    const float* dL_dcolor_scale; /* device scalar multiplying dL_dcolor (the upstream gradient of a fused loss), or
+                                     NULL (= 1).  Not available with SGR_FLAG_SIMPLE_BLEND. */
 } SgrBackwardArgs;
 
 /* Device-side status of the last forward that used `state` (read with sgr_read_status).  It is stored in the first

@@ -11,7 +11,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SGR_LIB_PATH") or os.path.join(_HERE, "libsgr_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 SGR_OK = 0
 SGR_E_INVALID_ARGUMENT = -1
@@ -21,6 +21,7 @@ SGR_E_INSTANCE_OVERFLOW = -4
 
 FLAG_SIMPLE_BLEND = 1
 FLAG_CLAMP_COLOR = 2
+FLAG_FORWARD_ONLY = 4
 
 _vp = ctypes.c_void_p
 
@@ -59,6 +60,11 @@ class SgrForwardArgs(ctypes.Structure):
         ("scratch", _vp),
         ("scratch_bytes", ctypes.c_uint64),
         ("stream", _vp),
+        ("loss_target", _vp),
+        ("loss_mask", _vp),
+        ("loss_dL_dcolor", _vp),
+        ("loss_out", _vp),
+        ("loss_scale", ctypes.c_float),
     ]
 
 
@@ -80,6 +86,7 @@ class SgrBackwardArgs(ctypes.Structure):
         ("scratch", _vp),
         ("scratch_bytes", ctypes.c_uint64),
         ("stream", _vp),
+        ("dL_dcolor_scale", _vp),
     ]
 
 

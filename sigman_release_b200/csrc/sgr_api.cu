@@ -116,7 +116,10 @@ void fill_ctx(ChunkCtx& c, const SgrProblem& p, void* state, void* scratch, cuda
     c.work_empty = reinterpret_cast<unsigned int*>(x + X.work_empty);
     c.work_seg = reinterpret_cast<uint2*>(x + X.work_seg);
     c.work_counts = reinterpret_cast<WorkCounts*>(x + X.work_counts);
+    c.loss_part = reinterpret_cast<float*>(x + X.loss_part);
     c.accum = reinterpret_cast<float*>(x + X.accum);
+    c.loss_target = nullptr; c.loss_mask = nullptr; c.loss_dL_dcolor = nullptr; c.loss_scale = 0.0f;
+    c.dL_scale = nullptr;
     c.stream = stream;
 }
 
@@ -177,6 +180,11 @@ int sgr_forward(const SgrForwardArgs* args) {
     if (!args->out_color || !args->out_depth || !args->out_alpha || (p.num_gaussians > 0 && !args->radii))
         return fail(SGR_E_INVALID_ARGUMENT, "null output pointer");
     if (!args->state || !args->scratch) return fail(SGR_E_INVALID_ARGUMENT, "null state / scratch");
+    const bool fused_loss = args->loss_target != nullptr;
+    if (fused_loss && (!args->loss_dL_dcolor || !args->loss_out))
+        return fail(SGR_E_INVALID_ARGUMENT, "fused loss needs loss_dL_dcolor and loss_out");
+    if (fused_loss && (p.flags & SGR_FLAG_SIMPLE_BLEND))
+        return fail(SGR_E_INVALID_ARGUMENT, "the fused loss is not available with SGR_FLAG_SIMPLE_BLEND");
     const int rpc = chunk_size(p);
     const uint64_t need_state = make_state_layout(p.num_subjects, p.views_per_subject, p.num_gaussians, p.image_height,
                                                   p.image_width, p.max_instances).total;
@@ -190,6 +198,10 @@ int sgr_forward(const SgrForwardArgs* args) {
     cudaStream_t stream = static_cast<cudaStream_t>(args->stream);
     ChunkCtx c;
     fill_ctx(c, p, args->state, args->scratch, stream);
+    if (fused_loss) {
+        c.loss_target = args->loss_target; c.loss_mask = args->loss_mask; c.loss_dL_dcolor = args->loss_dL_dcolor;
+        c.loss_scale = args->loss_scale;
+    }
     const int R = p.num_subjects * p.views_per_subject;
     init_header_kernel<<<1, 1, 0, stream>>>(c.header, p.max_instances);
     SGR_CUDA(cudaGetLastError());
@@ -211,6 +223,10 @@ int sgr_forward(const SgrForwardArgs* args) {
         } else {
             SGR_STAGE(kStWorklist, launch_worklist(c));
             SGR_STAGE(kStBlendFwd, launch_blend_forward(c, args->out_color, args->out_depth, args->out_alpha));
+            if (fused_loss) {
+                SGR_CUDA(launch_loss_reduce(c, args->loss_out));
+                g_launches += 1;
+            }
         }
     }
     (void)P;
@@ -236,10 +252,13 @@ int sgr_backward(const SgrBackwardArgs* args) {
     if (args->scratch_bytes < need_scratch)
         return fail(SGR_E_BUFFER_TOO_SMALL, "scratch buffer too small: %llu < %llu bytes", (unsigned long long)args->scratch_bytes, (unsigned long long)need_scratch);
     if (p.num_gaussians == 0) return SGR_OK;
+    if (args->dL_dcolor_scale && (p.flags & SGR_FLAG_SIMPLE_BLEND))
+        return fail(SGR_E_INVALID_ARGUMENT, "dL_dcolor_scale is not available with SGR_FLAG_SIMPLE_BLEND");
 
     cudaStream_t stream = static_cast<cudaStream_t>(args->stream);
     ChunkCtx c;
     fill_ctx(c, p, args->state, args->scratch, stream);
+    c.dL_scale = args->dL_dcolor_scale;
     const int R = p.num_subjects * p.views_per_subject;
     const size_t BN = size_t(p.num_subjects) * p.num_gaussians;
     SGR_CUDA(cudaMemsetAsync(args->dL_dmeans3D, 0, BN * 3 * 4, stream));

@@ -101,6 +101,7 @@ struct WarpSmem {
     float stash[kStashes][kDepth][32];
     float dpix[4][32];                          // backward: dL/dcolor (3) and dL/ddepth of the block's pixels
     unsigned char list[4][kBatch];              // per quarter: batch-local indices of the survivors (ascending)
+    unsigned int hit[kBatch];                   // forward: byte q of word j != 0 <=> quarter q blended record j
     uint64_t full[kNumStages];
 };
 
@@ -164,6 +165,8 @@ struct FwdArgs {
     const unsigned int* tile_off;
     const unsigned int* tile_cnt;
     const float4 *rec0, *rec1, *rec2;
+    unsigned int* rec0_words;     // rec0 as words: the forward refines the quarter masks (word 2 of every record)
+    int refine_masks;
     const float* bg;
     unsigned int* n_contrib;
     uint2* tile_time;
@@ -173,7 +176,40 @@ struct FwdArgs {
     const unsigned int *work_blend, *work_empty;
     WorkCounts* wc;
     int clamp_color;
+    // optional fused loss (include/sgr.h SgrForwardArgs::loss_*)
+    const float *loss_target, *loss_mask;
+    float* loss_dL_dcolor;
+    float* loss_part;
+    float loss_scale;
 };
+
+// Fused loss epilogue of one pixel: |clamp(c) * m - t * m| summed over the three channels; writes
+// d loss / d (unclamped colour) = sign(diff) * m * scale where the clamp did not saturate (torch's clamp / abs rules).
+__device__ __forceinline__ float loss_pixel(const FwdArgs& a, size_t rP, size_t P, size_t pix, float c0, float c1,
+                                            float c2) {
+    const float m = a.loss_mask ? a.loss_mask[rP + pix] : 1.0f;
+    const float* tg = a.loss_target + 3 * rP;
+    float* dl = a.loss_dL_dcolor + 3 * rP;
+    const float gs = m * a.loss_scale;
+    float part = 0.0f;
+    const float cs[3] = {c0, c1, c2};
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float c = cs[ch];
+        const float cl = fminf(fmaxf(c, 0.0f), 1.0f);
+        const float diff = cl * m - tg[ch * P + pix] * m;
+        part += fabsf(diff);
+        const bool pass = c >= 0.0f && c <= 1.0f;
+        dl[ch * P + pix] = pass ? (diff > 0.0f ? gs : diff < 0.0f ? -gs : 0.0f) : 0.0f;
+    }
+    return part;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
 
 using FwdSmem = WarpSmem<1, kSlots, kFwdStages>;
 using BwdSmem = WarpSmem<3, kBwdSlots, kBwdStages>;
@@ -202,6 +238,10 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
     float (*stash)[32] = sm.stash[0];
     const unsigned char* mylist = sm.list[qsel];
     unsigned int issued = 0, consumed = 0;       // ring counters (warp-uniform)
+    const bool refine = a.refine_masks != 0;
+    unsigned char* hit_bytes = reinterpret_cast<unsigned char*>(sm.hit) + qsel - 4;   // indexed with 4 * (j + 1)
+    sm.hit[lane] = 0u; sm.hit[lane + 32] = 0u;
+    __syncwarp();
 
     // ---------------- blocks of tiles with instances
     for (;;) {
@@ -218,7 +258,10 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
         const unsigned int nb = (n + kBatch - 1) / kBatch;
         const int tx = tile % a.g.tiles_x, ty = tile / a.g.tiles_x;
         const int bx0 = tx * kTile + (blk & 1) * kBlockW, by0 = ty * kTile + (blk >> 1) * kBlockH;
-        if (bx0 >= a.g.W || by0 >= a.g.H) continue;                 // block entirely outside the image
+        if (bx0 >= a.g.W || by0 >= a.g.H) {                        // block entirely outside the image
+            if (a.loss_target && lane == 0) a.loss_part[size_t(tile_local) * kBlocksPerTile + blk] = 0.0f;
+            continue;
+        }
         const unsigned long long t_begin = global_timer_ns();
         const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
         const bool inside = px < a.g.W && py < a.g.H;
@@ -309,6 +352,32 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
                         T = blend ? test_T : T;
                         last = blend ? idx[u] : last;
                         done = done || stop;
+                        // same-value stores of the quarter's lanes to one byte: benign
+                        if (refine && blend) hit_bytes[4u * (idx[u] - cbase)] = 1;
+                    }
+                }
+                __syncwarp();
+            }
+            // Mask refinement for the backward pass: clear the (block, quarter) bits of the records that no pixel of
+            // the quarter blended (alpha test, finished pixels) — the backward walk culls on the same word.
+#ifdef SGR_EXP_NO_BLOCK
+            if (false) {
+#else
+            if (refine && (cnt.x | cnt.y | cnt.z | cnt.w) != 0u) {
+#endif
+                const unsigned int* words = reinterpret_cast<const unsigned int*>(r0);
+#pragma unroll
+                for (unsigned int sub = 0; sub < unsigned(kBatch); sub += 32) {
+                    const unsigned int e = sub + lane;
+                    if (e < m) {
+                        const unsigned int nib = (words[4 * e + 2] >> (4 * blk)) & 0xfu;
+                        const unsigned int h = sm.hit[e];
+                        const unsigned int exact = ((h & 0x01010101u) * 0x10204080u) >> 28;
+                        const unsigned int clear = nib & ~exact;
+#ifndef SGR_EXP_NO_ATOMIC
+                        if (clear) atomicAnd(a.rec0_words + 4 * (off + cbase + e) + 2, ~(clear << (4 * blk)));
+#endif
+                        sm.hit[e] = 0u;
                     }
                 }
                 __syncwarp();
@@ -332,6 +401,12 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
             ++consumed;
         }
         __syncwarp();
+        if (a.loss_target) {
+            float part = 0.0f;
+            if (inside) part = loss_pixel(a, size_t(r) * P, P, size_t(py) * a.g.W + px, C0 + T * bg0, C1 + T * bg1, C2 + T * bg2);
+            part = warp_sum(part);
+            if (lane == 0) a.loss_part[size_t(tile_local) * kBlocksPerTile + blk] = part;
+        }
         if (inside) {
             const size_t pix = size_t(py) * a.g.W + px;
             float c0 = C0 + T * bg0, c1 = C1 + T * bg1, c2 = C2 + T * bg2;
@@ -364,6 +439,12 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
         const int r = a.render_base + rl;
         const int tx = tile % a.g.tiles_x, ty = tile / a.g.tiles_x;
         const int px = tx * kTile + (blk & 1) * kBlockW + (lane & 7), py = ty * kTile + (blk >> 1) * kBlockH + (lane >> 3);
+        if (a.loss_target) {
+            float part = 0.0f;
+            if (px < a.g.W && py < a.g.H) part = loss_pixel(a, size_t(r) * P, P, size_t(py) * a.g.W + px, bg0, bg1, bg2);
+            part = warp_sum(part);
+            if (lane == 0) a.loss_part[size_t(tile_local) * kBlocksPerTile + blk] = part;
+        }
         if (px < a.g.W && py < a.g.H) {
             const size_t pix = size_t(py) * a.g.W + px;
             float* oc = a.out_color + size_t(r) * 3 * P;
@@ -392,6 +473,7 @@ struct BwdArgs {
     const float* ck1;
     const uint2* work_seg;        // (chunk-local tile, segment) items, longest first
     WorkCounts* wc;
+    const float* dL_scale;        // device scalar multiplying dL_dcolor, or NULL
 };
 
 // Work item = (tile, segment, 8x4 pixel block): the block replays the list entries [lo, hi) of its segment back to
@@ -410,6 +492,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
     const float bg0 = a.bg[0], bg1 = a.bg[1], bg2 = a.bg[2];
     const unsigned int n_items = a.wc->n_seg * kBlocksPerTile;
     const float ddelx_dx = 0.5f * float(a.g.W), ddely_dy = 0.5f * float(a.g.H);
+    const float gscale = a.dL_scale ? *a.dL_scale : 1.0f;
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < kBwdStages; ++s) mbar_init(&sm.full[s], 1);
@@ -450,7 +533,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
         if (inside) {
             T_final = 1.0f - a.out_alpha[size_t(r) * P + pix];
             const float* dc = a.dL_dcolor + size_t(r) * 3 * P;
-            dp0 = dc[pix]; dp1 = dc[P + pix]; dp2 = dc[2 * P + pix];
+            dp0 = dc[pix] * gscale; dp1 = dc[P + pix] * gscale; dp2 = dc[2 * P + pix] * gscale;
             if (kDepthAlphaGrads) {
                 if (a.dL_ddepth) ddep = a.dL_ddepth[size_t(r) * P + pix];
                 if (a.dL_dalpha) dalp = a.dL_dalpha[size_t(r) * P + pix];
@@ -660,6 +743,21 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
     }
 }
 
+// Fused loss: fixed-order sum of the chunk's per-item partials (double), added to the device scalar.
+__global__ void __launch_bounds__(1024) loss_reduce_kernel(const float* part, unsigned int n, float* loss_out, int first,
+                                                           float scale) {
+    __shared__ double sh[1024];
+    double acc = 0.0;
+    for (unsigned int i = threadIdx.x; i < n; i += 1024) acc += double(part[i]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if (int(threadIdx.x) < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *loss_out = (first ? 0.0f : *loss_out) + float(sh[0] * double(scale));
+}
+
 int g_num_sms = 0;
 int num_sms() {
     if (g_num_sms == 0) {
@@ -689,11 +787,15 @@ cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out
     FwdArgs a;
     a.g = c.g; a.render_base = c.render_base; a.tile_off = c.tile_off; a.tile_cnt = c.tile_cnt;
     a.rec0 = c.rec0; a.rec1 = c.rec1; a.rec2 = c.rec2; a.bg = c.p->bg; a.n_contrib = c.n_contrib;
+    a.rec0_words = reinterpret_cast<unsigned int*>(c.rec0);
+    a.refine_masks = (c.p->flags & SGR_FLAG_FORWARD_ONLY) ? 0 : 1;
     a.tile_time = c.tile_time;
     a.out_color = out_color; a.out_depth = out_depth; a.out_alpha = out_alpha;
     a.ck0 = c.ck0; a.ck1 = c.ck1;
     a.work_blend = c.work_blend; a.work_empty = c.work_empty; a.wc = c.work_counts;
-    a.clamp_color = (c.p->flags & SGR_FLAG_CLAMP_COLOR) ? 1 : 0;
+    a.clamp_color = ((c.p->flags & SGR_FLAG_CLAMP_COLOR) || c.loss_target) ? 1 : 0;
+    a.loss_target = c.loss_target; a.loss_mask = c.loss_mask; a.loss_dL_dcolor = c.loss_dL_dcolor;
+    a.loss_part = c.loss_part; a.loss_scale = c.loss_scale;
     constexpr size_t smem = sizeof(FwdSmem) * kWarpsPerCta;
     static int per_sm = 0;
     if (per_sm == 0) {
@@ -706,6 +808,12 @@ cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out
     return cudaGetLastError();
 }
 
+cudaError_t launch_loss_reduce(const ChunkCtx& c, float* loss_out) {
+    const unsigned int n = unsigned(c.num_renders) * c.g.num_tiles * kBlocksPerTile;
+    loss_reduce_kernel<<<1, 1024, 0, c.stream>>>(c.loss_part, n, loss_out, c.render_base == 0 ? 1 : 0, c.loss_scale);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_blend_backward(const ChunkCtx& c, const float* out_alpha, const float* dL_dcolor,
                                   const float* dL_ddepth, const float* dL_dalpha) {
     BwdArgs a;
@@ -713,7 +821,7 @@ cudaError_t launch_blend_backward(const ChunkCtx& c, const float* out_alpha, con
     a.sorted_ids = c.sorted_ids; a.rec0 = c.rec0; a.rec1 = c.rec1; a.rec2 = c.rec2; a.bg = c.p->bg;
     a.n_contrib = c.n_contrib; a.out_alpha = out_alpha; a.dL_dcolor = dL_dcolor; a.dL_ddepth = dL_ddepth;
     a.dL_dalpha = dL_dalpha; a.accum = c.accum; a.plane = size_t(c.num_renders) * c.g.N;
-    a.ck0 = c.ck0; a.ck1 = c.ck1; a.work_seg = c.work_seg; a.wc = c.work_counts;
+    a.ck0 = c.ck0; a.ck1 = c.ck1; a.work_seg = c.work_seg; a.wc = c.work_counts; a.dL_scale = c.dL_scale;
     constexpr size_t smem = sizeof(BwdSmem) * kWarpsPerCta;
     const long long items = (long long)c.num_renders * c.g.num_tiles * kBlocksPerTile;
     const long long want = (items + kWarpsPerCta - 1) / kWarpsPerCta;

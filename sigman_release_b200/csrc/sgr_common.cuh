@@ -39,7 +39,7 @@ struct StateLayout {
 };
 // Layout of `scratch` (valid only inside one call).
 struct ScratchLayout {
-    uint64_t keys, g0, g1, g2, rect, cursor, work_small, work_big, work_blend, work_empty, work_seg, work_counts, accum, total;
+    uint64_t keys, g0, g1, g2, rect, cursor, work_small, work_big, work_blend, work_empty, work_seg, work_counts, loss_part, accum, total;
 };
 
 __host__ __device__ inline uint64_t align_up(uint64_t x, uint64_t a = 256) { return (x + a - 1) / a * a; }
@@ -87,6 +87,7 @@ inline ScratchLayout make_scratch_layout(int B, int V, int N, int H, int W, uint
     L.work_empty = o;  o = align_up(o + Rc * T * 4);
     L.work_seg = o;    o = align_up(o + (Rc * T + cap / kSegment + 1) * 8);       // (tile, segment) backward items
     L.work_counts = o; o = align_up(o + 256);
+    L.loss_part = o;   o = align_up(o + Rc * T * 8 * 4);                           // fused loss: one partial per work item
     L.accum = o;       o = align_up(o + Rc * N * 4 * kAccumPlanes);
     L.total = o;
     return L;
@@ -210,7 +211,13 @@ struct ChunkCtx {
     unsigned int *work_small, *work_big, *work_blend, *work_empty;
     uint2* work_seg;          // [Rc*T + cap/kSegment + 1]
     WorkCounts* work_counts;
+    float* loss_part;         // [Rc*T*8] fused-loss partial sums, one per (render, tile, pixel block)
     float* accum;             // [kAccumPlanes][Rc*N]
+    // optional fused loss (forward) / upstream gradient scalar (backward)
+    const float *loss_target, *loss_mask;
+    float* loss_dL_dcolor;
+    float loss_scale;
+    const float* dL_scale;
     cudaStream_t stream;
 };
 
@@ -221,6 +228,7 @@ cudaError_t launch_worklist_segments(const ChunkCtx& c);   // backward: (tile, s
 cudaError_t launch_scatter(const ChunkCtx& c);
 cudaError_t launch_sort_tiles(const ChunkCtx& c);
 cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out_depth, float* out_alpha);
+cudaError_t launch_loss_reduce(const ChunkCtx& c, float* loss_out);   // fused loss: sum of the chunk's partials
 cudaError_t launch_blend_backward(const ChunkCtx& c, const float* out_alpha, const float* dL_dcolor,
                                   const float* dL_ddepth, const float* dL_dalpha);
 cudaError_t launch_preprocess_backward(const ChunkCtx& c, const SgrBackwardArgs& a);

@@ -20,7 +20,7 @@ import torch
 
 from . import _native
 
-__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_batch", "rasterize_gaussians",
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_batch", "render_l1_loss", "rasterize_gaussians",
            "cov3d_from_scale_rot", "last_status"]
 
 
@@ -119,7 +119,7 @@ class _RasterizeBatch(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, cov3D, colors, opacities, means2D, viewmatrix, projmatrix, bg, H, W, tanfovx, tanfovy,
-                flags, renders_per_chunk):
+                flags, renders_per_chunk, loss_target=None, loss_mask=None):
         global _last_status
         L = _native.lib()
         B, N = int(means3D.shape[0]), int(means3D.shape[1])
@@ -132,6 +132,9 @@ class _RasterizeBatch(torch.autograd.Function):
             depth = torch.empty((B, V, 1, H, W), dtype=torch.float32, device=dev)
             alpha = torch.empty((B, V, 1, H, W), dtype=torch.float32, device=dev)
             radii = torch.empty((B, V, N), dtype=torch.int32, device=dev)
+            fused = loss_target is not None
+            loss = torch.empty((), dtype=torch.float32, device=dev) if fused else None
+            g_fused = torch.empty((B, V, 3, H, W), dtype=torch.float32, device=dev) if fused else None
             key = (dev.index, N, H, W)
             _drain_pending(block=False)
             first = key not in _est_per_render
@@ -150,6 +153,10 @@ class _RasterizeBatch(torch.autograd.Function):
                 a.state, a.state_bytes = _ptr(state), state_bytes
                 a.scratch, a.scratch_bytes = _ptr(scratch), scratch_bytes
                 a.stream = ctypes.c_void_p(stream.cuda_stream)
+                if fused:
+                    a.loss_target, a.loss_mask = _ptr(loss_target), _ptr(loss_mask)
+                    a.loss_dL_dcolor, a.loss_out = _ptr(g_fused), _ptr(loss)
+                    a.loss_scale = 1.0 / float(B * V * 3 * H * W)
                 _native.check(L.sgr_forward(ctypes.byref(a)))
                 if not sync_check:
                     pinned = torch.empty((64,), dtype=torch.uint8, pin_memory=True)
@@ -178,11 +185,23 @@ class _RasterizeBatch(torch.autograd.Function):
         ctx.dims = (B, V, N, H, W, float(tanfovx), float(tanfovy), cap, flags, renders_per_chunk, state_bytes)
         ctx.want_means2D = means2D is not None and means2D.requires_grad
         ctx.set_materialize_grads(False)     # unused depth / alpha outputs arrive as None, not as zero tensors
+        ctx.g_fused = g_fused
+        if fused:                            # only the loss is differentiable; the images are by-products
+            ctx.mark_non_differentiable(color, radii, depth, alpha)
+            return loss, color, radii, depth, alpha
         ctx.mark_non_differentiable(radii)
         return color, radii, depth, alpha
 
     @staticmethod
-    def backward(ctx, g_color, g_radii, g_depth, g_alpha):
+    def backward(ctx, *grads):
+        if ctx.g_fused is not None:          # fused loss: dL/dcolour was written by the forward's epilogue
+            g_loss, g_color, g_depth, g_alpha = grads[0], ctx.g_fused, None, None
+            if g_loss is None:
+                return (None,) * 16
+            g_loss = g_loss.detach().to(device=ctx.g_fused.device, dtype=torch.float32).contiguous()
+        else:
+            g_loss = None
+            g_color, _g_radii, g_depth, g_alpha = grads
         L = _native.lib()
         means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg, alpha, radii, state = ctx.saved_tensors
         B, V, N, H, W, tanfovx, tanfovy, cap, flags, rpc, state_bytes = ctx.dims
@@ -213,8 +232,9 @@ class _RasterizeBatch(torch.autograd.Function):
             a.state, a.state_bytes = _ptr(state), state_bytes
             a.scratch, a.scratch_bytes = _ptr(scratch), scratch_bytes
             a.stream = ctypes.c_void_p(stream.cuda_stream)
+            a.dL_dcolor_scale = _ptr(g_loss)
             _native.check(L.sgr_backward(ctypes.byref(a)))
-        return (d_means3D, d_cov3D, d_colors, d_opac, d_means2D, None, None, None, None, None, None, None, None, None)
+        return (d_means3D, d_cov3D, d_colors, d_opac, d_means2D) + (None,) * 11
 
 
 def rasterize_batch(means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg, image_height, image_width,
@@ -245,9 +265,46 @@ def rasterize_batch(means3D, cov3D, colors, opacities, viewmatrix, projmatrix, b
     if means2D is not None and tuple(means2D.shape) != (B, V, N, 3):
         raise ValueError("means2D must be [B,V,N,3]")
     flags = (_native.FLAG_CLAMP_COLOR if clamp_color else 0) | (_native.FLAG_SIMPLE_BLEND if simple_blend else 0)
+    if not (torch.is_grad_enabled() and any(t is not None and t.requires_grad
+                                            for t in (means3D, cov3D, colors, opacities, means2D))):
+        flags |= _native.FLAG_FORWARD_ONLY           # no backward can follow: skip the forward's bookkeeping for it
     return _RasterizeBatch.apply(means3D, cov3D, colors, opacities, means2D, viewmatrix, projmatrix, bg,
                                  int(image_height), int(image_width), float(tanfovx), float(tanfovy), flags,
-                                 int(renders_per_chunk))
+                                 int(renders_per_chunk), None, None)
+
+
+def render_l1_loss(means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg, image_height, image_width,
+                   tanfovx, tanfovy, target, mask=None, renders_per_chunk=0):
+    """Render B x V views and evaluate SIGMAN's reconstruction loss in the blend epilogue.
+
+    Equivalent to ``image = rasterize_batch(...)[0].clamp(0, 1)`` (gs.py:107) followed by
+    ``l1(image * mask, target * mask)`` with mean reduction (/root/reference/core/loss/whole_loss.py:126-130), but the
+    loss, the clamp mask and dL/dcolour never leave the blend kernel: no elementwise torch kernels, no autograd
+    graph over the images.  ``target`` [B,V,3,H,W], ``mask`` [B,V,1,H,W] or None.  Returns
+    ``(loss, image [B,V,3,H,W] clamped, radii, depth, alpha)``; only ``loss`` is differentiable (w.r.t. means3D,
+    cov3D, colors, opacities).
+    """
+    if means3D.dim() != 3 or means3D.shape[-1] != 3:
+        raise ValueError("means3D must be [B,N,3]")
+    B, N = int(means3D.shape[0]), int(means3D.shape[1])
+    if viewmatrix.dim() != 4 or tuple(viewmatrix.shape[2:]) != (4, 4) or int(viewmatrix.shape[0]) != B:
+        raise ValueError("viewmatrix must be [B,V,4,4]")
+    V = int(viewmatrix.shape[1])
+    H, W = int(image_height), int(image_width)
+    if opacities.dim() == 3:
+        opacities = opacities.reshape(B, N)
+    means3D = _check_input("means3D", means3D, (B, N, 3))
+    cov3D = _check_input("cov3D", cov3D, (B, N, 6))
+    colors = _check_input("colors", colors, (B, N, 3))
+    opacities = _check_input("opacities", opacities, (B, N))
+    viewmatrix = _check_input("viewmatrix", viewmatrix, (B, V, 4, 4))
+    projmatrix = _check_input("projmatrix", projmatrix, (B, V, 4, 4))
+    bg = _check_input("bg", bg, (3,))
+    target = _check_input("target", target.detach(), (B, V, 3, H, W))
+    if mask is not None:
+        mask = _check_input("mask", mask.detach(), (B, V, 1, H, W))
+    return _RasterizeBatch.apply(means3D, cov3D, colors, opacities, None, viewmatrix, projmatrix, bg, H, W,
+                                 float(tanfovx), float(tanfovy), 0, int(renders_per_chunk), target, mask)
 
 
 # ------------------------------------------------------------------------------------------------ optional inputs

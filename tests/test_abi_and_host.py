@@ -27,14 +27,14 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_native.SYMBOLS), declared ^ set(_native.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.sgr_abi_version() == 1
+    assert lib.sgr_abi_version() == _native.ABI_VERSION == 2
 
 
 def test_struct_layout_matches_header(lib):
     assert ctypes.sizeof(_native.SgrStatus) == 32
     assert ctypes.sizeof(_native.SgrProblem) == 104
-    assert ctypes.sizeof(_native.SgrForwardArgs) == 104 + 9 * 8
-    assert ctypes.sizeof(_native.SgrBackwardArgs) == 104 + 15 * 8
+    assert ctypes.sizeof(_native.SgrForwardArgs) == 104 + 9 * 8 + 5 * 8      # + the fused-loss block
+    assert ctypes.sizeof(_native.SgrBackwardArgs) == 104 + 16 * 8
 
 
 def test_buffer_size_queries(lib):
