@@ -43,8 +43,9 @@ typedef enum SgrError {
 enum {
     SGR_FLAG_SIMPLE_BLEND = 1,     /* use the straightforward (upstream-shaped) blend kernels: debugging aid */
     SGR_FLAG_CLAMP_COLOR = 2,      /* fuse gs.py:107 `rendered_image.clamp(0, 1)` into the blend epilogue */
-    SGR_FLAG_FORWARD_ONLY = 4      /* no backward will follow: skip the forward's bookkeeping for it (the refinement
+    SGR_FLAG_FORWARD_ONLY = 4,     /* no backward will follow: skip the forward's bookkeeping for it (the refinement
                                       of the per-instance cull masks to the quarters that actually blended) */
+    SGR_FLAG_TILE_TIMING = 8       /* record per-tile forward blend timings (sgr_debug_copy_state: tile_timing) */
 };
 
 /* Problem description shared by forward and backward.
@@ -167,10 +168,10 @@ int sgr_knn_mean_dist2(const float* points, int32_t num_points, float* out_mean_
 
 /* Measurement hooks (bench.py): per-stage device time with CUDA events recorded on the launch stream around every
  * stage of sgr_forward / sgr_backward while enabled, and a counter of the kernels this library has launched.
- * Stage order: preprocess, scan, scatter, sort, worklist, blend_forward, blend_backward, preprocess_backward.
+ * Stage order: preprocess, plan, scatter, sort, blend_forward, blend_backward, preprocess_backward.
  * sgr_profile_collect synchronises on the recorded events, returns summed milliseconds and the number of timed
  * stage invocations, and resets the accumulators. */
-#define SGR_NUM_STAGES 8
+#define SGR_NUM_STAGES 7
 void sgr_profile_enable(int on);
 int sgr_profile_collect(double* stage_ms, uint32_t* stage_invocations);
 uint64_t sgr_launch_count(void);
@@ -183,7 +184,7 @@ uint64_t sgr_launch_count(void);
  *   point_list   uint32[point_list_capacity]  Gaussian index of every instance of the render in sorted order —
  *                                  upstream's binningState.point_list restricted to the render
  *   tile_timing  uint32[tiles][2]  (start, duration) of the tile's forward blend in ns of the GPU global timer
- *                                  (low 32 bits; load-balance diagnostics)
+ *                                  (low 32 bits; load-balance diagnostics; needs SGR_FLAG_TILE_TIMING)
  * The shape arguments must be those of the forward that filled `state`. */
 int sgr_debug_copy_state(const void* state, int32_t num_subjects, int32_t views_per_subject, int32_t num_gaussians,
                          int32_t image_height, int32_t image_width, uint64_t max_instances, int32_t render,

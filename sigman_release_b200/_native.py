@@ -22,6 +22,7 @@ SGR_E_INSTANCE_OVERFLOW = -4
 FLAG_SIMPLE_BLEND = 1
 FLAG_CLAMP_COLOR = 2
 FLAG_FORWARD_ONLY = 4
+FLAG_TILE_TIMING = 8
 
 _vp = ctypes.c_void_p
 
@@ -122,8 +123,7 @@ SYMBOLS = {
     "sgr_debug_copy_state": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _u64, _i32, _vp, _vp, _vp, _u64, _vp, _vp]),
 }
 
-STAGES = ("preprocess", "scan", "scatter", "sort", "worklist", "blend_forward", "blend_backward",
-          "preprocess_backward")
+STAGES = ("preprocess", "plan", "scatter", "sort", "blend_forward", "blend_backward", "preprocess_backward")
 
 _LIB = None
 

@@ -35,9 +35,9 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 // ---- optional per-stage timing (bench.py roofline leg) and the launch counter -------------------------------------
-enum Stage { kStPreprocess = 0, kStScan, kStScatter, kStSort, kStWorklist, kStBlendFwd, kStBlendBwd, kStPreBwd, kNumStages };
+enum Stage { kStPreprocess = 0, kStPlan, kStScatter, kStSort, kStBlendFwd, kStBlendBwd, kStPreBwd, kNumStages };
 static_assert(kNumStages == SGR_NUM_STAGES, "stage list and SGR_NUM_STAGES differ");
-const int kStageLaunches[kNumStages] = {1, 1, 1, 2, 1, 1, 1, 1};
+const int kStageLaunches[kNumStages] = {1, 1, 1, 2, 1, 1, 1};
 
 struct StageEvent { int stage; cudaEvent_t beg, end; };
 bool g_profile = false;
@@ -104,6 +104,9 @@ void fill_ctx(ChunkCtx& c, const SgrProblem& p, void* state, void* scratch, cuda
     c.rec2 = reinterpret_cast<float4*>(s + S.rec2);
     c.ck0 = reinterpret_cast<float4*>(s + S.ck0);
     c.ck1 = reinterpret_cast<float*>(s + S.ck1);
+    c.plan = reinterpret_cast<ChunkPlan*>(s + S.plan);
+    c.work_seg = reinterpret_cast<uint2*>(s + S.work_seg);
+    c.chunk_index = 0;
     c.keys = reinterpret_cast<unsigned long long*>(x + X.keys);
     c.g0 = reinterpret_cast<float4*>(x + X.g0);
     c.g1 = reinterpret_cast<float4*>(x + X.g1);
@@ -114,18 +117,12 @@ void fill_ctx(ChunkCtx& c, const SgrProblem& p, void* state, void* scratch, cuda
     c.work_big = reinterpret_cast<unsigned int*>(x + X.work_big);
     c.work_blend = reinterpret_cast<unsigned int*>(x + X.work_blend);
     c.work_empty = reinterpret_cast<unsigned int*>(x + X.work_empty);
-    c.work_seg = reinterpret_cast<uint2*>(x + X.work_seg);
     c.work_counts = reinterpret_cast<WorkCounts*>(x + X.work_counts);
     c.loss_part = reinterpret_cast<float*>(x + X.loss_part);
     c.accum = reinterpret_cast<float*>(x + X.accum);
     c.loss_target = nullptr; c.loss_mask = nullptr; c.loss_dL_dcolor = nullptr; c.loss_scale = 0.0f;
     c.dL_scale = nullptr;
     c.stream = stream;
-}
-
-__global__ void init_header_kernel(StateHeader* h, unsigned long long capacity) {
-    h->inst_required = 0; h->capacity = capacity; h->overflow = 0; h->max_tile_instances = 0; h->nonempty_tiles = 0;
-    h->pad = 0; h->inst_cursor = 0;
 }
 
 __global__ void debug_ranges_kernel(const unsigned int* tile_off, const unsigned int* tile_cnt, int num_tiles,
@@ -203,17 +200,17 @@ int sgr_forward(const SgrForwardArgs* args) {
         c.loss_scale = args->loss_scale;
     }
     const int R = p.num_subjects * p.views_per_subject;
-    init_header_kernel<<<1, 1, 0, stream>>>(c.header, p.max_instances);
-    SGR_CUDA(cudaGetLastError());
-    g_launches += 1;
-    SGR_CUDA(cudaMemsetAsync(c.tile_cnt, 0, size_t(R) * c.g.num_tiles * 4, stream));
-    SGR_CUDA(cudaMemsetAsync(c.tile_time, 0, size_t(R) * c.g.num_tiles * 8, stream));
-    const size_t P = size_t(p.image_height) * p.image_width;
+    // tile_cnt and tile_time are adjacent in `state`: one memset (the status header is initialised by the plan kernel)
+    SGR_CUDA(cudaMemsetAsync(c.tile_cnt, 0, (reinterpret_cast<char*>(c.tile_time) - reinterpret_cast<char*>(c.tile_cnt)) +
+                                                size_t(R) * c.g.num_tiles * ((p.flags & SGR_FLAG_TILE_TIMING) ? 8 : 0), stream));
+    ChunkPlan* plan0 = c.plan;
     for (int r0 = 0; r0 < R; r0 += rpc) {
         c.render_base = r0;
         c.num_renders = (R - r0 < rpc) ? (R - r0) : rpc;
+        c.chunk_index = r0 / rpc;
+        c.plan = plan0 + c.chunk_index;
         if (p.num_gaussians > 0) SGR_STAGE(kStPreprocess, launch_preprocess(c, args->radii));
-        SGR_STAGE(kStScan, launch_scan_tiles(c));
+        SGR_STAGE(kStPlan, launch_plan(c));
         if (p.num_gaussians > 0) {
             SGR_STAGE(kStScatter, launch_scatter(c));
             SGR_STAGE(kStSort, launch_sort_tiles(c));
@@ -221,7 +218,6 @@ int sgr_forward(const SgrForwardArgs* args) {
         if (p.flags & SGR_FLAG_SIMPLE_BLEND) {
             SGR_STAGE(kStBlendFwd, launch_blend_forward_simple(c, args->out_color, args->out_depth, args->out_alpha));
         } else {
-            SGR_STAGE(kStWorklist, launch_worklist(c));
             SGR_STAGE(kStBlendFwd, launch_blend_forward(c, args->out_color, args->out_depth, args->out_alpha));
             if (fused_loss) {
                 SGR_CUDA(launch_loss_reduce(c, args->loss_out));
@@ -229,7 +225,6 @@ int sgr_forward(const SgrForwardArgs* args) {
             }
         }
     }
-    (void)P;
     return SGR_OK;
 }
 
@@ -261,18 +256,19 @@ int sgr_backward(const SgrBackwardArgs* args) {
     c.dL_scale = args->dL_dcolor_scale;
     const int R = p.num_subjects * p.views_per_subject;
     const size_t BN = size_t(p.num_subjects) * p.num_gaussians;
-    SGR_CUDA(cudaMemsetAsync(args->dL_dmeans3D, 0, BN * 3 * 4, stream));
-    SGR_CUDA(cudaMemsetAsync(args->dL_dcov3D, 0, BN * 6 * 4, stream));
-    SGR_CUDA(cudaMemsetAsync(args->dL_dcolors, 0, BN * 3 * 4, stream));
-    SGR_CUDA(cudaMemsetAsync(args->dL_dopacities, 0, BN * 4, stream));
+    (void)BN;   // the per-subject gradients are stored (not accumulated) by the chunk holding the subject's first view
+    ChunkPlan* plan0 = c.plan;
     for (int r0 = 0; r0 < R; r0 += rpc) {
         c.render_base = r0;
         c.num_renders = (R - r0 < rpc) ? (R - r0) : rpc;
+        c.chunk_index = r0 / rpc;
+        c.plan = plan0 + c.chunk_index;
         SGR_CUDA(cudaMemsetAsync(c.accum, 0, size_t(c.num_renders) * p.num_gaussians * 4 * kAccumPlanes, stream));
         if (p.flags & SGR_FLAG_SIMPLE_BLEND) {
             SGR_STAGE(kStBlendBwd, launch_blend_backward_simple(c, args->out_alpha, args->dL_dcolor, args->dL_ddepth, args->dL_dalpha));
         } else {
-            SGR_STAGE(kStWorklist, launch_worklist_segments(c));
+            // the (tile, segment) work list was planned by the forward; only its queue head is reset here
+            SGR_CUDA(cudaMemsetAsync(&c.plan->seg_cursor, 0, 4, stream));
             SGR_STAGE(kStBlendBwd, launch_blend_backward(c, args->out_alpha, args->dL_dcolor, args->dL_ddepth, args->dL_dalpha));
         }
         SGR_STAGE(kStPreBwd, launch_preprocess_backward(c, *args));

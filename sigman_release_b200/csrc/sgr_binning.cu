@@ -14,23 +14,45 @@
 namespace sgr {
 namespace {
 
-// ------------------------------------------------------------------------------------------------ scan
-struct ScanArgs {
+// ------------------------------------------------------------------------------------------------ plan
+// One single-CTA kernel per chunk (replaces upstream's InclusiveSum + the num_rendered device->host copy, and plans
+// everything that depends only on the per-tile instance counts):
+//   1. exclusive scan of tile_cnt -> tile_off, instance range reserved on the device (overflow -> chunk dropped);
+//   2. sort work lists (small / big tiles);
+//   3. forward blend work list: non-empty tiles by descending size class (longest-processing-time first for the
+//      persistent blend kernel) + the list of empty tiles (background only);
+//   4. backward work list (kept in `state`): every tile list cut into segments of kSegment records, items
+//      (tile, segment) by descending size class of the segment length.
+struct PlanArgs {
     int n;                        // tiles in the chunk (renders * tiles per render)
+    int first_chunk;              // != 0: initialise the status header
+    unsigned long long capacity;
+    unsigned int seg_region;      // first work_seg slot this chunk may use, before adding instances / kSegment
     unsigned int* tile_cnt;       // chunk slice
     unsigned int* tile_off;       // chunk slice
     unsigned int* cursor;         // chunk scatter cursors (zeroed here)
     StateHeader* header;
     WorkCounts* wc;
-    unsigned int *work_small, *work_big;
+    ChunkPlan* plan;
+    unsigned int *work_small, *work_big, *work_blend, *work_empty;
+    uint2* work_seg;
 };
 
 constexpr int kScanThreads = 1024;
+constexpr int kSizeClasses = 66;      // 2 * (bit length of the count) + next-lower bit; class 0 = empty
 
-__global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(ScanArgs a) {
+__device__ __forceinline__ int size_class(unsigned int c) {
+    if (c == 0) return 0;
+    const int msb = 31 - __clz(c);
+    const int half = msb ? int((c >> (msb - 1)) & 1u) : 0;
+    return 2 * (msb + 1) + half;
+}
+
+__global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
     __shared__ unsigned int s_warp[32];
-    __shared__ unsigned int s_total, s_nsmall, s_nbig, s_max, s_nonempty, s_dropped;
+    __shared__ unsigned int s_total, s_nsmall, s_nbig, s_max, s_nonempty, s_dropped, s_segbase;
     __shared__ unsigned long long s_base;
+    __shared__ unsigned int s_hist[kSizeClasses], s_start[kSizeClasses], s_hseg[kSizeClasses], s_sseg[kSizeClasses];
     const int t = threadIdx.x;
     const int ipt = (a.n + kScanThreads - 1) / kScanThreads;
     const int lo = min(a.n, t * ipt), hi = min(a.n, lo + ipt);
@@ -40,6 +62,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(ScanArgs a) {
         sum += c; mx = max(mx, c); ne += (c != 0);
     }
     if (t == 0) { s_nsmall = 0; s_nbig = 0; s_max = 0; s_nonempty = 0; }
+    if (t < kSizeClasses) { s_hist[t] = 0; s_hseg[t] = 0; }
     // block exclusive scan of `sum`
     unsigned int inc = sum;
 #pragma unroll
@@ -62,30 +85,42 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(ScanArgs a) {
     __syncthreads();
     const unsigned int excl = inc - sum + s_warp[t >> 5];
     if (t == 0) {
+        if (a.first_chunk) {
+            a.header->inst_required = 0; a.header->capacity = a.capacity; a.header->overflow = 0;
+            a.header->max_tile_instances = 0; a.header->nonempty_tiles = 0; a.header->pad = 0;
+            a.header->inst_cursor = 0;
+        }
         const unsigned long long base = a.header->inst_cursor;
         const unsigned long long total = s_total;
         a.header->inst_required += total;
         const bool fits = base + total <= a.header->capacity;
         s_dropped = fits ? 0u : 1u;
         s_base = base;
+        s_segbase = a.seg_region + static_cast<unsigned int>(base / kSegment);
         if (fits) a.header->inst_cursor = base + total; else a.header->overflow = 1u;
     }
     __syncthreads();
     const bool dropped = s_dropped != 0;
+    const int full_class = size_class(kSegment);
     unsigned int run = static_cast<unsigned int>(s_base) + excl;
     for (int k = lo; k < hi; ++k) {
-        const unsigned int c = a.tile_cnt[k];
+        unsigned int c = a.tile_cnt[k];
         a.cursor[k] = 0;
         if (dropped) {                            // render(s) emitted as background; reported via the status block
             a.tile_cnt[k] = 0;
             a.tile_off[k] = static_cast<unsigned int>(s_base);
-            continue;
+            c = 0;
+        } else {
+            a.tile_off[k] = run;
+            run += c;
         }
-        a.tile_off[k] = run;
-        run += c;
+        atomicAdd(&s_hist[size_class(c)], 1u);
         if (c != 0) {
             if (c <= static_cast<unsigned int>(kSmallSortCap)) a.work_small[atomicAdd(&s_nsmall, 1u)] = k;
             else a.work_big[atomicAdd(&s_nbig, 1u)] = k;
+            const unsigned int nfull = c / kSegment, rem = c - nfull * kSegment;
+            if (nfull) atomicAdd(&s_hseg[full_class], nfull);
+            if (rem) atomicAdd(&s_hseg[size_class(rem)], 1u);
         }
     }
     atomicMax(&s_max, mx);
@@ -100,84 +135,33 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(ScanArgs a) {
             a.header->max_tile_instances = max(a.header->max_tile_instances, s_max);
             a.header->nonempty_tiles += s_nonempty;
         }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ blend work lists
-struct WorkArgs {
-    int n;                            // tiles in the chunk
-    const unsigned int* tile_cnt;     // chunk slice
-    unsigned int *work_blend, *work_empty;
-    WorkCounts* wc;
-};
-
-constexpr int kSizeClasses = 66;      // 2 * (bit length of the count) + next-lower bit; class 0 = empty
-
-__device__ __forceinline__ int size_class(unsigned int c) {
-    if (c == 0) return 0;
-    const int msb = 31 - __clz(c);
-    const int half = msb ? int((c >> (msb - 1)) & 1u) : 0;
-    return 2 * (msb + 1) + half;
-}
-
-// Non-empty tiles ordered by descending size class (longest-processing-time-first for the persistent blend kernels)
-// and the list of empty tiles (background only).  One CTA; the chunk has at most a few 10^4 tiles.
-__global__ void __launch_bounds__(kScanThreads) worklist_kernel(WorkArgs a) {
-    __shared__ unsigned int s_hist[kSizeClasses], s_start[kSizeClasses];
-    const int t = threadIdx.x;
-    if (t < kSizeClasses) s_hist[t] = 0;
-    __syncthreads();
-    for (int k = t; k < a.n; k += kScanThreads) atomicAdd(&s_hist[size_class(a.tile_cnt[k])], 1u);
-    __syncthreads();
-    if (t == 0) {
-        unsigned int run = 0;
-        for (int c = kSizeClasses - 1; c >= 1; --c) { s_start[c] = run; run += s_hist[c]; }
+        unsigned int r1 = 0, r2 = 0;
+        for (int c = kSizeClasses - 1; c >= 1; --c) {
+            s_start[c] = r1; r1 += s_hist[c];
+            s_sseg[c] = r2; r2 += s_hseg[c];
+        }
         s_start[0] = 0;
-        a.wc->n_blend = run;
+        a.wc->n_blend = r1;
         a.wc->n_empty = s_hist[0];
         a.wc->blend_cursor = 0;
         a.wc->empty_cursor = 0;
+        a.plan->n_seg = r2;
+        a.plan->seg_base = s_segbase;
+        a.plan->seg_cursor = 0;
     }
     __syncthreads();
-    for (int k = t; k < a.n; k += kScanThreads) {
-        const int c = size_class(a.tile_cnt[k]);
-        const unsigned int pos = atomicAdd(&s_start[c], 1u);
-        if (c == 0) a.work_empty[pos] = k; else a.work_blend[pos] = k;
-    }
-}
-
-// Backward work list: every tile list is cut into segments of kSegment records; items are (tile, segment) pairs
-// ordered by descending size class of the segment length (all full segments first).
-__global__ void __launch_bounds__(kScanThreads) worklist_segments_kernel(WorkArgs a, uint2* work_seg) {
-    __shared__ unsigned int s_hist[kSizeClasses], s_start[kSizeClasses];
-    const int t = threadIdx.x;
-    const int full_class = size_class(kSegment);
-    if (t < kSizeClasses) s_hist[t] = 0;
-    __syncthreads();
-    for (int k = t; k < a.n; k += kScanThreads) {
-        const unsigned int c = a.tile_cnt[k];
-        if (c == 0) continue;
-        const unsigned int nfull = c / kSegment, rem = c - nfull * kSegment;
-        if (nfull) atomicAdd(&s_hist[full_class], nfull);
-        if (rem) atomicAdd(&s_hist[size_class(rem)], 1u);
-    }
-    __syncthreads();
-    if (t == 0) {
-        unsigned int run = 0;
-        for (int c = kSizeClasses - 1; c >= 1; --c) { s_start[c] = run; run += s_hist[c]; }
-        a.wc->n_seg = run;
-        a.wc->seg_cursor = 0;
-    }
-    __syncthreads();
-    for (int k = t; k < a.n; k += kScanThreads) {
-        const unsigned int c = a.tile_cnt[k];
-        if (c == 0) continue;
+    uint2* work_seg = a.work_seg + s_segbase;
+    for (int k = lo; k < hi; ++k) {
+        const unsigned int c = dropped ? 0u : a.tile_cnt[k];
+        const unsigned int pos = atomicAdd(&s_start[size_class(c)], 1u);
+        if (c == 0) { a.work_empty[pos] = k; continue; }
+        a.work_blend[pos] = k;
         const unsigned int nfull = c / kSegment, rem = c - nfull * kSegment;
         if (nfull) {
-            const unsigned int pos = atomicAdd(&s_start[full_class], nfull);
-            for (unsigned int s = 0; s < nfull; ++s) work_seg[pos + s] = make_uint2(unsigned(k), s);
+            const unsigned int sp = atomicAdd(&s_sseg[full_class], nfull);
+            for (unsigned int sgi = 0; sgi < nfull; ++sgi) work_seg[sp + sgi] = make_uint2(unsigned(k), sgi);
         }
-        if (rem) work_seg[atomicAdd(&s_start[size_class(rem)], 1u)] = make_uint2(unsigned(k), nfull);
+        if (rem) work_seg[atomicAdd(&s_sseg[size_class(rem)], 1u)] = make_uint2(unsigned(k), nfull);
     }
 }
 
@@ -207,13 +191,22 @@ __device__ __forceinline__ void block_minmax(unsigned long long& mn, unsigned lo
     __syncthreads();                               // s_red may still be read from a previous use
     if ((threadIdx.x & 31) == 0) { s_red[2 * w] = mn; s_red[2 * w + 1] = mx; }
     __syncthreads();
-    unsigned long long rmn = s_red[0], rmx = s_red[1];
+    if (w == 0) {                                  // second stage: one warp reduces the per-warp results
+        const int l = threadIdx.x;
+        unsigned long long rmn = l < THREADS / 32 ? s_red[2 * l] : ~0ull;
+        unsigned long long rmx = l < THREADS / 32 ? s_red[2 * l + 1] : 0ull;
 #pragma unroll
-    for (int k = 1; k < THREADS / 32; ++k) {
-        rmn = s_red[2 * k] < rmn ? s_red[2 * k] : rmn;
-        rmx = s_red[2 * k + 1] > rmx ? s_red[2 * k + 1] : rmx;
+        for (int d = 16; d > 0; d >>= 1) {
+            const unsigned long long a = __shfl_xor_sync(0xffffffffu, rmn, d);
+            const unsigned long long b = __shfl_xor_sync(0xffffffffu, rmx, d);
+            rmn = a < rmn ? a : rmn;
+            rmx = b > rmx ? b : rmx;
+        }
+        if (l == 0) { s_red[2 * (THREADS / 32)] = rmn; s_red[2 * (THREADS / 32) + 1] = rmx; }
     }
-    mn = rmn; mx = rmx;
+    __syncthreads();
+    mn = s_red[2 * (THREADS / 32)];
+    mx = s_red[2 * (THREADS / 32) + 1];
 }
 
 // In-place exclusive scan of hist[NB] (NB = THREADS * PER).
@@ -250,7 +243,10 @@ __device__ __forceinline__ void block_exclusive_scan(unsigned int* hist, unsigne
 }
 
 // Sorts the n keys of one tile, writes ids + gathered records.  kb: n-element key buffer (shared or global).
-template <int THREADS, int NB>
+// KPT > 0: the tile has at most THREADS * KPT keys and every thread keeps its keys in registers, so the three passes
+// over the unsorted keys (range, histogram, scatter) cost ONE exposed global-memory latency instead of three (the
+// per-tile sort is a latency chain, not a bandwidth problem); KPT == 0 re-reads the keys from global memory.
+template <int THREADS, int NB, int KPT>
 __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local, unsigned long long* kb,
                                               bool kb_in_rec0, unsigned int* hist, unsigned int* s_warp,
                                               unsigned long long* s_red) {
@@ -260,14 +256,28 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
     const unsigned int n = a.tile_cnt[tg];
     const size_t off = a.tile_off[tg];
     const unsigned long long* keys = a.keys + off;
+    constexpr int KR = KPT > 0 ? KPT : 1;
+    unsigned long long kr[KR];
 
     // 0. key range
     unsigned long long mn = ~0ull, mx = 0ull;
-    for (unsigned int k = t; k < n; k += THREADS) {
-        const unsigned long long key = keys[k];
-        mn = key < mn ? key : mn;
-        mx = key > mx ? key : mx;
+    if (KPT > 0) {
+#pragma unroll
+        for (int j = 0; j < KR; ++j) {
+            const unsigned int k = t + j * THREADS;
+            kr[j] = k < n ? keys[k] : 0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < KR; ++j)
+            if (t + j * THREADS < n) { mn = kr[j] < mn ? kr[j] : mn; mx = kr[j] > mx ? kr[j] : mx; }
+    } else {
+        for (unsigned int k = t; k < n; k += THREADS) {
+            const unsigned long long key = keys[k];
+            mn = key < mn ? key : mn;
+            mx = key > mx ? key : mx;
+        }
     }
+    for (int k = t; k < NB; k += THREADS) hist[k] = 0;     // visible after the barriers inside block_minmax
     block_minmax<THREADS>(mn, mx, s_red);
     const unsigned long long range = mx - mn;
     const int bits = range ? 64 - __clzll(static_cast<long long>(range)) : 0;
@@ -276,18 +286,29 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
     const int shift = max(0, bits - LOG_NB);
 
     // 1. bucket histogram
-    for (int k = t; k < NB; k += THREADS) hist[k] = 0;
-    __syncthreads();
-    for (unsigned int k = t; k < n; k += THREADS)
-        atomicAdd(&hist[static_cast<unsigned int>((keys[k] - mn) >> shift)], 1u);
+    if (KPT > 0) {
+#pragma unroll
+        for (int j = 0; j < KR; ++j)
+            if (t + j * THREADS < n) atomicAdd(&hist[static_cast<unsigned int>((kr[j] - mn) >> shift)], 1u);
+    } else {
+        for (unsigned int k = t; k < n; k += THREADS)
+            atomicAdd(&hist[static_cast<unsigned int>((keys[k] - mn) >> shift)], 1u);
+    }
     __syncthreads();
     // 2. bucket starts
     block_exclusive_scan<THREADS, NB>(hist, s_warp);
     // 3. scatter into bucket order (arbitrary order inside a bucket); afterwards hist[b] = end of bucket b
-    for (unsigned int k = t; k < n; k += THREADS) {
-        const unsigned long long key = keys[k];
-        const unsigned int pos = atomicAdd(&hist[static_cast<unsigned int>((key - mn) >> shift)], 1u);
-        kb[pos] = key;
+    if (KPT > 0) {
+#pragma unroll
+        for (int j = 0; j < KR; ++j)
+            if (t + j * THREADS < n)
+                kb[atomicAdd(&hist[static_cast<unsigned int>((kr[j] - mn) >> shift)], 1u)] = kr[j];
+    } else {
+        for (unsigned int k = t; k < n; k += THREADS) {
+            const unsigned long long key = keys[k];
+            const unsigned int pos = atomicAdd(&hist[static_cast<unsigned int>((key - mn) >> shift)], 1u);
+            kb[pos] = key;
+        }
     }
     __syncthreads();
     // 4. exact rank inside the bucket -> final position; the owner of an element immediately gathers its 48-byte
@@ -338,10 +359,17 @@ __global__ void __launch_bounds__(kSmallSortThreads) sort_small_kernel(SortArgs 
     __shared__ unsigned long long kb[kSmallSortCap];
     __shared__ unsigned int hist[kSmallSortBuckets];
     __shared__ unsigned int s_warp[32];
-    __shared__ unsigned long long s_red[2 * (kSmallSortThreads / 32)];
+    __shared__ unsigned long long s_red[2 * (kSmallSortThreads / 32) + 2];
     const unsigned int nw = *a.work_count;
-    for (unsigned int w = blockIdx.x; w < nw; w += gridDim.x)
-        sort_one_tile<kSmallSortThreads, kSmallSortBuckets>(a, a.work[w], kb, false, hist, s_warp, s_red);
+    for (unsigned int w = blockIdx.x; w < nw; w += gridDim.x) {
+        const int tile_local = a.work[w];
+        const unsigned int n = a.tile_cnt[size_t(a.render_base) * a.num_tiles + tile_local];
+        if (n <= 4u * kSmallSortThreads)
+            sort_one_tile<kSmallSortThreads, kSmallSortBuckets, 4>(a, tile_local, kb, false, hist, s_warp, s_red);
+        else
+            sort_one_tile<kSmallSortThreads, kSmallSortBuckets, kSmallSortCap / kSmallSortThreads>(
+                a, tile_local, kb, false, hist, s_warp, s_red);
+    }
 }
 
 __global__ void __launch_bounds__(kBigSortThreads) sort_big_kernel(SortArgs a) {
@@ -349,7 +377,7 @@ __global__ void __launch_bounds__(kBigSortThreads) sort_big_kernel(SortArgs a) {
     unsigned long long* kb_s = reinterpret_cast<unsigned long long*>(smem_raw);                 // kBigSortSmemCap
     unsigned int* hist = reinterpret_cast<unsigned int*>(kb_s + kBigSortSmemCap);               // kBigSortBuckets
     __shared__ unsigned int s_warp[32];
-    __shared__ unsigned long long s_red[2 * (kBigSortThreads / 32)];
+    __shared__ unsigned long long s_red[2 * (kBigSortThreads / 32) + 2];
     const unsigned int nw = *a.work_count;
     for (unsigned int w = blockIdx.x; w < nw; w += gridDim.x) {
         const int tile_local = a.work[w];
@@ -358,46 +386,36 @@ __global__ void __launch_bounds__(kBigSortThreads) sort_big_kernel(SortArgs a) {
         // lists that do not fit in shared memory borrow the tile's own rec0 segment (16 B/instance, not yet written)
         const bool spill = n > static_cast<unsigned int>(kBigSortSmemCap);
         unsigned long long* kb = spill ? reinterpret_cast<unsigned long long*>(a.rec0 + a.tile_off[tg]) : kb_s;
-        sort_one_tile<kBigSortThreads, kBigSortBuckets>(a, tile_local, kb, spill, hist, s_warp, s_red);
+        if (n <= 8u * kBigSortThreads)
+            sort_one_tile<kBigSortThreads, kBigSortBuckets, 8>(a, tile_local, kb, false, hist, s_warp, s_red);
+        else
+            sort_one_tile<kBigSortThreads, kBigSortBuckets, 0>(a, tile_local, kb, spill, hist, s_warp, s_red);
     }
 }
 
 }  // namespace
 
-cudaError_t launch_scan_tiles(const ChunkCtx& c) {
-    ScanArgs a;
+cudaError_t launch_plan(const ChunkCtx& c) {
+    PlanArgs a;
     const size_t base = size_t(c.render_base) * c.g.num_tiles;
     a.n = c.num_renders * c.g.num_tiles;
+    a.first_chunk = c.render_base == 0 ? 1 : 0;
+    a.capacity = c.p->max_instances;
+    // every chunk owns the slots [render_base * T + chunk_index + instances before it / kSegment, ...): a chunk with
+    // n tiles and m instances emits at most n + m / kSegment items
+    a.seg_region = static_cast<unsigned int>(base + size_t(c.chunk_index));
     a.tile_cnt = c.tile_cnt + base;
     a.tile_off = c.tile_off + base;
     a.cursor = c.cursor;
     a.header = c.header;
     a.wc = c.work_counts;
+    a.plan = c.plan;
     a.work_small = c.work_small;
     a.work_big = c.work_big;
-    scan_tiles_kernel<<<1, kScanThreads, 0, c.stream>>>(a);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_worklist(const ChunkCtx& c) {
-    WorkArgs a;
-    a.n = c.num_renders * c.g.num_tiles;
-    a.tile_cnt = c.tile_cnt + size_t(c.render_base) * c.g.num_tiles;
     a.work_blend = c.work_blend;
     a.work_empty = c.work_empty;
-    a.wc = c.work_counts;
-    worklist_kernel<<<1, kScanThreads, 0, c.stream>>>(a);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_worklist_segments(const ChunkCtx& c) {
-    WorkArgs a;
-    a.n = c.num_renders * c.g.num_tiles;
-    a.tile_cnt = c.tile_cnt + size_t(c.render_base) * c.g.num_tiles;
-    a.work_blend = nullptr;
-    a.work_empty = nullptr;
-    a.wc = c.work_counts;
-    worklist_segments_kernel<<<1, kScanThreads, 0, c.stream>>>(a, c.work_seg);
+    a.work_seg = c.work_seg;
+    plan_kernel<<<1, kScanThreads, 0, c.stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
             a.out_alpha[size_t(r) * P + pix] = Wt;
             a.n_contrib[size_t(r) * P + pix] = last;
         }
-        if (lane == 0) {                         // diagnostics: start of block 0, duration of the slowest block
+        if (a.tile_time && lane == 0) {          // diagnostics: start of block 0, duration of the slowest block
             const unsigned long long now = global_timer_ns();
             if (blk == 0) a.tile_time[tg].x = (unsigned int)t_begin;
             atomicMax(&a.tile_time[tg].y, (unsigned int)(now - t_begin));
@@ -471,8 +471,8 @@ struct BwdArgs {
     size_t plane;
     const float4* ck0;            // forward checkpoints (sgr_common.cuh::kSegment)
     const float* ck1;
-    const uint2* work_seg;        // (chunk-local tile, segment) items, longest first
-    WorkCounts* wc;
+    const uint2* work_seg;        // all chunks' (chunk-local tile, segment) items; this chunk's start at plan->seg_base
+    ChunkPlan* plan;
     const float* dL_scale;        // device scalar multiplying dL_dcolor, or NULL
 };
 
@@ -490,7 +490,8 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
     BwdSmem& sm = reinterpret_cast<BwdSmem*>(smem_raw)[warp];
     const size_t P = size_t(a.g.H) * a.g.W;
     const float bg0 = a.bg[0], bg1 = a.bg[1], bg2 = a.bg[2];
-    const unsigned int n_items = a.wc->n_seg * kBlocksPerTile;
+    const unsigned int n_items = a.plan->n_seg * kBlocksPerTile;
+    const uint2* work_seg = a.work_seg + a.plan->seg_base;
     const float ddelx_dx = 0.5f * float(a.g.W), ddely_dy = 0.5f * float(a.g.H);
     const float gscale = a.dL_scale ? *a.dL_scale : 1.0f;
     if (lane == 0) {
@@ -509,9 +510,9 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
     // and for lane = (trip, quarter) pairs reading one pixel of their quarter (phase C).
 
     for (;;) {
-        const unsigned int item = pop_item(&a.wc->seg_cursor, n_items, lane);
+        const unsigned int item = pop_item(&a.plan->seg_cursor, n_items, lane);
         if (item == 0xffffffffu) break;
-        const uint2 ws = a.work_seg[item / kBlocksPerTile];
+        const uint2 ws = work_seg[item / kBlocksPerTile];
         const unsigned int tile_local = ws.x;
         const unsigned int lo = ws.y * unsigned(kSegment);
         const int blk = item % kBlocksPerTile;
@@ -789,7 +790,7 @@ cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out
     a.rec0 = c.rec0; a.rec1 = c.rec1; a.rec2 = c.rec2; a.bg = c.p->bg; a.n_contrib = c.n_contrib;
     a.rec0_words = reinterpret_cast<unsigned int*>(c.rec0);
     a.refine_masks = (c.p->flags & SGR_FLAG_FORWARD_ONLY) ? 0 : 1;
-    a.tile_time = c.tile_time;
+    a.tile_time = (c.p->flags & SGR_FLAG_TILE_TIMING) ? c.tile_time : nullptr;
     a.out_color = out_color; a.out_depth = out_depth; a.out_alpha = out_alpha;
     a.ck0 = c.ck0; a.ck1 = c.ck1;
     a.work_blend = c.work_blend; a.work_empty = c.work_empty; a.wc = c.work_counts;
@@ -821,7 +822,7 @@ cudaError_t launch_blend_backward(const ChunkCtx& c, const float* out_alpha, con
     a.sorted_ids = c.sorted_ids; a.rec0 = c.rec0; a.rec1 = c.rec1; a.rec2 = c.rec2; a.bg = c.p->bg;
     a.n_contrib = c.n_contrib; a.out_alpha = out_alpha; a.dL_dcolor = dL_dcolor; a.dL_ddepth = dL_ddepth;
     a.dL_dalpha = dL_dalpha; a.accum = c.accum; a.plane = size_t(c.num_renders) * c.g.N;
-    a.ck0 = c.ck0; a.ck1 = c.ck1; a.work_seg = c.work_seg; a.wc = c.work_counts; a.dL_scale = c.dL_scale;
+    a.ck0 = c.ck0; a.ck1 = c.ck1; a.work_seg = c.work_seg; a.plan = c.plan; a.dL_scale = c.dL_scale;
     constexpr size_t smem = sizeof(BwdSmem) * kWarpsPerCta;
     const long long items = (long long)c.num_renders * c.g.num_tiles * kBlocksPerTile;
     const long long want = (items + kWarpsPerCta - 1) / kWarpsPerCta;

@@ -33,13 +33,18 @@ struct alignas(256) StateHeader {
 };
 static_assert(sizeof(SgrStatus) == 32, "SgrStatus layout is part of the ABI");
 
+// Backward work list of one chunk, planned by the forward (kept in `state`): items work_seg[seg_base .. + n_seg).
+struct ChunkPlan {
+    unsigned int n_seg, seg_base, seg_cursor, pad;
+};
+
 // Layout of `state` (kept forward -> backward) for a problem shape.
 struct StateLayout {
-    uint64_t header, tile_off, tile_cnt, tile_time, n_contrib, sorted_ids, rec0, rec1, rec2, ck0, ck1, total;
+    uint64_t header, tile_off, tile_cnt, tile_time, n_contrib, sorted_ids, rec0, rec1, rec2, ck0, ck1, plan, work_seg, total;
 };
 // Layout of `scratch` (valid only inside one call).
 struct ScratchLayout {
-    uint64_t keys, g0, g1, g2, rect, cursor, work_small, work_big, work_blend, work_empty, work_seg, work_counts, loss_part, accum, total;
+    uint64_t keys, g0, g1, g2, rect, cursor, work_small, work_big, work_blend, work_empty, work_counts, loss_part, accum, total;
 };
 
 __host__ __device__ inline uint64_t align_up(uint64_t x, uint64_t a = 256) { return (x + a - 1) / a * a; }
@@ -64,6 +69,8 @@ inline StateLayout make_state_layout(int B, int V, int N, int H, int W, uint64_t
     L.rec2 = o;        o = align_up(o + cap * 16);
     L.ck0 = o;         o = align_up(o + ckpt_slots(cap) * kCkptPerSlot * 16);   // (T, C0, C1, C2) per pixel and slot
     L.ck1 = o;         o = align_up(o + ckpt_slots(cap) * kCkptPerSlot * 4);    // D
+    L.plan = o;        o = align_up(o + R * sizeof(ChunkPlan));                 // one per chunk (at most R chunks)
+    L.work_seg = o;    o = align_up(o + (R * T + cap / kSegment + R + 1) * 8);  // backward (tile, segment) items
     L.total = o;
     return L;
 }
@@ -85,7 +92,6 @@ inline ScratchLayout make_scratch_layout(int B, int V, int N, int H, int W, uint
     L.work_big = o;    o = align_up(o + Rc * T * 4);
     L.work_blend = o;  o = align_up(o + Rc * T * 4);
     L.work_empty = o;  o = align_up(o + Rc * T * 4);
-    L.work_seg = o;    o = align_up(o + (Rc * T + cap / kSegment + 1) * 8);       // (tile, segment) backward items
     L.work_counts = o; o = align_up(o + 256);
     L.loss_part = o;   o = align_up(o + Rc * T * 8 * 4);                           // fused loss: one partial per work item
     L.accum = o;       o = align_up(o + Rc * N * 4 * kAccumPlanes);
@@ -103,8 +109,6 @@ struct WorkCounts {
     unsigned int n_empty;      // tiles without instances (background only)
     unsigned int blend_cursor; // dynamic work queue heads of the persistent blend kernels
     unsigned int empty_cursor;
-    unsigned int n_seg;        // backward items: (tile, segment) pairs, longest first
-    unsigned int seg_cursor;
 };
 
 constexpr int kSmallSortCap = 4096;       // instances sorted in a 40 KB shared-memory CTA
@@ -203,13 +207,15 @@ struct ChunkCtx {
     float4 *rec0, *rec1, *rec2;   // [cap]
     float4* ck0;              // [ckpt_slots][256] forward checkpoints (T, C0, C1, C2)
     float* ck1;               // [ckpt_slots][256] forward checkpoints D
+    ChunkPlan* plan;          // this chunk's backward plan
+    uint2* work_seg;          // [R*T + cap/kSegment + R + 1] backward items of all chunks
+    int chunk_index;
     // scratch
     unsigned long long* keys; // [cap]
     float4 *g0, *g1, *g2;     // [Rc*N]
     uint2* rect;              // [Rc*N] packed tile rectangle
     unsigned int* cursor;     // [Rc*T]
     unsigned int *work_small, *work_big, *work_blend, *work_empty;
-    uint2* work_seg;          // [Rc*T + cap/kSegment + 1]
     WorkCounts* work_counts;
     float* loss_part;         // [Rc*T*8] fused-loss partial sums, one per (render, tile, pixel block)
     float* accum;             // [kAccumPlanes][Rc*N]
@@ -222,9 +228,7 @@ struct ChunkCtx {
 };
 
 cudaError_t launch_preprocess(const ChunkCtx& c, int32_t* radii);
-cudaError_t launch_scan_tiles(const ChunkCtx& c);
-cudaError_t launch_worklist(const ChunkCtx& c);     // forward: blend/empty tile work lists from tile_cnt
-cudaError_t launch_worklist_segments(const ChunkCtx& c);   // backward: (tile, segment) work list from tile_cnt
+cudaError_t launch_plan(const ChunkCtx& c);   // tile offsets, sort / blend / backward-segment work lists, status header
 cudaError_t launch_scatter(const ChunkCtx& c);
 cudaError_t launch_sort_tiles(const ChunkCtx& c);
 cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out_depth, float* out_alpha);
