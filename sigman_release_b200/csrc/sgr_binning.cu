@@ -9,6 +9,8 @@
 //
 // Per-tile sort = one MSD bucket pass over the tile's key range in shared memory followed by an exact rank inside
 // each (small) bucket; linear work in the list length, no power-of-two padding.
+#include <cstdlib>
+
 #include "sgr_common.cuh"
 
 namespace sgr {
@@ -448,6 +450,15 @@ cudaError_t launch_sort_tiles(const ChunkCtx& c) {
         if ((e = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking)) != cudaSuccess) return e;
         if ((e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
         if ((e = cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    static int mode = -1;      // experiment switch: 0 concurrent (default), 1 serial, 2 small only, 3 big only
+    if (mode < 0) { const char* m = getenv("SGR_SORT_MODE"); mode = m ? atoi(m) : 0; }
+    if (mode != 0) {
+        a.work = c.work_big; a.work_count = &c.work_counts->n_big;
+        if (mode != 2) sort_big_kernel<<<min(num_sms, total_tiles), kBigSortThreads, big_smem, c.stream>>>(a);
+        a.work = c.work_small; a.work_count = &c.work_counts->n_small;
+        if (mode != 3) sort_small_kernel<<<min(num_sms * 5, total_tiles), kSmallSortThreads, 0, c.stream>>>(a);
+        return cudaGetLastError();
     }
     if ((e = cudaEventRecord(ev_fork, c.stream)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(side, ev_fork, 0)) != cudaSuccess) return e;

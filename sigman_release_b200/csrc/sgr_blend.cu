@@ -37,7 +37,6 @@ constexpr int kWarpsPerCta = 8;
 constexpr int kBlendThreads = kWarpsPerCta * 32;
 constexpr int kBlocksPerTile = 8;              // a 16x16 tile = eight 8x4 pixel blocks = eight work items
 constexpr int kBlockW = 8, kBlockH = 4;        // pixel block of one warp (four 4x2 quarters walk separate lists)
-constexpr int kSlots = 16;                     // forward: trips per phase pass (depth of the per-warp stash)
 constexpr int kBwdSlots = 16;                  // backward: trips per phase pass
 constexpr unsigned int kFull = 0xffffffffu;
 
@@ -95,13 +94,13 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 template <int kStashes, int kDepth, int kNumStages>
 struct WarpSmem {
     static constexpr int stages = kNumStages;
-    float4 r0[kNumStages][kBatch];
-    float4 r1[kNumStages][kBatch];
-    float4 r2[kNumStages][kBatch];
+    float4 r0[kNumStages][kBatch + 1];          // slot kBatch of every stage = the sentinel record (never blends)
+    float4 r1[kNumStages][kBatch + 1];
+    float4 r2[kNumStages][kBatch + 1];
     float stash[kStashes][kDepth][32];
     float dpix[4][32];                          // backward: dL/dcolor (3) and dL/ddepth of the block's pixels
     unsigned char list[4][kBatch];              // per quarter: batch-local indices of the survivors (ascending)
-    unsigned int hit[kBatch];                   // forward: byte q of word j != 0 <=> quarter q blended record j
+    unsigned int hit[kBatch + 1];               // forward: byte q of word j != 0 <=> quarter q blended record j
     uint64_t full[kNumStages];
 };
 
@@ -109,9 +108,16 @@ struct WarpSmem {
 // 32 records per round (lane = record) read their precomputed quarter mask (rec0.z, built once per instance by the
 // tile sort, sgr_common.cuh::quarter_mask), one ballot per quarter, warp-parallel compaction of the survivors'
 // batch-local indices into list[quarter][...] (ascending).  Returns the four survivor counts.
+template <bool kPadSentinel>
 __device__ __forceinline__ uint4 cull_batch(const float4* r0, unsigned int m, int blk, unsigned char (*list)[kBatch],
                                             int lane) {
     const unsigned int lt = (1u << lane) - 1u;
+    if (kPadSentinel) {           // every list entry the compaction does not overwrite points at the sentinel record
+        unsigned int* lw = reinterpret_cast<unsigned int*>(&list[0][0]);
+        const unsigned int fill = kBatch * 0x01010101u;
+        lw[lane] = fill; lw[lane + 32] = fill;
+        __syncwarp();
+    }
     const unsigned int* words = reinterpret_cast<const unsigned int*>(r0);
     unsigned int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
 #pragma unroll
@@ -211,7 +217,7 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-using FwdSmem = WarpSmem<1, kSlots, kFwdStages>;
+using FwdSmem = WarpSmem<1, 1, kFwdStages>;      // the forward needs no stash
 using BwdSmem = WarpSmem<3, kBwdSlots, kBwdStages>;
 
 #ifndef SGR_FWD_MIN_CTAS
@@ -235,12 +241,16 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
     __syncwarp();
     const int qsel = ((lane >> 2) & 1) | ((lane >> 3) & 2);        // 4x2 pixel quarter of this lane: x half | 2 * y half
     const unsigned int qmask = 0x00000f0fu << ((lane & 4) | (lane & 16));   // the quarter's 8 lanes
-    float (*stash)[32] = sm.stash[0];
     const unsigned char* mylist = sm.list[qsel];
     unsigned int issued = 0, consumed = 0;       // ring counters (warp-uniform)
     const bool refine = a.refine_masks != 0;
-    unsigned char* hit_bytes = reinterpret_cast<unsigned char*>(sm.hit) + qsel - 4;   // indexed with 4 * (j + 1)
+    unsigned char* hit_bytes = reinterpret_cast<unsigned char*>(sm.hit) + qsel;       // indexed with 4 * j
     sm.hit[lane] = 0u; sm.hit[lane + 32] = 0u;
+    if (lane < kFwdStages) {      // the sentinel record: threshold +inf -> never valid, alpha 0, colour 0
+        sm.r0[lane][kBatch] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0x7f800000));
+        sm.r1[lane][kBatch] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        sm.r2[lane][kBatch] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
     __syncwarp();
 
     // ---------------- blocks of tiles with instances
@@ -291,73 +301,57 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
             const float4* r0 = sm.r0[s];
             const float4* r1 = sm.r1[s];
             const float4* r2 = sm.r2[s];
-            const uint4 cnt = cull_batch(r0, m, blk, sm.list, lane);
+            const uint4 cnt = cull_batch<true>(r0, m, blk, sm.list, lane);
             // quarters whose 8 pixels are all finished need no further evaluation
             const unsigned int dmask = __ballot_sync(kFull, done);
             const unsigned int my_n = ((dmask & qmask) == qmask) ? 0u : (qsel == 0 ? cnt.x : qsel == 1 ? cnt.y : qsel == 2 ? cnt.z : cnt.w);
             const int total = int(__reduce_max_sync(kFull, my_n));
-            for (int base = 0; base < total; base += kSlots) {
-                const int trips = min(kSlots, total - base);
-                // ---- phase A: alpha of the next `trips` survivors of this lane's quarter.  Trips are independent;
-                // blocks of four are written load-first so the compiler interleaves the four dependent chains.
-                for (int t0 = 0; t0 < trips; t0 += 4) {
-                    const unsigned int packed = *reinterpret_cast<const unsigned int*>(mylist + base + t0);
-                    float4 q0[4], q1[4];
-                    bool has[4];
+            // One trip = every quarter evaluates its next survivor (lane = pixel).  Four trips per iteration, written
+            // load-first so that the four independent alpha chains interleave ahead of the sequential compositing
+            // recurrence.  List entries past a quarter's count point at the sentinel record (alpha = 0): no bounds
+            // checks in the loop.  Quarters that are finished still walk (ok = false for all their lanes).
+            unsigned int lastj = 0xffffffffu;
+            for (int t0 = 0; t0 < total; t0 += 4) {
+                const unsigned int packed = *reinterpret_cast<const unsigned int*>(mylist + t0);
+                float4 q0[4], q1[4], q2[4];
+                unsigned int jj[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        has[u] = unsigned(base + t0 + u) < my_n;
-                        const unsigned int j = has[u] ? ((packed >> (8 * u)) & 0xffu) : 0u;
-                        q0[u] = r0[j];
-                        q1[u] = r1[j];
-                    }
-                    float al[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float dx = q0[u].x - pxf, dy = q0[u].y - pyf;
-                        const float power = gauss_power(q1[u].x, q1[u].y, q1[u].z, dx, dy);
-                        const bool valid = has[u] && !(power > 0.0f) && !(power < q0[u].w);
-                        const float alpha = fminf(kAlphaMax, q1[u].w * exp_core(valid ? power : 0.0f));
-                        al[u] = valid ? alpha : 0.0f;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) stash[t0 + u][lane] = al[u];
+                for (int u = 0; u < 4; ++u) {
+                    jj[u] = (packed >> (8 * u)) & 0xffu;
+                    q0[u] = r0[jj[u]];
+                    q1[u] = r1[jj[u]];
+                    q2[u] = r2[jj[u]];
                 }
-                __syncwarp();
-                // ---- phase B: front-to-back compositing (the sequential part), predicated, loads hoisted
-                for (int t0 = 0; t0 < trips; t0 += 4) {
-                    const unsigned int packed = *reinterpret_cast<const unsigned int*>(mylist + base + t0);
-                    float al[4];
-                    float4 q2[4];
-                    unsigned int idx[4];
+                float al[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const unsigned int j = (unsigned(base + t0 + u) < my_n) ? ((packed >> (8 * u)) & 0xffu) : 0u;
-                        al[u] = stash[t0 + u][lane];
-                        q2[u] = r2[j];
-                        idx[u] = cbase + j + 1;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const bool ok = !done && !(al[u] < kAlphaMin);
-                        const float test_T = __fmaf_rn(-al[u], T, T);
-                        const bool stop = ok && (test_T < kTMin);
-                        const bool blend = ok && !stop;
-                        const float w = blend ? al[u] * T : 0.0f;      // adding c * 0 leaves the sums bit-unchanged
-                        C0 = __fmaf_rn(q2[u].x, w, C0);
-                        C1 = __fmaf_rn(q2[u].y, w, C1);
-                        C2 = __fmaf_rn(q2[u].z, w, C2);
-                        Wt += w;
-                        D = __fmaf_rn(q2[u].w, w, D);
-                        T = blend ? test_T : T;
-                        last = blend ? idx[u] : last;
-                        done = done || stop;
-                        // same-value stores of the quarter's lanes to one byte: benign
-                        if (refine && blend) hit_bytes[4u * (idx[u] - cbase)] = 1;
-                    }
+                for (int u = 0; u < 4; ++u) {
+                    const float dx = q0[u].x - pxf, dy = q0[u].y - pyf;
+                    const float power = gauss_power(q1[u].x, q1[u].y, q1[u].z, dx, dy);
+                    const bool valid = !(power > 0.0f) && !(power < q0[u].w);
+                    const float alpha = fminf(kAlphaMax, q1[u].w * exp_core(valid ? power : 0.0f));
+                    al[u] = valid ? alpha : 0.0f;
                 }
-                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const bool ok = !done && !(al[u] < kAlphaMin);
+                    const float test_T = __fmaf_rn(-al[u], T, T);
+                    const bool stop = ok && (test_T < kTMin);
+                    const bool blend = ok && !stop;
+                    const float w = blend ? al[u] * T : 0.0f;      // adding c * 0 leaves the sums bit-unchanged
+                    C0 = __fmaf_rn(q2[u].x, w, C0);
+                    C1 = __fmaf_rn(q2[u].y, w, C1);
+                    C2 = __fmaf_rn(q2[u].z, w, C2);
+                    Wt += w;
+                    D = __fmaf_rn(q2[u].w, w, D);
+                    T = blend ? test_T : T;
+                    lastj = blend ? jj[u] : lastj;
+                    done = done || stop;
+                    // same-value stores of the quarter's lanes to one byte: benign
+                    if (refine && blend) hit_bytes[4u * jj[u]] = 1;
+                }
             }
+            if (lastj != 0xffffffffu) last = cbase + lastj + 1u;
+            __syncwarp();
             // Mask refinement for the backward pass: clear the (block, quarter) bits of the records that no pixel of
             // the quarter blended (alpha test, finished pixels) — the backward walk culls on the same word.
 #ifdef SGR_EXP_NO_BLOCK
@@ -589,7 +583,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
             const float4* r0 = sm.r0[s];
             const float4* r1 = sm.r1[s];
             const float4* r2 = sm.r2[s];
-            const uint4 cnt = cull_batch(r0, m, blk, sm.list, lane);
+            const uint4 cnt = cull_batch<false>(r0, m, blk, sm.list, lane);
             const unsigned int my_n = qsel == 0 ? cnt.x : qsel == 1 ? cnt.y : qsel == 2 ? cnt.z : cnt.w;
             const int total = int(max(max(cnt.x, cnt.y), max(cnt.z, cnt.w)));
             // trip t of the batch handles the quarter's survivor number (my_n - 1 - t): back to front
