@@ -107,12 +107,14 @@ struct WarpSmem {
 // Cull a batch of m <= kBatch records against the four 4x2 quarters of the warp's 8x4 pixel block `blk` of the tile:
 // 32 records per round (lane = record) read their precomputed quarter mask (rec0.z, built once per instance by the
 // tile sort, sgr_common.cuh::quarter_mask), one ballot per quarter, warp-parallel compaction of the survivors'
-// batch-local indices into list[quarter][...] (ascending).  Returns the four survivor counts.
-template <bool kPadSentinel>
+// batch-local indices into list[quarter][...] (ascending; descending with kReverse — the backward walks back to front);
+// unused list entries point at the sentinel record.  Returns the four survivor counts.
+template <bool kReverse>
 __device__ __forceinline__ uint4 cull_batch(const float4* r0, unsigned int m, int blk, unsigned char (*list)[kBatch],
                                             int lane) {
-    const unsigned int lt = (1u << lane) - 1u;
-    if (kPadSentinel) {           // every list entry the compaction does not overwrite points at the sentinel record
+    // lanes before (ascending) / after (descending) this one
+    const unsigned int lt = kReverse ? ~((2u << lane) - 1u) : (1u << lane) - 1u;
+    {                             // every list entry the compaction does not overwrite points at the sentinel record
         unsigned int* lw = reinterpret_cast<unsigned int*>(&list[0][0]);
         const unsigned int fill = kBatch * 0x01010101u;
         lw[lane] = fill; lw[lane + 32] = fill;
@@ -121,8 +123,9 @@ __device__ __forceinline__ uint4 cull_batch(const float4* r0, unsigned int m, in
     const unsigned int* words = reinterpret_cast<const unsigned int*>(r0);
     unsigned int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
 #pragma unroll
-    for (unsigned int sub = 0; sub < unsigned(kBatch); sub += 32) {
-        if (sub >= m) break;
+    for (unsigned int round = 0; round < unsigned(kBatch) / 32; ++round) {
+        const unsigned int sub = kReverse ? unsigned(kBatch) - 32u * (round + 1u) : 32u * round;
+        if (sub >= m) { if (kReverse) continue; else break; }
         const unsigned int e = sub + lane;
         const unsigned int bits = (e < m) ? ((words[4 * e + 2] >> (4 * blk)) & 0xfu) : 0u;
         if (__ballot_sync(kFull, bits != 0u) == 0u) continue;     // no record of the round touches this block
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
             const float4* r0 = sm.r0[s];
             const float4* r1 = sm.r1[s];
             const float4* r2 = sm.r2[s];
-            const uint4 cnt = cull_batch<true>(r0, m, blk, sm.list, lane);
+            const uint4 cnt = cull_batch<false>(r0, m, blk, sm.list, lane);
             // quarters whose 8 pixels are all finished need no further evaluation
             const unsigned int dmask = __ballot_sync(kFull, done);
             const unsigned int my_n = ((dmask & qmask) == qmask) ? 0u : (qsel == 0 ? cnt.x : qsel == 1 ? cnt.y : qsel == 2 ? cnt.z : cnt.w);
@@ -495,6 +498,12 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
     }
     __syncwarp();
     const int qsel = ((lane >> 2) & 1) | ((lane >> 3) & 2);        // 4x2 pixel quarter of this lane: x half | 2 * y half
+    if (lane < kBwdStages) {      // the sentinel record: threshold +inf -> never valid
+        sm.r0[lane][kBatch] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0x7f800000));
+        sm.r1[lane][kBatch] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        sm.r2[lane][kBatch] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    __syncwarp();
     float (*stA)[32] = sm.stash[0];             // phase A: alpha; phase B overwrites it with dL/dalpha
     float (*stW)[32] = sm.stash[1];             // blend weight alpha * T (0 = the pixel did not blend this Gaussian)
     float (*stG)[32] = sm.stash[2];             // G = exp(power)
@@ -583,24 +592,26 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
             const float4* r0 = sm.r0[s];
             const float4* r1 = sm.r1[s];
             const float4* r2 = sm.r2[s];
-            const uint4 cnt = cull_batch<false>(r0, m, blk, sm.list, lane);
-            const unsigned int my_n = qsel == 0 ? cnt.x : qsel == 1 ? cnt.y : qsel == 2 ? cnt.z : cnt.w;
+            const uint4 cnt = cull_batch<true>(r0, m, blk, sm.list, lane);
             const int total = int(max(max(cnt.x, cnt.y), max(cnt.z, cnt.w)));
             // trip t of the batch handles the quarter's survivor number (my_n - 1 - t): back to front
             const float nTb = -T_final * bg_dot;
             for (int base = 0; base < total; base += kBwdSlots) {
                 const int trips = min(kBwdSlots, total - base);
-                // ---- phase A: alpha (0 = no blend) and G; load-first blocks of four so the chains interleave
+                // ---- phases A + B: alpha / G of four trips (independent, load-first), then the sequential per-pixel
+                // recurrences -> dL/dalpha and blend weight per trip, stashed for phase C.  The lists are descending
+                // (trip t = the quarter's t-th survivor from the back) and sentinel-padded.
                 for (int t0 = 0; t0 < trips; t0 += 4) {
-                    float4 q0[4], q1[4];
+                    const unsigned int packed = *reinterpret_cast<const unsigned int*>(mylist + base + t0);
+                    float4 q0[4], q1[4], q2[4];
                     bool has[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const int k = int(my_n) - 1 - (base + t0 + u);
-                        const unsigned int j = k >= 0 ? mylist[k] : 0u;
-                        has[u] = k >= 0 && (cbase + j < last);
+                        const unsigned int j = (packed >> (8 * u)) & 0xffu;
+                        has[u] = cbase + j < last;
                         q0[u] = r0[j];
                         q1[u] = r1[j];
+                        q2[u] = r2[j];
                     }
                     float al[4], gg[4];
 #pragma unroll
@@ -612,26 +623,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
                         const float alpha = fminf(kAlphaMax, q1[u].w * gg[u]);
                         al[u] = (valid && !(alpha < kAlphaMin)) ? alpha : 0.0f;
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int t = t0 + u;
-                        const int col = lane ^ ((t & 3) | ((t & 4) << 1));
-                        stA[t][col] = al[u];
-                        stG[t][col] = gg[u];
-                    }
-                }
-                __syncwarp();
-                // ---- phase B: the sequential per-pixel recurrences -> dL/dalpha and blend weight per trip
-                for (int t0 = 0; t0 < trips; t0 += 4) {
-                    float al[4], dl[4], wg[4];
-                    float4 q2[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int t = t0 + u;
-                        const int k = int(my_n) - 1 - (base + t);
-                        al[u] = stA[t][lane ^ ((t & 3) | ((t & 4) << 1))];
-                        q2[u] = r2[k >= 0 ? mylist[k] : 0u];
-                    }
+                    float dl[4], wg[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const float alpha = al[u];
@@ -668,6 +660,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
                         const int col = lane ^ ((t & 3) | ((t & 4) << 1));
                         stA[t][col] = dl[u];
                         stW[t][col] = wg[u];
+                        stG[t][col] = gg[u];
                     }
                 }
                 __syncwarp();
@@ -683,9 +676,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
                         const bool cvalid = pi < npairs;
                         const int cq = pi < c0n ? 0 : pi < e1 ? 1 : pi < e2 ? 2 : 3;
                         const int ct = cvalid ? pi - (cq == 0 ? 0 : cq == 1 ? c0n : cq == 2 ? e1 : e2) : 0;
-                        const unsigned int n_cq = cq == 0 ? cnt.x : cq == 1 ? cnt.y : cq == 2 ? cnt.z : cnt.w;
-                        const int k = int(n_cq) - 1 - (base + ct);
-                        const unsigned int j = cvalid ? sm.list[cq][k] : 0u;
+                        const unsigned int j = cvalid ? sm.list[cq][base + ct] : 0u;
                         const float4 q0 = r0[j];
                         const float4 q1 = r1[j];
                         const int cswz = (ct & 3) | ((ct & 4) << 1);
