@@ -69,6 +69,10 @@ typedef struct SgrProblem {
     uint64_t max_instances;      /* capacity of the instance arrays inside `state` (all renders together) */
     int32_t renders_per_chunk;   /* 0 = library default; renders processed per launch set */
     int32_t flags;               /* SGR_FLAG_* */
+    uint32_t max_tile_instances_hint; /* longest per-tile list seen for this kind of scene (SgrStatus of an earlier
+                                    call), 0 = unknown: only sizes the shared memory of the long-list sort; any value
+                                    is correct */
+    uint32_t reserved;
 } SgrProblem;
 
 /* Replaces `_C.rasterize_gaussians` (forward).  Outputs match the tuple unpacked at gs.py:99:

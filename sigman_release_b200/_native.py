@@ -46,6 +46,8 @@ class SgrProblem(ctypes.Structure):
         ("max_instances", ctypes.c_uint64),
         ("renders_per_chunk", ctypes.c_int32),
         ("flags", ctypes.c_int32),
+        ("max_tile_instances_hint", ctypes.c_uint32),
+        ("reserved", ctypes.c_uint32),
     ]
 
 

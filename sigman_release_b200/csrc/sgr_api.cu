@@ -113,8 +113,6 @@ void fill_ctx(ChunkCtx& c, const SgrProblem& p, void* state, void* scratch, cuda
     c.g2 = reinterpret_cast<float4*>(x + X.g2);
     c.rect = reinterpret_cast<uint2*>(x + X.rect);
     c.cursor = reinterpret_cast<unsigned int*>(x + X.cursor);
-    c.work_small = reinterpret_cast<unsigned int*>(x + X.work_small);
-    c.work_big = reinterpret_cast<unsigned int*>(x + X.work_big);
     c.work_blend = reinterpret_cast<unsigned int*>(x + X.work_blend);
     c.work_empty = reinterpret_cast<unsigned int*>(x + X.work_empty);
     c.work_counts = reinterpret_cast<WorkCounts*>(x + X.work_counts);

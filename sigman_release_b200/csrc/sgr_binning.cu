@@ -20,9 +20,9 @@ namespace {
 // One single-CTA kernel per chunk (replaces upstream's InclusiveSum + the num_rendered device->host copy, and plans
 // everything that depends only on the per-tile instance counts):
 //   1. exclusive scan of tile_cnt -> tile_off, instance range reserved on the device (overflow -> chunk dropped);
-//   2. sort work lists (small / big tiles);
-//   3. forward blend work list: non-empty tiles by descending size class (longest-processing-time first for the
-//      persistent blend kernel) + the list of empty tiles (background only);
+//   2. + 3. ONE work list of the non-empty tiles by descending size class: the forward blend kernel walks it longest-
+//      processing-time first, the sort kernels split it at n_big (tiles with >= kSmallSortCap instances come first);
+//      plus the list of empty tiles (background only);
 //   4. backward work list (kept in `state`): every tile list cut into segments of kSegment records, items
 //      (tile, segment) by descending size class of the segment length.
 struct PlanArgs {
@@ -36,7 +36,7 @@ struct PlanArgs {
     StateHeader* header;
     WorkCounts* wc;
     ChunkPlan* plan;
-    unsigned int *work_small, *work_big, *work_blend, *work_empty;
+    unsigned int *work_blend, *work_empty;
     uint2* work_seg;
 };
 
@@ -52,7 +52,7 @@ __device__ __forceinline__ int size_class(unsigned int c) {
 
 __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
     __shared__ unsigned int s_warp[32];
-    __shared__ unsigned int s_total, s_nsmall, s_nbig, s_max, s_nonempty, s_dropped, s_segbase;
+    __shared__ unsigned int s_total, s_max, s_nonempty, s_dropped, s_segbase;
     __shared__ unsigned long long s_base;
     __shared__ unsigned int s_hist[kSizeClasses], s_start[kSizeClasses], s_hseg[kSizeClasses], s_sseg[kSizeClasses];
     const int t = threadIdx.x;
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
         const unsigned int c = a.tile_cnt[k];
         sum += c; mx = max(mx, c); ne += (c != 0);
     }
-    if (t == 0) { s_nsmall = 0; s_nbig = 0; s_max = 0; s_nonempty = 0; }
+    if (t == 0) { s_max = 0; s_nonempty = 0; }
     if (t < kSizeClasses) { s_hist[t] = 0; s_hseg[t] = 0; }
     // block exclusive scan of `sum`
     unsigned int inc = sum;
@@ -118,8 +118,6 @@ __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
         }
         atomicAdd(&s_hist[size_class(c)], 1u);
         if (c != 0) {
-            if (c <= static_cast<unsigned int>(kSmallSortCap)) a.work_small[atomicAdd(&s_nsmall, 1u)] = k;
-            else a.work_big[atomicAdd(&s_nbig, 1u)] = k;
             const unsigned int nfull = c / kSegment, rem = c - nfull * kSegment;
             if (nfull) atomicAdd(&s_hseg[full_class], nfull);
             if (rem) atomicAdd(&s_hseg[size_class(rem)], 1u);
@@ -129,8 +127,6 @@ __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
     atomicAdd(&s_nonempty, ne);
     __syncthreads();
     if (t == 0) {
-        a.wc->n_small = s_nsmall;
-        a.wc->n_big = s_nbig;
         a.wc->chunk_instances = dropped ? 0u : s_total;
         a.wc->chunk_dropped = s_dropped;
         if (!dropped) {
@@ -143,6 +139,8 @@ __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
             s_sseg[c] = r2; r2 += s_hseg[c];
         }
         s_start[0] = 0;
+        a.wc->n_big = s_start[size_class(kSmallSortCap) - 1];    // tiles of the classes >= class(kSmallSortCap)
+        a.wc->sort_cursor = 0;
         a.wc->n_blend = r1;
         a.wc->n_empty = s_hist[0];
         a.wc->blend_cursor = 0;
@@ -176,8 +174,9 @@ struct SortArgs {
     unsigned int* sorted_ids;
     float4 *rec0, *rec1, *rec2;
     const float4 *g0, *g1, *g2;
-    const unsigned int* work;        // chunk-local tile indices
-    const unsigned int* work_count;
+    const unsigned int* work;        // chunk-local indices of the non-empty tiles, longest list first
+    WorkCounts* wc;                  // n_big: the first n_big tiles go to the big kernel; sort_cursor: small queue
+    unsigned int big_smem_keys;      // key capacity of the big kernel's shared-memory buffer
 };
 
 template <int THREADS>
@@ -362,8 +361,14 @@ __global__ void __launch_bounds__(kSmallSortThreads) sort_small_kernel(SortArgs 
     __shared__ unsigned int hist[kSmallSortBuckets];
     __shared__ unsigned int s_warp[32];
     __shared__ unsigned long long s_red[2 * (kSmallSortThreads / 32) + 2];
-    const unsigned int nw = *a.work_count;
-    for (unsigned int w = blockIdx.x; w < nw; w += gridDim.x) {
+    __shared__ unsigned int s_item;
+    const unsigned int first = a.wc->n_big, nw = a.wc->n_blend;
+    for (;;) {                                   // dynamic queue, longest lists first
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = first + atomicAdd(&a.wc->sort_cursor, 1u);
+        __syncthreads();
+        const unsigned int w = s_item;
+        if (w >= nw) break;
         const int tile_local = a.work[w];
         const unsigned int n = a.tile_cnt[size_t(a.render_base) * a.num_tiles + tile_local];
         if (n <= 4u * kSmallSortThreads)
@@ -377,18 +382,18 @@ __global__ void __launch_bounds__(kSmallSortThreads) sort_small_kernel(SortArgs 
 __global__ void __launch_bounds__(kBigSortThreads) sort_big_kernel(SortArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* kb_s = reinterpret_cast<unsigned long long*>(smem_raw);                 // kBigSortSmemCap
-    unsigned int* hist = reinterpret_cast<unsigned int*>(kb_s + kBigSortSmemCap);               // kBigSortBuckets
+    unsigned int* hist = reinterpret_cast<unsigned int*>(kb_s + a.big_smem_keys);               // kBigSortBuckets
     __shared__ unsigned int s_warp[32];
     __shared__ unsigned long long s_red[2 * (kBigSortThreads / 32) + 2];
-    const unsigned int nw = *a.work_count;
+    const unsigned int nw = a.wc->n_big;
     for (unsigned int w = blockIdx.x; w < nw; w += gridDim.x) {
         const int tile_local = a.work[w];
         const size_t tg = size_t(a.render_base) * a.num_tiles + tile_local;
         const unsigned int n = a.tile_cnt[tg];
         // lists that do not fit in shared memory borrow the tile's own rec0 segment (16 B/instance, not yet written)
-        const bool spill = n > static_cast<unsigned int>(kBigSortSmemCap);
+        const bool spill = n > a.big_smem_keys;
         unsigned long long* kb = spill ? reinterpret_cast<unsigned long long*>(a.rec0 + a.tile_off[tg]) : kb_s;
-        if (n <= 8u * kBigSortThreads)
+        if (n <= 8u * kBigSortThreads && !spill)
             sort_one_tile<kBigSortThreads, kBigSortBuckets, 8>(a, tile_local, kb, false, hist, s_warp, s_red);
         else
             sort_one_tile<kBigSortThreads, kBigSortBuckets, 0>(a, tile_local, kb, spill, hist, s_warp, s_red);
@@ -412,8 +417,6 @@ cudaError_t launch_plan(const ChunkCtx& c) {
     a.header = c.header;
     a.wc = c.work_counts;
     a.plan = c.plan;
-    a.work_small = c.work_small;
-    a.work_big = c.work_big;
     a.work_blend = c.work_blend;
     a.work_empty = c.work_empty;
     a.work_seg = c.work_seg;
@@ -426,6 +429,7 @@ cudaError_t launch_sort_tiles(const ChunkCtx& c) {
     a.N = c.g.N; a.num_tiles = c.g.num_tiles; a.tiles_x = c.g.tiles_x; a.render_base = c.render_base;
     a.tile_off = c.tile_off; a.tile_cnt = c.tile_cnt; a.keys = c.keys; a.sorted_ids = c.sorted_ids;
     a.rec0 = c.rec0; a.rec1 = c.rec1; a.rec2 = c.rec2; a.g0 = c.g0; a.g1 = c.g1; a.g2 = c.g2;
+    a.work = c.work_blend; a.wc = c.work_counts;
     static int num_sms = 0;
     static bool attr_set = false;
     if (num_sms == 0) {
@@ -434,15 +438,28 @@ cudaError_t launch_sort_tiles(const ChunkCtx& c) {
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (num_sms <= 0) num_sms = 148;
     }
-    const size_t big_smem = size_t(kBigSortSmemCap) * 8 + size_t(kBigSortBuckets) * 4;
+    // Shared-memory key buffer of the big kernel: sized from the caller's hint of the longest list (a CTA that takes
+    // the whole SM's shared memory keeps the small-tile CTAs off that SM); longer lists spill to global memory.
+    unsigned int big_keys = kBigSortSmemCap;
+    if (c.p->max_tile_instances_hint > 0) {
+        const unsigned long long want = (unsigned long long)c.p->max_tile_instances_hint * 5 / 4;
+        big_keys = unsigned(want < 8192 ? 8192 : (want > kBigSortSmemCap ? kBigSortSmemCap : want));
+    }
+    a.big_smem_keys = big_keys;
+    const size_t big_smem = size_t(big_keys) * 8 + size_t(kBigSortBuckets) * 4;
+    static int small_per_sm = 0;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(big_smem));
+        cudaError_t e = cudaFuncSetAttribute(sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             int(size_t(kBigSortSmemCap) * 8 + size_t(kBigSortBuckets) * 4));
         if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&small_per_sm, sort_small_kernel, kSmallSortThreads, 0);
+        if (e != cudaSuccess) return e;
+        if (small_per_sm <= 0) small_per_sm = 1;
         attr_set = true;
     }
     const int total_tiles = c.num_renders * c.g.num_tiles;
-    // The few long lists (one 1024-thread CTA each, latency bound) run on a side stream concurrently with the many
-    // short ones: fork after the scatter, join before the blend.
+    // The few long lists (one 1024-thread CTA each, latency bound) run concurrently with the many short ones on a
+    // side stream: fork after the scatter, join before the blend.
     static cudaStream_t side = nullptr;
     static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaError_t e;
@@ -454,23 +471,19 @@ cudaError_t launch_sort_tiles(const ChunkCtx& c) {
     static int mode = -1;      // experiment switch: 0 concurrent (default), 1 serial, 2 small only, 3 big only
     if (mode < 0) { const char* m = getenv("SGR_SORT_MODE"); mode = m ? atoi(m) : 0; }
     if (mode != 0) {
-        a.work = c.work_big; a.work_count = &c.work_counts->n_big;
         if (mode != 2) sort_big_kernel<<<min(num_sms, total_tiles), kBigSortThreads, big_smem, c.stream>>>(a);
-        a.work = c.work_small; a.work_count = &c.work_counts->n_small;
-        if (mode != 3) sort_small_kernel<<<min(num_sms * 5, total_tiles), kSmallSortThreads, 0, c.stream>>>(a);
+        if (mode != 3) sort_small_kernel<<<min(num_sms * small_per_sm, total_tiles), kSmallSortThreads, 0, c.stream>>>(a);
         return cudaGetLastError();
     }
+    // The long-list kernel goes first on the caller's stream (it is the longer pole and must not queue behind the
+    // short-list CTAs for SM resources); the short-list kernel follows on the side stream and fills the rest.
     if ((e = cudaEventRecord(ev_fork, c.stream)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(side, ev_fork, 0)) != cudaSuccess) return e;
-    a.work = c.work_big;
-    a.work_count = &c.work_counts->n_big;
-    sort_big_kernel<<<min(num_sms, total_tiles), kBigSortThreads, big_smem, side>>>(a);
+    sort_big_kernel<<<min(num_sms, total_tiles), kBigSortThreads, big_smem, c.stream>>>(a);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    sort_small_kernel<<<min(num_sms * small_per_sm, total_tiles), kSmallSortThreads, 0, side>>>(a);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if ((e = cudaEventRecord(ev_join, side)) != cudaSuccess) return e;
-    a.work = c.work_small;
-    a.work_count = &c.work_counts->n_small;
-    sort_small_kernel<<<min(num_sms * 5, total_tiles), kSmallSortThreads, 0, c.stream>>>(a);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
     return cudaStreamWaitEvent(c.stream, ev_join, 0);
 }
 

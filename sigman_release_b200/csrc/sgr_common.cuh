@@ -44,7 +44,7 @@ struct StateLayout {
 };
 // Layout of `scratch` (valid only inside one call).
 struct ScratchLayout {
-    uint64_t keys, g0, g1, g2, rect, cursor, work_small, work_big, work_blend, work_empty, work_counts, loss_part, accum, total;
+    uint64_t keys, g0, g1, g2, rect, cursor, work_blend, work_empty, work_counts, loss_part, accum, total;
 };
 
 __host__ __device__ inline uint64_t align_up(uint64_t x, uint64_t a = 256) { return (x + a - 1) / a * a; }
@@ -88,8 +88,6 @@ inline ScratchLayout make_scratch_layout(int B, int V, int N, int H, int W, uint
     L.g2 = o;          o = align_up(o + Rc * N * 16);
     L.rect = o;        o = align_up(o + Rc * N * 8);
     L.cursor = o;      o = align_up(o + Rc * T * 4);
-    L.work_small = o;  o = align_up(o + Rc * T * 4);
-    L.work_big = o;    o = align_up(o + Rc * T * 4);
     L.work_blend = o;  o = align_up(o + Rc * T * 4);
     L.work_empty = o;  o = align_up(o + Rc * T * 4);
     L.work_counts = o; o = align_up(o + 256);
@@ -101,8 +99,8 @@ inline ScratchLayout make_scratch_layout(int B, int V, int N, int H, int W, uint
 
 // Per-chunk work-list counters (device).
 struct WorkCounts {
-    unsigned int n_small;      // tiles with 1..kSmallSortCap instances
-    unsigned int n_big;        // tiles with more
+    unsigned int n_big;        // tiles with >= kSmallSortCap instances: the first n_big entries of the blend list
+    unsigned int sort_cursor;  // dynamic queue head of the small-tile sort
     unsigned int chunk_instances;
     unsigned int chunk_dropped;   // != 0: chunk did not fit into max_instances
     unsigned int n_blend;      // non-empty tiles, longest lists first (blend work list)
@@ -111,7 +109,7 @@ struct WorkCounts {
     unsigned int empty_cursor;
 };
 
-constexpr int kSmallSortCap = 4096;       // instances sorted in a 40 KB shared-memory CTA
+constexpr int kSmallSortCap = 4096;       // lists shorter than this are sorted in a 40 KB shared-memory CTA (power of two)
 constexpr int kSmallSortThreads = 256;
 constexpr int kSmallSortBuckets = 1024;
 constexpr int kBigSortThreads = 1024;
@@ -215,7 +213,7 @@ struct ChunkCtx {
     float4 *g0, *g1, *g2;     // [Rc*N]
     uint2* rect;              // [Rc*N] packed tile rectangle
     unsigned int* cursor;     // [Rc*T]
-    unsigned int *work_small, *work_big, *work_blend, *work_empty;
+    unsigned int *work_blend, *work_empty;
     WorkCounts* work_counts;
     float* loss_part;         // [Rc*T*8] fused-loss partial sums, one per (render, tile, pixel block)
     float* accum;             // [kAccumPlanes][Rc*N]

@@ -21,7 +21,7 @@ import torch
 from . import _native
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_batch", "render_l1_loss", "rasterize_gaussians",
-           "cov3d_from_scale_rot", "last_status"]
+           "cov3d_from_scale_rot", "last_status", "check_status"]
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -47,6 +47,7 @@ class GaussianRasterizationSettings(NamedTuple):
 _OVERFLOW_MODE = os.environ.get("SGR_OVERFLOW_CHECK", "deferred")      # "sync" | "deferred"
 _HEADROOM = 1.5
 _est_per_render: dict = {}
+_max_tile_hint: dict = {}      # (N, H, W) -> longest per-tile list observed (sizes the long-list sort's shared memory)
 _last_status: Optional[dict] = None
 _pending: list = []            # deferred status checks: (event, pinned tensor, key, renders)
 
@@ -73,6 +74,7 @@ def _drain_pending(block: bool) -> None:
         ev.synchronize()
         st = _status_from_bytes(pinned)
         _last_status = st
+        _max_tile_hint[key[1:]] = max(_max_tile_hint.get(key[1:], 0), st["max_tile_instances"])
         per = int(st["instances_required"] / max(R, 1) * _HEADROOM) + 1024
         _est_per_render[key] = max(_est_per_render.get(key, 0), per)
         if st["overflow"]:
@@ -84,6 +86,14 @@ def _drain_pending(block: bool) -> None:
                 "background-only for the dropped renders.  The estimate has been raised; re-run the step "
                 "(or set SGR_OVERFLOW_CHECK=sync).")
     _pending[:] = keep
+
+
+def check_status() -> Optional[dict]:
+    """Waits for every deferred overflow check (``SGR_OVERFLOW_CHECK=deferred``) and raises ``SgrError`` if a
+    forward since the last check ran out of instance capacity; returns the latest status block.  Call it where the
+    training loop synchronises anyway (logging, optimizer step)."""
+    _drain_pending(block=True)
+    return _last_status
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -112,6 +122,7 @@ def _fill_problem(p: _native.SgrProblem, B, V, N, H, W, tanfovx, tanfovy, means3
     p.max_instances = cap
     p.renders_per_chunk = rpc
     p.flags = flags
+    p.max_tile_instances_hint = _max_tile_hint.get((N, H, W), 0)
 
 
 class _RasterizeBatch(torch.autograd.Function):
@@ -171,6 +182,7 @@ class _RasterizeBatch(torch.autograd.Function):
                     _native.check(rc)
                 need_per = int(st.instances_required / max(R, 1) * _HEADROOM) + 1024
                 _est_per_render[key] = max(_est_per_render.get(key, 0), need_per)
+                _max_tile_hint[key[1:]] = max(_max_tile_hint.get(key[1:], 0), int(st.max_tile_instances))
                 _last_status = dict(instances_required=int(st.instances_required),
                                     instances_capacity=int(st.instances_capacity), overflow=int(st.overflow),
                                     max_tile_instances=int(st.max_tile_instances),
@@ -206,7 +218,10 @@ class _RasterizeBatch(torch.autograd.Function):
         means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg, alpha, radii, state = ctx.saved_tensors
         B, V, N, H, W, tanfovx, tanfovy, cap, flags, rpc, state_bytes = ctx.dims
         dev = means3D.device
-        _drain_pending(block=True)       # a deferred overflow of the forward surfaces here
+        # Deferred overflow checks never block the launch path (a blocking wait here would idle the GPU for the whole
+        # launch latency of the backward): an overflow surfaces at the first rasteriser call after its status copy
+        # has landed, or at check_status().
+        _drain_pending(block=False)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev)
             if g_color is None:

@@ -32,9 +32,9 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_struct_layout_matches_header(lib):
     assert ctypes.sizeof(_native.SgrStatus) == 32
-    assert ctypes.sizeof(_native.SgrProblem) == 104
-    assert ctypes.sizeof(_native.SgrForwardArgs) == 104 + 9 * 8 + 5 * 8      # + the fused-loss block
-    assert ctypes.sizeof(_native.SgrBackwardArgs) == 104 + 16 * 8
+    assert ctypes.sizeof(_native.SgrProblem) == 112
+    assert ctypes.sizeof(_native.SgrForwardArgs) == 112 + 9 * 8 + 5 * 8      # + the fused-loss block
+    assert ctypes.sizeof(_native.SgrBackwardArgs) == 112 + 16 * 8
 
 
 def test_buffer_size_queries(lib):

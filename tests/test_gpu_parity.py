@@ -9,7 +9,7 @@ import torch
 import oracle
 from gpu_utils import TAN, debug_state, gpu_forward, oracle_forward, saved_state, scene_tensors, to_dev, view_tensors
 from scene_utils import small_scene
-from sigman_release_b200 import cameras, rasterizer, scenes
+from sigman_release_b200 import _native, cameras, rasterizer, scenes
 
 pytestmark = pytest.mark.gpu
 
@@ -245,6 +245,28 @@ def test_instance_overflow_is_detected_and_retried():
         rasterizer._OVERFLOW_MODE = old
     assert torch.equal(out1[0], out2[0])
     assert rasterizer._est_per_render[key] >= st["instances_required"]
+
+
+def test_deferred_overflow_surfaces_at_check_status():
+    """Deferred mode never blocks the launch path: the overflow of a forward is reported by check_status() (or by the
+    next rasteriser call after the status copy landed), the estimate is raised and the re-run is correct."""
+    sc = scenes.random_gaussians(5000, seed=1)
+    key = (torch.cuda.current_device(), 5000, 128, 128)
+    out1, _, _ = gpu_forward(sc, [30], 128, 128)
+    rasterizer.check_status()
+    rasterizer._est_per_render[key] = 16
+    old = rasterizer._OVERFLOW_MODE
+    rasterizer._OVERFLOW_MODE = "deferred"
+    try:
+        gpu_forward(sc, [30], 128, 128)
+        with pytest.raises(_native.SgrError) as ei:
+            rasterizer.check_status()
+        assert ei.value.code == _native.SGR_E_INSTANCE_OVERFLOW
+        out3, _, _ = gpu_forward(sc, [30], 128, 128)
+        assert rasterizer.check_status()["overflow"] == 0
+    finally:
+        rasterizer._OVERFLOW_MODE = old
+    assert torch.equal(out1[0], out3[0])
 
 
 def test_knn_mean_dist2_matches_bruteforce_oracle():
