@@ -164,6 +164,27 @@ int sgr_cov3d_from_scale_rot_backward(const float* scales, const float* rotation
                                       int32_t num_gaussians, const float* dL_dcov3D, float* dL_dscales,
                                       float* dL_drotations, void* stream);
 
+/* Replaces the per-subject preparation of gs.py:69-73 for n = B*N Gaussians in one kernel:
+ * scale = (scale_raw + 1) * sqrt(max(dist2, 1e-7)) with the kNN factor treated as a constant (gs.py:70-72),
+ * Sigma = R diag(scale^2) R^T (get_covariance, gs.py:17-23), packed (xx,xy,xz,yy,yz,zz) (strip_lowerdiag, gs.py:29-38).
+ * rotation is the row-major 3x3 "rotation-like" matrix SIGMAN feeds as gaussians['cov3d'].  bf16_autocast != 0
+ * reproduces the operand / result rounding of the reference's two bmm's under accelerate's bf16 autocast. */
+int sgr_prep_cov3d(const float* scale_raw, const float* rotation, const float* dist2, int64_t n, int32_t bf16_autocast,
+                   float* cov3D, void* stream);
+int sgr_prep_cov3d_backward(const float* scale_raw, const float* rotation, const float* dist2, int64_t n,
+                            int32_t bf16_autocast, const float* dL_dcov3D, float* dL_dscale_raw, float* dL_drotation,
+                            void* stream);
+
+/* Optional colour path of the upstream API (`shs` instead of `colors_precomp`; unused by SIGMAN, gs.py:91,102):
+ * upstream computeColorFromSH and its backward.  shs [N, max_coeffs, 3], degree 0..3 uses the first (degree+1)^2
+ * coefficients; colors = max(0, SH(normalize(mean - campos)) + 0.5), clamped[N,3] records the clamp.
+ * The backward writes dL_dshs [N, max_coeffs, 3] and dL_dmeans3D [N,3] (the view-direction term only). */
+int sgr_sh_colors(const float* means3D, const float* shs, const float* campos, int32_t num_gaussians, int32_t degree,
+                  int32_t max_coeffs, float* colors, uint8_t* clamped, void* stream);
+int sgr_sh_colors_backward(const float* means3D, const float* shs, const float* campos, int32_t num_gaussians,
+                           int32_t degree, int32_t max_coeffs, const uint8_t* clamped, const float* dL_dcolors,
+                           float* dL_dshs, float* dL_dmeans3D, void* stream);
+
 /* Replaces `simple_knn._C.distCUDA2` (gs.py:70): mean squared distance to the 3 nearest other points.
  * `scratch` must hold sgr_knn_scratch_bytes(num_points) bytes. */
 uint64_t sgr_knn_scratch_bytes(int32_t num_points);

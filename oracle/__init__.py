@@ -198,3 +198,31 @@ def knn_mean_dist2(points) -> np.ndarray:
     out = np.zeros((p.shape[0],), np.float32)
     L.oracle_knn_mean_dist2(p.shape[0], _p(p), _p(out))
     return out
+
+
+def sh_colors(means3D, shs, campos, degree, dtype=np.float32):
+    """upstream computeColorFromSH: (colors [N,3] clamped at 0, clamped flags [N,3] bool).  shs [N,K,3]."""
+    L = lib()
+    dt = np.dtype(dtype)
+    m = np.ascontiguousarray(np.asarray(means3D, dt)); sh = np.ascontiguousarray(np.asarray(shs, dt))
+    cp = np.ascontiguousarray(np.asarray(campos, dt).reshape(3))
+    N, K = m.shape[0], sh.shape[1]
+    assert (degree + 1) ** 2 <= K
+    out = np.zeros((N, 3), dt); cl = np.zeros((N, 3), np.uint8)
+    fn = L.oracle_sh_colors_f32 if dt == np.float32 else L.oracle_sh_colors_f64
+    fn(ctypes.c_int(N), ctypes.c_int(int(degree)), ctypes.c_int(K), _p(m), _p(sh), _p(cp), _p(out), _p(cl))
+    return out, cl.astype(bool)
+
+
+def prep_cov3d(scale_raw, rot, dist2, dtype=np.float32) -> np.ndarray:
+    """gs.py:69-73: Sigma = R diag(((s + 1) sqrt(max(d2, 1e-7)))^2) R^T packed to 6 values.  rot [n,3,3]."""
+    L = lib()
+    dt = np.dtype(dtype)
+    s = np.ascontiguousarray(np.asarray(scale_raw, dt)).reshape(-1, 3)
+    r = np.ascontiguousarray(np.asarray(rot, dt)).reshape(-1, 9)
+    d = np.ascontiguousarray(np.asarray(dist2, dt)).reshape(-1)
+    n = s.shape[0]
+    out = np.zeros((n, 6), dt)
+    fn = L.oracle_prep_cov3d_f32 if dt == np.float32 else L.oracle_prep_cov3d_f64
+    fn(ctypes.c_int64(n), _p(s), _p(r), _p(d), _p(out))
+    return out

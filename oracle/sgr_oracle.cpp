@@ -545,6 +545,73 @@ void knn_mean_dist2(int N, const float* pts, float* out) {
     }
 }
 
+
+// ------------------------------------------------------------------ optional colour path: spherical harmonics
+// upstream computeColorFromSH (SURVEY.md A.2 "SH path"; unused by SIGMAN, which passes colors_precomp with
+// sh_degree = 0, /root/reference/core/gaussians/gs.py:91,102): real SH basis of Kerbl et al. 2023 up to degree 3,
+// evaluated on dir = normalize(mean - campos); colour = sum_k basis_k(dir) * sh[k] + 0.5, clamped at 0 with the clamp
+// recorded so that the backward zeroes the gradient of clamped channels.
+constexpr double kSH0 = 0.28209479177387814, kSH1 = 0.4886025119029199;
+constexpr double kSH2[5] = {1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792,
+                            0.5462742152960396};
+constexpr double kSH3[7] = {-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154,
+                            -0.4570457994644658, 1.445305721320277, -0.5900435899266435};
+
+template <typename R>
+void sh_basis(int deg, R x, R y, R z, R* b) {
+    b[0] = R(kSH0);
+    if (deg < 1) return;
+    b[1] = -R(kSH1) * y; b[2] = R(kSH1) * z; b[3] = -R(kSH1) * x;
+    if (deg < 2) return;
+    const R xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    b[4] = R(kSH2[0]) * xy; b[5] = R(kSH2[1]) * yz; b[6] = R(kSH2[2]) * (R(2) * zz - xx - yy);
+    b[7] = R(kSH2[3]) * xz; b[8] = R(kSH2[4]) * (xx - yy);
+    if (deg < 3) return;
+    b[9] = R(kSH3[0]) * y * (R(3) * xx - yy); b[10] = R(kSH3[1]) * xy * z;
+    b[11] = R(kSH3[2]) * y * (R(4) * zz - xx - yy); b[12] = R(kSH3[3]) * z * (R(2) * zz - R(3) * xx - R(3) * yy);
+    b[13] = R(kSH3[4]) * x * (R(4) * zz - xx - yy); b[14] = R(kSH3[5]) * z * (xx - yy);
+    b[15] = R(kSH3[6]) * x * (xx - R(3) * yy);
+}
+
+template <typename R>
+void sh_colors(int N, int deg, int max_coeffs, const R* means, const R* shs, const R* campos, R* colors,
+               unsigned char* clamped) {
+    const int K = (deg + 1) * (deg + 1);
+    for (int i = 0; i < N; ++i) {
+        const R dx = means[3 * i] - campos[0], dy = means[3 * i + 1] - campos[1], dz = means[3 * i + 2] - campos[2];
+        const R inv = R(1) / std::sqrt(dx * dx + dy * dy + dz * dz);
+        R b[16];
+        sh_basis<R>(deg, dx * inv, dy * inv, dz * inv, b);
+        for (int c = 0; c < 3; ++c) {
+            R v = 0;
+            for (int k = 0; k < K; ++k) v += b[k] * shs[(size_t(i) * max_coeffs + k) * 3 + c];
+            v += R(0.5);
+            clamped[3 * i + c] = v < R(0) ? 1 : 0;
+            colors[3 * i + c] = v < R(0) ? R(0) : v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ per-subject preparation of gs.py:69-73
+// scale = (s + 1) * sqrt(max(d2, 1e-7)) (kNN factor detached), Sigma = Rm diag(scale^2) Rm^T, packed (xx,xy,xz,yy,yz,zz)
+// (get_covariance + strip_lowerdiag, gs.py:17-38).  Rm is the "rotation-like" 3x3 matrix SIGMAN feeds (row-major).
+template <typename R>
+void prep_cov3d(int64_t n, const R* s_raw, const R* rot, const R* dist2, R* cov6) {
+    for (int64_t i = 0; i < n; ++i) {
+        const R d2 = dist2[i] < R(1e-7) ? R(1e-7) : dist2[i];
+        const R sg = std::sqrt(d2);
+        R e[3];
+        for (int k = 0; k < 3; ++k) { const R sc = (s_raw[3 * i + k] + R(1)) * sg; e[k] = sc * sc; }
+        const R* Rm = rot + 9 * i;
+        const int ia[6] = {0, 0, 0, 1, 1, 2}, ib[6] = {0, 1, 2, 1, 2, 2};
+        for (int q = 0; q < 6; ++q) {
+            R v = 0;
+            for (int k = 0; k < 3; ++k) v += Rm[3 * ia[q] + k] * e[k] * Rm[3 * ib[q] + k];
+            cov6[6 * i + q] = v;
+        }
+    }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------- C ABI
@@ -636,5 +703,20 @@ void oracle_cov3d_from_scale_rot_f64(int N, const double* scales, const double* 
     cov3d_from_scale_rot(N, scales, rots, mod, cov6);
 }
 void oracle_knn_mean_dist2(int N, const float* pts, float* out) { knn_mean_dist2(N, pts, out); }
+
+void oracle_sh_colors_f32(int N, int deg, int max_coeffs, const float* means, const float* shs, const float* campos,
+                          float* colors, unsigned char* clamped) {
+    sh_colors<float>(N, deg, max_coeffs, means, shs, campos, colors, clamped);
+}
+void oracle_sh_colors_f64(int N, int deg, int max_coeffs, const double* means, const double* shs, const double* campos,
+                          double* colors, unsigned char* clamped) {
+    sh_colors<double>(N, deg, max_coeffs, means, shs, campos, colors, clamped);
+}
+void oracle_prep_cov3d_f32(int64_t n, const float* s_raw, const float* rot, const float* dist2, float* cov6) {
+    prep_cov3d<float>(n, s_raw, rot, dist2, cov6);
+}
+void oracle_prep_cov3d_f64(int64_t n, const double* s_raw, const double* rot, const double* dist2, double* cov6) {
+    prep_cov3d<double>(n, s_raw, rot, dist2, cov6);
+}
 
 }  // extern "C"

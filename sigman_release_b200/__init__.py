@@ -10,5 +10,8 @@ from .rasterizer import (  # noqa: E402,F401
     rasterize_gaussians,
     cov3d_from_scale_rot,
     last_status,
+    check_status,
+    render_l1_loss,
+    sh_colors,
 )
-from .renderer import GaussianRenderer, distCUDA2, get_covariance  # noqa: E402,F401
+from .renderer import GaussianRenderer, distCUDA2, get_covariance, prep_cov3d  # noqa: E402,F401

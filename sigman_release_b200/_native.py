@@ -117,6 +117,10 @@ SYMBOLS = {
     "sgr_mark_visible": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp, _vp]),
     "sgr_cov3d_from_scale_rot": (ctypes.c_int, [_vp, _vp, _f32, _i32, _vp, _vp]),
     "sgr_cov3d_from_scale_rot_backward": (ctypes.c_int, [_vp, _vp, _f32, _i32, _vp, _vp, _vp, _vp]),
+    "sgr_prep_cov3d": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, _i32, _vp, _vp]),
+    "sgr_prep_cov3d_backward": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, _i32, _vp, _vp, _vp, _vp]),
+    "sgr_sh_colors": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "sgr_sh_colors_backward": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "sgr_knn_scratch_bytes": (_u64, [_i32]),
     "sgr_knn_mean_dist2": (ctypes.c_int, [_vp, _i32, _vp, _vp, _u64, _vp]),
     "sgr_profile_enable": (None, [ctypes.c_int]),

@@ -329,6 +329,47 @@ int sgr_cov3d_from_scale_rot_backward(const float* scales, const float* rotation
     return SGR_OK;
 }
 
+int sgr_prep_cov3d(const float* scale_raw, const float* rotation, const float* dist2, int64_t n, int32_t bf16_autocast,
+                   float* cov3D, void* stream) {
+    if (n < 0 || (n > 0 && (!scale_raw || !rotation || !dist2 || !cov3D))) return fail(SGR_E_INVALID_ARGUMENT, "bad prep_cov3d arguments");
+    SGR_CUDA(launch_prep_cov3d(scale_raw, rotation, dist2, n, bf16_autocast != 0, cov3D, static_cast<cudaStream_t>(stream)));
+    g_launches += n > 0;
+    return SGR_OK;
+}
+
+int sgr_prep_cov3d_backward(const float* scale_raw, const float* rotation, const float* dist2, int64_t n,
+                            int32_t bf16_autocast, const float* dL_dcov3D, float* dL_dscale_raw, float* dL_drotation,
+                            void* stream) {
+    if (n < 0 || (n > 0 && (!scale_raw || !rotation || !dist2 || !dL_dcov3D || !dL_dscale_raw || !dL_drotation)))
+        return fail(SGR_E_INVALID_ARGUMENT, "bad prep_cov3d backward arguments");
+    SGR_CUDA(launch_prep_cov3d_backward(scale_raw, rotation, dist2, n, bf16_autocast != 0, dL_dcov3D, dL_dscale_raw,
+                                        dL_drotation, static_cast<cudaStream_t>(stream)));
+    g_launches += n > 0;
+    return SGR_OK;
+}
+
+int sgr_sh_colors(const float* means3D, const float* shs, const float* campos, int32_t N, int32_t degree,
+                  int32_t max_coeffs, float* colors, uint8_t* clamped, void* stream) {
+    if (N < 0 || degree < 0 || degree > 3 || max_coeffs < (degree + 1) * (degree + 1) ||
+        (N > 0 && (!means3D || !shs || !campos || !colors || !clamped)))
+        return fail(SGR_E_INVALID_ARGUMENT, "bad sh_colors arguments (degree 0..3, max_coeffs >= (degree+1)^2)");
+    SGR_CUDA(launch_sh_colors(means3D, shs, campos, N, degree, max_coeffs, colors, clamped, static_cast<cudaStream_t>(stream)));
+    g_launches += N > 0;
+    return SGR_OK;
+}
+
+int sgr_sh_colors_backward(const float* means3D, const float* shs, const float* campos, int32_t N, int32_t degree,
+                           int32_t max_coeffs, const uint8_t* clamped, const float* dL_dcolors, float* dL_dshs,
+                           float* dL_dmeans3D, void* stream) {
+    if (N < 0 || degree < 0 || degree > 3 || max_coeffs < (degree + 1) * (degree + 1) ||
+        (N > 0 && (!means3D || !shs || !campos || !clamped || !dL_dcolors || !dL_dshs || !dL_dmeans3D)))
+        return fail(SGR_E_INVALID_ARGUMENT, "bad sh_colors backward arguments");
+    SGR_CUDA(launch_sh_colors_backward(means3D, shs, campos, N, degree, max_coeffs, clamped, dL_dcolors, dL_dshs,
+                                       dL_dmeans3D, static_cast<cudaStream_t>(stream)));
+    g_launches += N > 0;
+    return SGR_OK;
+}
+
 int sgr_debug_copy_state(const void* state, int32_t B, int32_t V, int32_t N, int32_t H, int32_t W,
                          uint64_t max_instances, int32_t render, uint32_t* tile_ranges, uint32_t* n_contrib,
                          uint32_t* point_list, uint64_t point_list_capacity, uint32_t* tile_timing, void* stream) {

@@ -240,4 +240,14 @@ cudaError_t launch_cov3d_from_scale_rot(const float* scales, const float* rots, 
 cudaError_t launch_cov3d_from_scale_rot_backward(const float* scales, const float* rots, float mod, int N,
                                                  const float* dcov, float* dscales, float* drots, cudaStream_t s);
 
+cudaError_t launch_prep_cov3d(const float* s_raw, const float* rot, const float* dist2, long long n, bool bf16,
+                              float* cov6, cudaStream_t s);
+cudaError_t launch_prep_cov3d_backward(const float* s_raw, const float* rot, const float* dist2, long long n, bool bf16,
+                                       const float* dcov, float* ds_raw, float* drot, cudaStream_t s);
+cudaError_t launch_sh_colors(const float* means, const float* shs, const float* campos, int N, int deg, int max_coeffs,
+                             float* colors, uint8_t* clamped, cudaStream_t s);
+cudaError_t launch_sh_colors_backward(const float* means, const float* shs, const float* campos, int N, int deg,
+                                      int max_coeffs, const uint8_t* clamped, const float* dcolors, float* dshs,
+                                      float* dmeans, cudaStream_t s);
+
 }  // namespace sgr

@@ -21,7 +21,7 @@ import torch
 from . import _native
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_batch", "render_l1_loss", "rasterize_gaussians",
-           "cov3d_from_scale_rot", "last_status", "check_status"]
+           "cov3d_from_scale_rot", "sh_colors", "last_status", "check_status"]
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -361,14 +361,60 @@ def cov3d_from_scale_rot(scales, rotations, scale_modifier=1.0):
     return _Cov3DFromScaleRot.apply(scales, rotations, float(scale_modifier))
 
 
+class _SHColors(torch.autograd.Function):
+    """upstream computeColorFromSH (+ backward): colours [N,3] from shs [N,K,3] seen from ``campos``."""
+
+    @staticmethod
+    def forward(ctx, means3D, shs, campos, degree):
+        L = _native.lib()
+        N, K = int(shs.shape[0]), int(shs.shape[1])
+        colors = torch.empty((N, 3), dtype=torch.float32, device=means3D.device)
+        clamped = torch.empty((N, 3), dtype=torch.uint8, device=means3D.device)
+        with torch.cuda.device(means3D.device):
+            st = torch.cuda.current_stream(means3D.device)
+            _native.check(L.sgr_sh_colors(_ptr(means3D), _ptr(shs), _ptr(campos), N, int(degree), K, _ptr(colors),
+                                          _ptr(clamped), ctypes.c_void_p(st.cuda_stream)))
+        ctx.save_for_backward(means3D, shs, campos, clamped)
+        ctx.degree = int(degree)
+        return colors
+
+    @staticmethod
+    def backward(ctx, g_colors):
+        L = _native.lib()
+        means3D, shs, campos, clamped = ctx.saved_tensors
+        N, K = int(shs.shape[0]), int(shs.shape[1])
+        g_colors = g_colors.contiguous().float()
+        d_shs = torch.empty_like(shs)
+        d_means = torch.empty_like(means3D)
+        with torch.cuda.device(means3D.device):
+            st = torch.cuda.current_stream(means3D.device)
+            _native.check(L.sgr_sh_colors_backward(_ptr(means3D), _ptr(shs), _ptr(campos), N, ctx.degree, K,
+                                                   _ptr(clamped), _ptr(g_colors), _ptr(d_shs), _ptr(d_means),
+                                                   ctypes.c_void_p(st.cuda_stream)))
+        return d_means, d_shs, None, None
+
+
+def sh_colors(means3D, shs, campos, degree):
+    """``max(0, SH_degree(normalize(means3D - campos)) . shs + 0.5)`` — the ``shs`` input path of the upstream API.
+    means3D [N,3], shs [N,K,3] with K >= (degree+1)^2, campos [3]; differentiable w.r.t. means3D and shs."""
+    N = int(means3D.shape[0])
+    if shs.dim() != 3 or int(shs.shape[0]) != N or int(shs.shape[2]) != 3:
+        raise ValueError("shs must be [N,K,3]")
+    degree = int(degree)
+    if not 0 <= degree <= 3 or int(shs.shape[1]) < (degree + 1) ** 2:
+        raise ValueError("sh_degree must be 0..3 with at least (degree+1)^2 coefficients per Gaussian")
+    means3D = _check_input("means3D", means3D, (N, 3))
+    shs = _check_input("shs", shs, tuple(shs.shape))
+    campos = _check_input("campos", campos.to(means3D.device, torch.float32).reshape(3), (3,))
+    return _SHColors.apply(means3D, shs, campos, degree)
+
+
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                         raster_settings: GaussianRasterizationSettings):
     """One view of one Gaussian set — upstream ``rasterize_gaussians`` (same argument order)."""
-    if sh is not None and sh.numel() > 0:
-        raise NotImplementedError(
-            "spherical-harmonics colours are not on the SIGMAN path (sh_degree=0, shs=None, "
-            "/root/reference/core/gaussians/gs.py:91,102); pass colors_precomp")
     N = int(means3D.shape[0])
+    if sh is not None and sh.numel() > 0:       # upstream's SH colour path (SIGMAN passes colors_precomp, gs.py:102)
+        colors_precomp = sh_colors(means3D, sh, raster_settings.campos, raster_settings.sh_degree)
     if cov3Ds_precomp is None or cov3Ds_precomp.numel() == 0:
         cov3D = cov3d_from_scale_rot(scales, rotations, raster_settings.scale_modifier)
     else:

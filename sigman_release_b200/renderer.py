@@ -16,7 +16,7 @@ import torch
 from . import _native
 from .rasterizer import _ptr, rasterize_batch
 
-__all__ = ["GaussianRenderer", "distCUDA2", "get_covariance", "strip_lowerdiag"]
+__all__ = ["GaussianRenderer", "distCUDA2", "get_covariance", "strip_lowerdiag", "prep_cov3d"]
 
 
 def distCUDA2(points: torch.Tensor) -> torch.Tensor:
@@ -49,11 +49,57 @@ def get_covariance(scaling: torch.Tensor, rotation: torch.Tensor, scaling_modifi
     return strip_lowerdiag(RS @ rotation.transpose(-1, -2))
 
 
+class _PrepCov3D(torch.autograd.Function):
+    """gs.py:69-73 in one kernel: cov3D [.., 6] from raw scale [.., 3], rotation-like matrix [.., 3, 3] and the
+    (detached) kNN mean squared distance [..]; backward to scale and rotation."""
+
+    @staticmethod
+    def forward(ctx, scale_raw, rotation, dist2, bf16_autocast):
+        L = _native.lib()
+        n = scale_raw.numel() // 3
+        cov = torch.empty(tuple(scale_raw.shape[:-1]) + (6,), dtype=torch.float32, device=scale_raw.device)
+        with torch.cuda.device(scale_raw.device):
+            st = torch.cuda.current_stream(scale_raw.device)
+            _native.check(L.sgr_prep_cov3d(_ptr(scale_raw), _ptr(rotation), _ptr(dist2), n, int(bool(bf16_autocast)),
+                                           _ptr(cov), ctypes.c_void_p(st.cuda_stream)))
+        ctx.save_for_backward(scale_raw, rotation, dist2)
+        ctx.bf16 = int(bool(bf16_autocast))
+        return cov
+
+    @staticmethod
+    def backward(ctx, g_cov):
+        L = _native.lib()
+        scale_raw, rotation, dist2 = ctx.saved_tensors
+        n = scale_raw.numel() // 3
+        g_cov = g_cov.contiguous().float()
+        ds = torch.empty_like(scale_raw)
+        dr = torch.empty_like(rotation)
+        with torch.cuda.device(scale_raw.device):
+            st = torch.cuda.current_stream(scale_raw.device)
+            _native.check(L.sgr_prep_cov3d_backward(_ptr(scale_raw), _ptr(rotation), _ptr(dist2), n, ctx.bf16,
+                                                    _ptr(g_cov), _ptr(ds), _ptr(dr), ctypes.c_void_p(st.cuda_stream)))
+        return ds, dr, None, None
+
+
+def prep_cov3d(scale_raw: torch.Tensor, rotation: torch.Tensor, dist2: torch.Tensor, bf16_autocast: bool = False):
+    """Fused ``(s + 1) * sqrt(max(d2, 1e-7))`` -> ``R diag(scale^2) R^T`` -> 6-pack of gs.py:69-73 (and its backward).
+    scale_raw [..,3], rotation [..,3,3], dist2 [..] (treated as a constant, like the ``.detach()`` of gs.py:71)."""
+    lead = tuple(scale_raw.shape[:-1])
+    if tuple(rotation.shape) != lead + (3, 3) or tuple(dist2.shape) != lead:
+        raise ValueError("prep_cov3d: scale_raw [..,3], rotation [..,3,3], dist2 [..] must agree")
+    for name, t in (("scale_raw", scale_raw), ("rotation", rotation), ("dist2", dist2)):
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise ValueError(f"{name} must be a float32 CUDA tensor")
+    return _PrepCov3D.apply(scale_raw.contiguous(), rotation.contiguous(), dist2.detach().contiguous(), bf16_autocast)
+
+
 class GaussianRenderer:
     def __init__(self, opt):
         self.opt = opt
         self.bg_color = torch.tensor([1, 1, 1], dtype=torch.float32, device="cuda")
         self.tan_half_fov = np.tan(0.5 * self.opt.FoVy)
+        # True reproduces the bf16 rounding the reference's get_covariance bmm's see under accelerate's autocast
+        self.bf16_autocast = False
 
     def prepare(self, gaussians):
         """Per-subject preparation of gs.py:64-73, batched over B: returns (means3D, cov3D [B,N,6], rgb, opacity)."""
@@ -64,10 +110,8 @@ class GaussianRenderer:
         rgbs = gaussians["rgb"].contiguous().float()
         B = means3D.shape[0]
         with torch.no_grad():
-            dist2 = torch.stack([torch.clamp_min(distCUDA2(means3D[b]), 0.0000001) for b in range(B)])
-            base = torch.sqrt(dist2)[..., None]                 # detached kNN factor (gs.py:71)
-        scale = (scales + 1) * base
-        cov3D = get_covariance(scale, rot)
+            dist2 = torch.stack([distCUDA2(means3D[b]) for b in range(B)])      # detached kNN factor (gs.py:70-71)
+        cov3D = prep_cov3d(scales, rot, dist2, bf16_autocast=self.bf16_autocast)
         return means3D, cov3D, rgbs, opacity
 
     def render(self, gaussians, cam_view, cam_view_proj, cam_pos, bg_color=None, scale_modifier=0.5):

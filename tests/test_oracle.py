@@ -246,3 +246,63 @@ def test_knn_mean_dist2_bruteforce():
     # duplicates are neighbours at distance 0 (exclusion is by index)
     p2 = np.concatenate([p[:5], p[:5]])
     assert oracle.knn_mean_dist2(p2).min() >= 0
+
+
+# ------------------------------------------------------------------------------------------------ optional paths
+def _torch_sh(means, shs, campos, deg):
+    """Independent torch restatement of the real SH basis (Kerbl et al. 2023) for autograd checks."""
+    import torch
+    C0, C1 = 0.28209479177387814, 0.4886025119029199
+    C2 = [1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396]
+    C3 = [-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+          1.445305721320277, -0.5900435899266435]
+    d = means - campos
+    d = d / d.norm(dim=1, keepdim=True)
+    x, y, z = d[:, 0:1], d[:, 1:2], d[:, 2:3]
+    r = C0 * shs[:, 0]
+    if deg > 0:
+        r = r - C1 * y * shs[:, 1] + C1 * z * shs[:, 2] - C1 * x * shs[:, 3]
+    if deg > 1:
+        xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+        r = (r + C2[0] * xy * shs[:, 4] + C2[1] * yz * shs[:, 5] + C2[2] * (2 * zz - xx - yy) * shs[:, 6]
+             + C2[3] * xz * shs[:, 7] + C2[4] * (xx - yy) * shs[:, 8])
+    if deg > 2:
+        r = (r + C3[0] * y * (3 * xx - yy) * shs[:, 9] + C3[1] * xy * z * shs[:, 10]
+             + C3[2] * y * (4 * zz - xx - yy) * shs[:, 11] + C3[3] * z * (2 * zz - 3 * xx - 3 * yy) * shs[:, 12]
+             + C3[4] * x * (4 * zz - xx - yy) * shs[:, 13] + C3[5] * z * (xx - yy) * shs[:, 14]
+             + C3[6] * x * (xx - 3 * yy) * shs[:, 15])
+    return torch.clamp_min(r + 0.5, 0.0)
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+def test_sh_colors_oracle_matches_torch_restatement(deg):
+    import torch
+    rng = np.random.default_rng(deg)
+    m = rng.normal(size=(200, 3)); sh = rng.normal(size=(200, 16, 3)) * 1.5; cp = np.array([0.3, -0.2, 2.5])
+    got, clamped = oracle.sh_colors(m, sh, cp, deg, np.float64)
+    want = _torch_sh(torch.tensor(m), torch.tensor(sh), torch.tensor(cp), deg).numpy()
+    np.testing.assert_allclose(got, want, atol=1e-13)
+    assert clamped.any() and (got[clamped] == 0).all()
+    # degree-0 known answer: colour = max(0, 0.2820948 * dc + 0.5), independent of the view direction
+    if deg == 0:
+        np.testing.assert_allclose(got, np.maximum(0.28209479177387814 * sh[:, 0] + 0.5, 0), atol=1e-15)
+    got32, _ = oracle.sh_colors(m, sh, cp, deg, np.float32)
+    np.testing.assert_allclose(got32, want, atol=2e-6)
+
+
+def test_prep_cov3d_oracle_matches_reference_ops():
+    """The torch ops of /root/reference/core/gaussians/gs.py:17-38,69-73, restated, against the oracle (fp64)."""
+    import torch
+    rng = np.random.default_rng(7)
+    n = 300
+    s = torch.tensor(rng.uniform(-1, 1, (n, 3))); R = torch.tensor(rng.normal(size=(n, 3, 3)))
+    d2 = torch.tensor(np.concatenate([rng.uniform(1e-6, 1e-4, n - 2), [0.0, 1e-9]]))
+    scales_ = torch.sqrt(torch.clamp_min(d2, 0.0000001))[..., None].repeat(1, 3)
+    scale = (s + 1) * scales_
+    Lm = torch.zeros_like(R)
+    Lm[:, 0, 0] = scale[:, 0]; Lm[:, 1, 1] = scale[:, 1]; Lm[:, 2, 2] = scale[:, 2]
+    cov = R @ (Lm ** 2) @ R.permute(0, 2, 1)
+    want = torch.stack([cov[:, 0, 0], cov[:, 0, 1], cov[:, 0, 2], cov[:, 1, 1], cov[:, 1, 2], cov[:, 2, 2]], 1).numpy()
+    got = oracle.prep_cov3d(s.numpy(), R.numpy(), d2.numpy(), np.float64)
+    # off-diagonal entries cancel: tolerance relative to the Gaussian's largest covariance entry
+    assert float((np.abs(got - want) / np.abs(want).max(axis=1, keepdims=True)).max()) <= 1e-12
