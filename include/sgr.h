@@ -190,6 +190,11 @@ int sgr_sh_colors_backward(const float* means3D, const float* shs, const float* 
 uint64_t sgr_knn_scratch_bytes(int32_t num_points);
 int sgr_knn_mean_dist2(const float* points, int32_t num_points, float* out_mean_dist2, void* scratch,
                        uint64_t scratch_bytes, void* stream);
+/* The same for num_subjects independent point sets [B,N,3] -> [B,N] in one launch set (the reference calls
+ * distCUDA2 once per subject inside its Python loop, gs.py:62-70). */
+uint64_t sgr_knn_scratch_bytes_batched(int32_t num_subjects, int32_t num_points);
+int sgr_knn_mean_dist2_batched(const float* points, int32_t num_subjects, int32_t num_points, float* out_mean_dist2,
+                               void* scratch, uint64_t scratch_bytes, void* stream);
 
 /* Measurement hooks (bench.py): per-stage device time with CUDA events recorded on the launch stream around every
  * stage of sgr_forward / sgr_backward while enabled, and a counter of the kernels this library has launched.

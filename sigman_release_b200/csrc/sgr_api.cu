@@ -150,6 +150,7 @@ using namespace sgr;
 extern "C" {
 
 int sgr_set_error_(int code, const char* msg) { return fail(code, "%s", msg); }   // used by sgr_knn.cu
+void sgr_count_launches_(unsigned int n) { g_launches += n; }
 
 int sgr_abi_version(void) { return SGR_ABI_VERSION; }
 const char* sgr_last_error(void) { return g_err; }

@@ -20,19 +20,24 @@ struct KnnHeader {
 };
 
 struct KnnLayout {
-    uint64_t header, cell_of, cell_start, cell_fill, sorted, total;
+    uint64_t header, cell_of, cell_start, cell_fill, block_sum, sorted, total;
 };
 
 constexpr unsigned int kMaxCells = 1u << 21;
+constexpr int kScanThreads = 1024, kScanPer = 8;
+constexpr unsigned int kScanBlock = kScanThreads * kScanPer;            // cells per scan CTA
+constexpr unsigned int kScanBlocks = kMaxCells / kScanBlock;            // 256
 
-KnnLayout knn_layout(int N) {
+// Per-subject regions, subject b at index b of every array.
+KnnLayout knn_layout(int B, int N) {
     KnnLayout L;
     uint64_t o = 0;
-    L.header = o;     o = align_up(o + sizeof(KnnHeader));
-    L.cell_of = o;    o = align_up(o + uint64_t(N) * 4);
-    L.cell_start = o; o = align_up(o + uint64_t(kMaxCells + 1) * 4);
-    L.cell_fill = o;  o = align_up(o + uint64_t(kMaxCells) * 4);
-    L.sorted = o;     o = align_up(o + uint64_t(N) * 16);
+    L.header = o;     o = align_up(o + uint64_t(B) * sizeof(KnnHeader));
+    L.cell_of = o;    o = align_up(o + uint64_t(B) * N * 4);
+    L.cell_start = o; o = align_up(o + uint64_t(B) * (kMaxCells + 1) * 4);
+    L.cell_fill = o;  o = align_up(o + uint64_t(B) * kMaxCells * 4);
+    L.block_sum = o;  o = align_up(o + uint64_t(B) * kScanBlocks * 4);
+    L.sorted = o;     o = align_up(o + uint64_t(B) * N * 16);
     L.total = o;
     return L;
 }
@@ -46,11 +51,16 @@ __device__ __forceinline__ float atomic_max_float(float* addr, float v) {
                        : __uint_as_float(atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v)));
 }
 
-__global__ void knn_init_kernel(KnnHeader* h) {
-    for (int k = 0; k < 3; ++k) { h->lo[k] = FLT_MAX; h->hi[k] = -FLT_MAX; }
+__global__ void knn_init_kernel(KnnHeader* h, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    for (int k = 0; k < 3; ++k) { h[b].lo[k] = FLT_MAX; h[b].hi[k] = -FLT_MAX; }
 }
 
-__global__ void __launch_bounds__(256) knn_bbox_kernel(const float* __restrict__ pts, int N, KnnHeader* h) {
+// grid (x, B): bounding box of every subject
+__global__ void __launch_bounds__(256) knn_bbox_kernel(const float* __restrict__ pts_all, int N, KnnHeader* h_all) {
+    const float* pts = pts_all + size_t(blockIdx.y) * N * 3;
+    KnnHeader* h = h_all + blockIdx.y;
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
 #pragma unroll
@@ -71,7 +81,10 @@ __global__ void __launch_bounds__(256) knn_bbox_kernel(const float* __restrict__
 
 // Cell edge so that an average occupied neighbourhood holds a handful of points: the points are a surface sample, so
 // the edge is derived from the bounding-box surface scale rather than its volume.
-__global__ void knn_grid_kernel(KnnHeader* h, int N) {
+__global__ void knn_grid_kernel(KnnHeader* h_all, int N, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    KnnHeader* h = h_all + b;
     float ext[3];
     for (int k = 0; k < 3; ++k) ext[k] = fmaxf(h->hi[k] - h->lo[k], 1e-12f);
     const float area = 2.0f * (ext[0] * ext[1] + ext[1] * ext[2] + ext[0] * ext[2]);
@@ -101,73 +114,106 @@ __device__ __forceinline__ int3 cell_coord(const KnnHeader* h, float x, float y,
     return c;
 }
 
-__global__ void __launch_bounds__(256) knn_count_kernel(const float* __restrict__ pts, int N, const KnnHeader* h,
-                                                        unsigned int* cell_of, unsigned int* cell_count) {
+__global__ void __launch_bounds__(256) knn_count_kernel(const float* __restrict__ pts_all, int N, const KnnHeader* h_all,
+                                                        unsigned int* cell_of_all, unsigned int* cell_count_all) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    const int b = blockIdx.y;
+    const float* pts = pts_all + size_t(b) * N * 3;
+    const KnnHeader* h = h_all + b;
     const int3 c = cell_coord(h, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
     const unsigned int id = (unsigned(c.z) * h->dim[1] + c.y) * h->dim[0] + c.x;
-    cell_of[i] = id;
-    atomicAdd(cell_count + id, 1u);
+    cell_of_all[size_t(b) * N + i] = id;
+    atomicAdd(cell_count_all + size_t(b) * (kMaxCells + 1) + id, 1u);
 }
 
-// single-CTA exclusive scan of cell counts (<= 2^21 cells): cell_start[c], cell_start[num_cells] = N
-__global__ void __launch_bounds__(1024) knn_scan_kernel(const KnnHeader* h, unsigned int* cell_start /* in: counts */) {
+// Exclusive scan of the cell counts in three grid-wide steps (a single CTA walking up to 2^21 cells was the longest
+// kernel of the whole kNN): per-CTA scans of kScanBlock cells + block totals, a scan of the <= 256 totals, offset add.
+__global__ void __launch_bounds__(kScanThreads) knn_scan_blocks_kernel(const KnnHeader* h_all, unsigned int* cell_start_all,
+                                                                       unsigned int* block_sum_all) {
     __shared__ unsigned int s_warp[32];
-    __shared__ unsigned int s_carry;
-    const unsigned int n = h->num_cells;
+    const int b = blockIdx.y;
+    const unsigned int n = h_all[b].num_cells;
+    const unsigned int base = blockIdx.x * kScanBlock;
+    if (base >= n) return;
+    unsigned int* cell_start = cell_start_all + size_t(b) * (kMaxCells + 1);
     const int t = threadIdx.x;
-    if (t == 0) s_carry = 0;
-    __syncthreads();
-    for (unsigned int base = 0; base < n; base += 1024 * 8) {
-        unsigned int v[8], sum = 0;
+    unsigned int v[kScanPer], sum = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const unsigned int k = base + t * 8 + j;
-            v[j] = k < n ? cell_start[k] : 0u;
-            sum += v[j];
-        }
-        unsigned int inc = sum;
+    for (int j = 0; j < kScanPer; ++j) {
+        const unsigned int k = base + t * kScanPer + j;
+        v[j] = k < n ? cell_start[k] : 0u;
+        sum += v[j];
+    }
+    unsigned int inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int u = __shfl_up_sync(0xffffffffu, inc, d);
+        if ((t & 31) >= d) inc += u;
+    }
+    if ((t & 31) == 31) s_warp[t >> 5] = inc;
+    __syncthreads();
+    if (t < 32) {
+        unsigned int w = s_warp[t], wi = w;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const unsigned int u = __shfl_up_sync(0xffffffffu, inc, d);
-            if ((t & 31) >= d) inc += u;
+            const unsigned int u = __shfl_up_sync(0xffffffffu, wi, d);
+            if (t >= d) wi += u;
         }
-        if ((t & 31) == 31) s_warp[t >> 5] = inc;
-        __syncthreads();
-        if (t < 32) {
-            unsigned int w = s_warp[t], wi = w;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned int u = __shfl_up_sync(0xffffffffu, wi, d);
-                if (t >= d) wi += u;
-            }
-            s_warp[t] = wi - w;
-        }
-        __syncthreads();
-        unsigned int run = s_carry + s_warp[t >> 5] + inc - sum;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const unsigned int k = base + t * 8 + j;
-            if (k < n) cell_start[k] = run;
-            run += v[j];
-        }
-        __syncthreads();
-        if (t == 1023) s_carry = run;
-        __syncthreads();
+        s_warp[t] = wi - w;
+        if (t == 31) block_sum_all[size_t(b) * kScanBlocks + blockIdx.x] = wi;
     }
-    if (t == 0) cell_start[n] = s_carry;
+    __syncthreads();
+    unsigned int run = s_warp[t >> 5] + inc - sum;
+#pragma unroll
+    for (int j = 0; j < kScanPer; ++j) {
+        const unsigned int k = base + t * kScanPer + j;
+        if (k < n) cell_start[k] = run;
+        run += v[j];
+    }
 }
 
-__global__ void __launch_bounds__(256) knn_fill_kernel(const float* __restrict__ pts, int N,
-                                                       const unsigned int* __restrict__ cell_of,
-                                                       const unsigned int* __restrict__ cell_start,
-                                                       unsigned int* cell_fill, float4* sorted) {
+__global__ void __launch_bounds__(kScanBlocks) knn_scan_tops_kernel(const KnnHeader* h_all, unsigned int* block_sum_all,
+                                                                    unsigned int* cell_start_all, int N) {
+    __shared__ unsigned int s_warp[kScanBlocks / 32];
+    const int b = blockIdx.x, t = threadIdx.x;
+    const unsigned int n = h_all[b].num_cells;
+    const unsigned int nblk = (n + kScanBlock - 1) / kScanBlock;
+    unsigned int* bs = block_sum_all + size_t(b) * kScanBlocks;
+    const unsigned int v = unsigned(t) < nblk ? bs[t] : 0u;
+    unsigned int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int u = __shfl_up_sync(0xffffffffu, inc, d);
+        if ((t & 31) >= d) inc += u;
+    }
+    if ((t & 31) == 31) s_warp[t >> 5] = inc;
+    __syncthreads();
+    unsigned int off = 0;
+    for (int w = 0; w < (t >> 5); ++w) off += s_warp[w];
+    bs[t] = off + inc - v;
+    if (t == 0) cell_start_all[size_t(b) * (kMaxCells + 1) + n] = unsigned(N);
+}
+
+__global__ void __launch_bounds__(256) knn_scan_add_kernel(const KnnHeader* h_all, const unsigned int* block_sum_all,
+                                                           unsigned int* cell_start_all) {
+    const int b = blockIdx.y;
+    const unsigned int n = h_all[b].num_cells;
+    for (unsigned int k = kScanBlock + blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+        cell_start_all[size_t(b) * (kMaxCells + 1) + k] += block_sum_all[size_t(b) * kScanBlocks + k / kScanBlock];
+}
+
+__global__ void __launch_bounds__(256) knn_fill_kernel(const float* __restrict__ pts_all, int N,
+                                                       const unsigned int* __restrict__ cell_of_all,
+                                                       const unsigned int* __restrict__ cell_start_all,
+                                                       unsigned int* cell_fill_all, float4* sorted_all) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    const unsigned int c = cell_of[i];
-    const unsigned int pos = cell_start[c] + atomicAdd(cell_fill + c, 1u);
-    sorted[pos] = make_float4(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], __int_as_float(i));
+    const int b = blockIdx.y;
+    const float* pts = pts_all + size_t(b) * N * 3;
+    const unsigned int c = cell_of_all[size_t(b) * N + i];
+    const unsigned int pos = cell_start_all[size_t(b) * (kMaxCells + 1) + c] + atomicAdd(cell_fill_all + size_t(b) * kMaxCells + c, 1u);
+    sorted_all[size_t(b) * N + pos] = make_float4(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], __int_as_float(i));
 }
 
 __device__ __forceinline__ void insert3(float d, float& b0, float& b1, float& b2) {
@@ -179,12 +225,19 @@ __device__ __forceinline__ void insert3(float d, float& b0, float& b1, float& b2
     }
 }
 
-__global__ void __launch_bounds__(128) knn_query_kernel(const float* __restrict__ pts, int N, const KnnHeader* h,
-                                                        const unsigned int* __restrict__ cell_start,
-                                                        const float4* __restrict__ sorted, float* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const float px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
+// One thread per point, IN CELL ORDER (thread j takes sorted[j]): the threads of a warp sit in the same or adjacent
+// cells, so their cell-table and point reads coalesce and their ring walks have the same length.
+__global__ void __launch_bounds__(128) knn_query_kernel(int N, const KnnHeader* h_all,
+                                                        const unsigned int* __restrict__ cell_start_all,
+                                                        const float4* __restrict__ sorted_all, float* __restrict__ out_all) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const int b = blockIdx.y;
+    const KnnHeader* h = h_all + b;
+    const unsigned int* cell_start = cell_start_all + size_t(b) * (kMaxCells + 1);
+    const float4* sorted = sorted_all + size_t(b) * N;
+    const float4 me = sorted[j];
+    const float px = me.x, py = me.y, pz = me.z;
     const int3 c = cell_coord(h, px, py, pz);
     const int dx = h->dim[0], dy = h->dim[1], dz = h->dim[2];
     const float cell = h->cell;
@@ -202,21 +255,33 @@ __global__ void __launch_bounds__(128) knn_query_kernel(const float* __restrict_
         for (int z = max(z0, 0); z <= min(z1, dz - 1); ++z)
             for (int y = max(y0, 0); y <= min(y1, dy - 1); ++y) {
                 const bool shell_row = (z == z0 || z == z1 || y == y0 || y == y1);
-                const int step = shell_row ? 1 : max(1, x1 - x0);        // interior rows: only the two end cells
-                for (int x = x0; x <= x1; x += step) {
-                    if (x < 0 || x >= dx) continue;
-                    const unsigned int id = (unsigned(z) * dy + y) * dx + x;
-                    const unsigned int s = cell_start[id], e = cell_start[id + 1];
+                if (shell_row) {
+                    // the row's cells are consecutive in the table: one [start, end) range for the whole row
+                    const int xa = max(x0, 0), xb = min(x1, dx - 1);
+                    const unsigned int id = (unsigned(z) * dy + y) * dx;
+                    const unsigned int s = cell_start[id + xa], e = cell_start[id + xb + 1];
                     for (unsigned int k = s; k < e; ++k) {
                         const float4 q = __ldg(sorted + k);
-                        if (__float_as_int(q.w) == i) continue;
+                        if (k == unsigned(j)) continue;
                         const float ddx = q.x - px, ddy = q.y - py, ddz = q.z - pz;
                         insert3(ddx * ddx + ddy * ddy + ddz * ddz, b0, b1, b2);
+                    }
+                } else {                                  // interior rows: only the two end cells
+                    for (int x = x0; x <= x1; x += max(1, x1 - x0)) {
+                        if (x < 0 || x >= dx) continue;
+                        const unsigned int id = (unsigned(z) * dy + y) * dx + x;
+                        const unsigned int s = cell_start[id], e = cell_start[id + 1];
+                        for (unsigned int k = s; k < e; ++k) {
+                            const float4 q = __ldg(sorted + k);
+                            if (k == unsigned(j)) continue;
+                            const float ddx = q.x - px, ddy = q.y - py, ddz = q.z - pz;
+                            insert3(ddx * ddx + ddy * ddy + ddz * ddz, b0, b1, b2);
+                        }
                     }
                 }
             }
     }
-    out[i] = (b0 + b1 + b2) / 3.0f;
+    out_all[size_t(b) * N + __float_as_int(me.w)] = (b0 + b1 + b2) / 3.0f;
 }
 
 }  // namespace
@@ -226,19 +291,21 @@ using namespace sgr;
 
 extern "C" {
 
-uint64_t sgr_knn_scratch_bytes(int32_t num_points) {
-    if (num_points < 0) return 0;
-    return knn_layout(num_points).total;
+uint64_t sgr_knn_scratch_bytes_batched(int32_t num_subjects, int32_t num_points) {
+    if (num_points < 0 || num_subjects <= 0) return 0;
+    return knn_layout(num_subjects, num_points).total;
 }
+uint64_t sgr_knn_scratch_bytes(int32_t num_points) { return sgr_knn_scratch_bytes_batched(1, num_points); }
 
 // defined in sgr_api.cu
 int sgr_set_error_(int code, const char* msg);
+void sgr_count_launches_(unsigned int n);
 
-int sgr_knn_mean_dist2(const float* points, int32_t N, float* out, void* scratch, uint64_t scratch_bytes,
-                       void* stream) {
-    if (N < 0 || (N > 0 && (!points || !out))) return sgr_set_error_(SGR_E_INVALID_ARGUMENT, "bad knn arguments");
+int sgr_knn_mean_dist2_batched(const float* points, int32_t B, int32_t N, float* out, void* scratch,
+                               uint64_t scratch_bytes, void* stream) {
+    if (B <= 0 || N < 0 || (N > 0 && (!points || !out))) return sgr_set_error_(SGR_E_INVALID_ARGUMENT, "bad knn arguments");
     if (N == 0) return SGR_OK;
-    const KnnLayout L = knn_layout(N);
+    const KnnLayout L = knn_layout(B, N);
     if (!scratch || scratch_bytes < L.total) return sgr_set_error_(SGR_E_BUFFER_TOO_SMALL, "knn scratch buffer too small");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     char* x = static_cast<char*>(scratch);
@@ -246,20 +313,30 @@ int sgr_knn_mean_dist2(const float* points, int32_t N, float* out, void* scratch
     unsigned int* cell_of = reinterpret_cast<unsigned int*>(x + L.cell_of);
     unsigned int* cell_start = reinterpret_cast<unsigned int*>(x + L.cell_start);
     unsigned int* cell_fill = reinterpret_cast<unsigned int*>(x + L.cell_fill);
+    unsigned int* block_sum = reinterpret_cast<unsigned int*>(x + L.block_sum);
     float4* sorted = reinterpret_cast<float4*>(x + L.sorted);
     cudaError_t e;
-    if ((e = cudaMemsetAsync(cell_start, 0, (uint64_t(kMaxCells) + 1) * 4, s)) != cudaSuccess ||
-        (e = cudaMemsetAsync(cell_fill, 0, uint64_t(kMaxCells) * 4, s)) != cudaSuccess)
+    // cell_start and cell_fill are adjacent: one memset
+    if ((e = cudaMemsetAsync(cell_start, 0, L.block_sum - L.cell_start, s)) != cudaSuccess)
         return sgr_set_error_(SGR_E_CUDA, cudaGetErrorString(e));
-    knn_init_kernel<<<1, 1, 0, s>>>(h);
-    knn_bbox_kernel<<<min((N + 255) / 256, 592), 256, 0, s>>>(points, N, h);
-    knn_grid_kernel<<<1, 1, 0, s>>>(h, N);
-    knn_count_kernel<<<(N + 255) / 256, 256, 0, s>>>(points, N, h, cell_of, cell_start);
-    knn_scan_kernel<<<1, 1024, 0, s>>>(h, cell_start);
-    knn_fill_kernel<<<(N + 255) / 256, 256, 0, s>>>(points, N, cell_of, cell_start, cell_fill, sorted);
-    knn_query_kernel<<<(N + 127) / 128, 128, 0, s>>>(points, N, h, cell_start, sorted, out);
+    const int gb = (N + 255) / 256;
+    knn_init_kernel<<<(B + 31) / 32, 32, 0, s>>>(h, B);
+    knn_bbox_kernel<<<dim3(min(gb, 148), B), 256, 0, s>>>(points, N, h);
+    knn_grid_kernel<<<(B + 31) / 32, 32, 0, s>>>(h, N, B);
+    knn_count_kernel<<<dim3(gb, B), 256, 0, s>>>(points, N, h, cell_of, cell_start);
+    knn_scan_blocks_kernel<<<dim3(kScanBlocks, B), kScanThreads, 0, s>>>(h, cell_start, block_sum);
+    knn_scan_tops_kernel<<<B, kScanBlocks, 0, s>>>(h, block_sum, cell_start, N);
+    knn_scan_add_kernel<<<dim3(296, B), 256, 0, s>>>(h, block_sum, cell_start);
+    knn_fill_kernel<<<dim3(gb, B), 256, 0, s>>>(points, N, cell_of, cell_start, cell_fill, sorted);
+    knn_query_kernel<<<dim3((N + 127) / 128, B), 128, 0, s>>>(N, h, cell_start, sorted, out);
     if ((e = cudaGetLastError()) != cudaSuccess) return sgr_set_error_(SGR_E_CUDA, cudaGetErrorString(e));
+    sgr_count_launches_(9);
     return SGR_OK;
+}
+
+int sgr_knn_mean_dist2(const float* points, int32_t N, float* out, void* scratch, uint64_t scratch_bytes,
+                       void* stream) {
+    return sgr_knn_mean_dist2_batched(points, 1, N, out, scratch, scratch_bytes, stream);
 }
 
 }  // extern "C"

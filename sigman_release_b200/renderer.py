@@ -16,7 +16,7 @@ import torch
 from . import _native
 from .rasterizer import _ptr, rasterize_batch
 
-__all__ = ["GaussianRenderer", "distCUDA2", "get_covariance", "strip_lowerdiag", "prep_cov3d"]
+__all__ = ["GaussianRenderer", "distCUDA2", "distCUDA2_batched", "get_covariance", "strip_lowerdiag", "prep_cov3d"]
 
 
 def distCUDA2(points: torch.Tensor) -> torch.Tensor:
@@ -35,6 +35,25 @@ def distCUDA2(points: torch.Tensor) -> torch.Tensor:
         st = torch.cuda.current_stream(pts.device)
         _native.check(L.sgr_knn_mean_dist2(_ptr(pts), N, _ptr(out), _ptr(scratch), nbytes,
                                            ctypes.c_void_p(st.cuda_stream)))
+    return out
+
+
+def distCUDA2_batched(points: torch.Tensor) -> torch.Tensor:
+    """``distCUDA2`` for B independent point sets [B,N,3] -> [B,N] in one launch set (gs.py:62-70 calls it per subject)."""
+    L = _native.lib()
+    if not points.is_cuda:
+        raise ValueError("distCUDA2_batched needs a CUDA tensor (no CPU path)")
+    pts = points.detach().contiguous().float()
+    if pts.dim() != 3 or pts.shape[2] != 3:
+        raise ValueError("points must be [B,N,3]")
+    B, N = int(pts.shape[0]), int(pts.shape[1])
+    out = torch.empty((B, N), dtype=torch.float32, device=pts.device)
+    nbytes = int(L.sgr_knn_scratch_bytes_batched(B, N))
+    with torch.cuda.device(pts.device):
+        scratch = torch.empty((nbytes,), dtype=torch.uint8, device=pts.device)
+        st = torch.cuda.current_stream(pts.device)
+        _native.check(L.sgr_knn_mean_dist2_batched(_ptr(pts), B, N, _ptr(out), _ptr(scratch), nbytes,
+                                                   ctypes.c_void_p(st.cuda_stream)))
     return out
 
 
@@ -110,7 +129,7 @@ class GaussianRenderer:
         rgbs = gaussians["rgb"].contiguous().float()
         B = means3D.shape[0]
         with torch.no_grad():
-            dist2 = torch.stack([distCUDA2(means3D[b]) for b in range(B)])      # detached kNN factor (gs.py:70-71)
+            dist2 = distCUDA2_batched(means3D)                  # detached kNN factor (gs.py:70-71), all subjects
         cov3D = prep_cov3d(scales, rot, dist2, bf16_autocast=self.bf16_autocast)
         return means3D, cov3D, rgbs, opacity
 

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# Parity tests check every forward synchronously (a capacity overflow is retried inside the call); the deferred,
+# non-blocking mode of the training path is exercised by the tests that switch it on explicitly.
+os.environ.setdefault("SGR_OVERFLOW_CHECK", "sync")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -282,6 +282,17 @@ def test_knn_mean_dist2_matches_bruteforce_oracle():
     np.testing.assert_array_equal(got, oracle.knn_mean_dist2(pts))
 
 
+def test_knn_batched_equals_per_subject_calls():
+    from sigman_release_b200.renderer import distCUDA2, distCUDA2_batched
+    pts = np.stack([scenes.body_gaussians(30_000, seed=s, jitter=1.0)["means3D"] for s in range(3)])
+    pts[2, :5] = pts[2, 5]                                       # coincident points: zero distances
+    t = to_dev(pts)
+    got = distCUDA2_batched(t)
+    for b in range(3):
+        assert torch.equal(got[b], distCUDA2(t[b]))
+    np.testing.assert_array_equal(got[1, :4000].cpu().numpy(), oracle.knn_mean_dist2(pts[1])[:4000])
+
+
 def test_cov3d_from_scale_rot_and_backward():
     rng = np.random.default_rng(3)
     n = 1000
