@@ -52,6 +52,24 @@ def batch_rodrigues(rot_vecs: torch.Tensor) -> torch.Tensor:
     return eye + s * K + (1 - c) * torch.bmm(K, K)
 
 
+def _times_skew(M: torch.Tensor, axis: torch.Tensor) -> torch.Tensor:
+    """M @ [axis]_x for M [n,3,3], axis [n,3] with elementwise ops (a batched 3x3 bmm runs as 10^5..10^6 tiny SIMT
+    GEMMs and would dominate the step)."""
+    x, y, z = axis[:, 0:1], axis[:, 1:2], axis[:, 2:3]
+    c0, c1, c2 = M[:, :, 0], M[:, :, 1], M[:, :, 2]
+    return torch.stack([c1 * z - c2 * y, c2 * x - c0 * z, c0 * y - c1 * x], dim=2)
+
+
+def compose_rotation(init_rot: torch.Tensor, rot_vecs: torch.Tensor) -> torch.Tensor:
+    """``init_rot @ batch_rodrigues(rot_vecs)`` (autoencoder.py:333-334) without bmm:
+    A (I + sin K + (1 - cos) K^2) = A + sin (A K) + (1 - cos) (A K) K."""
+    angle = torch.norm(rot_vecs + 1e-8, dim=1, keepdim=True)
+    axis = rot_vecs / angle
+    AK = _times_skew(init_rot, axis)
+    AKK = _times_skew(AK, axis)
+    return init_rot + torch.sin(angle)[:, :, None] * AK + (1 - torch.cos(angle))[:, :, None] * AKK
+
+
 class AttributeHead(torch.nn.Module):
     """The shared (DDP-synchronised) parameters of the stand-in: a per-channel affine map of the 13 features."""
 
@@ -72,7 +90,7 @@ def gaussians_from_features(feats: torch.Tensor, init_pcd: torch.Tensor, init_ro
     rgb = rgb * (1 + SIGMOID_SATURATION * 2) - SIGMOID_SATURATION
     scale = (scale - 0.5) * 2
     rot = (rot - 0.5) * math.pi
-    R = torch.bmm(init_rot.reshape(-1, 3, 3), batch_rodrigues(rot.reshape(-1, 3))).reshape(B, N, 3, 3)
+    R = compose_rotation(init_rot.reshape(-1, 3, 3), rot.reshape(-1, 3)).reshape(B, N, 3, 3)
     return {"position": init_pcd + offset, "opacity": opacity, "scale": scale, "cov3d": R, "rgb": rgb}
 
 

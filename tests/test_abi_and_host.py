@@ -118,3 +118,19 @@ def test_product_does_not_import_oracle():
                 txt = open(path).read()
                 assert not re.search(r"#include\s+[<\"][^>\"]*oracle", txt), path
                 assert "libsgr_oracle" not in txt and "-lsgr_oracle" not in txt, path
+
+
+def test_driver_rotation_composition_matches_bmm():
+    """train_driver.compose_rotation (elementwise) == init_rot @ batch_rodrigues(v) (autoencoder.py:333-334)."""
+    import torch
+    from sigman_release_b200.train_driver import batch_rodrigues, compose_rotation, gaussians_from_features
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn((50, 3, 3), generator=g, dtype=torch.float64)
+    v = torch.randn((50, 3), generator=g, dtype=torch.float64)
+    assert torch.allclose(compose_rotation(A, v), torch.bmm(A, batch_rodrigues(v)), atol=1e-12)
+    R = batch_rodrigues(v)
+    assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3, dtype=torch.float64).expand(50, 3, 3), atol=1e-6)
+    feats = torch.randn((2, 7, 13), generator=g)
+    out = gaussians_from_features(feats, torch.zeros((2, 7, 3)), torch.eye(3).expand(2, 7, 3, 3))
+    assert out["position"].shape == (2, 7, 3) and out["cov3d"].shape == (2, 7, 3, 3)
+    assert float(out["opacity"].min()) > 0 and float(out["scale"].abs().max()) < 1 and float(out["rgb"].max()) <= 1.001

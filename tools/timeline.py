@@ -27,6 +27,11 @@ def step():
     loss = rasterizer.render_l1_loss(t["means3D"], t["cov3D"], t["colors"], t["opacities"], vmt, pmt, bg, H, W, tan, tan, target)[0]
     loss.backward()
 
+if len(sys.argv) > 1 and sys.argv[1] == "driver":      # the config-5 stand-in step instead of the bench step
+    from sigman_release_b200.train_driver import RenderLossTrainer
+    tr = RenderLossTrainer(8, 10, 100_000, 512, torch.device("cuda", 0), seed=0)
+    step = tr.step
+
 for _ in range(5):
     step()
 torch.cuda.synchronize()
