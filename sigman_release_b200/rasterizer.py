@@ -283,6 +283,8 @@ def rasterize_batch(means3D, cov3D, colors, opacities, viewmatrix, projmatrix, b
     if not (torch.is_grad_enabled() and any(t is not None and t.requires_grad
                                             for t in (means3D, cov3D, colors, opacities, means2D))):
         flags |= _native.FLAG_FORWARD_ONLY           # no backward can follow: skip the forward's bookkeeping for it
+    if os.environ.get("SGR_TILE_TIMING"):            # diagnostics (tools/tile_timing.py)
+        flags |= _native.FLAG_TILE_TIMING
     return _RasterizeBatch.apply(means3D, cov3D, colors, opacities, means2D, viewmatrix, projmatrix, bg,
                                  int(image_height), int(image_width), float(tanfovx), float(tanfovy), flags,
                                  int(renders_per_chunk), None, None)
