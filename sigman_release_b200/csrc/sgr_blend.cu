@@ -30,8 +30,15 @@
 namespace sgr {
 namespace {
 
-constexpr int kBatch = 64;                     // records per ring stage (culled 32 at a time: lane = record)
-constexpr int kFwdStages = 3;                  // per-warp TMA ring depth, forward
+#ifndef SGR_FWD_BATCH
+#define SGR_FWD_BATCH 128
+#endif
+#ifndef SGR_FWD_STAGES
+#define SGR_FWD_STAGES 2
+#endif
+constexpr int kFwdBatch = SGR_FWD_BATCH;       // records per ring stage (culled 32 at a time: lane = record), forward
+constexpr int kBwdBatch = 64;                  // ... backward
+constexpr int kFwdStages = SGR_FWD_STAGES;     // per-warp TMA ring depth, forward
 constexpr int kBwdStages = 2;                  // backward (larger stash; keeps two CTAs per SM)
 constexpr int kWarpsPerCta = 8;
 constexpr int kBlendThreads = kWarpsPerCta * 32;
@@ -91,7 +98,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
-template <int kStashes, int kDepth, int kNumStages>
+template <int kStashes, int kDepth, int kNumStages, int kBatch>
 struct WarpSmem {
     static constexpr int stages = kNumStages;
     float4 r0[kNumStages][kBatch + 1];          // slot kBatch of every stage = the sentinel record (never blends)
@@ -109,7 +116,7 @@ struct WarpSmem {
 // tile sort, sgr_common.cuh::quarter_mask), one ballot per quarter, warp-parallel compaction of the survivors'
 // batch-local indices into list[quarter][...] (ascending; descending with kReverse — the backward walks back to front);
 // unused list entries point at the sentinel record.  Returns the four survivor counts.
-template <bool kReverse>
+template <bool kReverse, int kBatch>
 __device__ __forceinline__ uint4 cull_batch(const float4* r0, unsigned int m, int blk, unsigned char (*list)[kBatch],
                                             int lane) {
     // lanes before (ascending) / after (descending) this one
@@ -117,7 +124,8 @@ __device__ __forceinline__ uint4 cull_batch(const float4* r0, unsigned int m, in
     {                             // every list entry the compaction does not overwrite points at the sentinel record
         unsigned int* lw = reinterpret_cast<unsigned int*>(&list[0][0]);
         const unsigned int fill = kBatch * 0x01010101u;
-        lw[lane] = fill; lw[lane + 32] = fill;
+#pragma unroll
+        for (int w = 0; w < kBatch; w += 32) lw[w + lane] = fill;
         __syncwarp();
     }
     const unsigned int* words = reinterpret_cast<const unsigned int*>(r0);
@@ -220,8 +228,8 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-using FwdSmem = WarpSmem<1, 1, kFwdStages>;      // the forward needs no stash
-using BwdSmem = WarpSmem<3, kBwdSlots, kBwdStages>;
+using FwdSmem = WarpSmem<1, 1, kFwdStages, kFwdBatch>;      // the forward needs no stash
+using BwdSmem = WarpSmem<3, kBwdSlots, kBwdStages, kBwdBatch>;
 
 #ifndef SGR_FWD_MIN_CTAS
 #define SGR_FWD_MIN_CTAS 2
@@ -248,11 +256,12 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
     unsigned int issued = 0, consumed = 0;       // ring counters (warp-uniform)
     const bool refine = a.refine_masks != 0;
     unsigned char* hit_bytes = reinterpret_cast<unsigned char*>(sm.hit) + qsel;       // indexed with 4 * j
-    sm.hit[lane] = 0u; sm.hit[lane + 32] = 0u;
+#pragma unroll
+    for (int w = 0; w < kFwdBatch; w += 32) sm.hit[w + lane] = 0u;
     if (lane < kFwdStages) {      // the sentinel record: threshold +inf -> never valid, alpha 0, colour 0
-        sm.r0[lane][kBatch] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0x7f800000));
-        sm.r1[lane][kBatch] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        sm.r2[lane][kBatch] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        sm.r0[lane][kFwdBatch] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0x7f800000));
+        sm.r1[lane][kFwdBatch] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        sm.r2[lane][kFwdBatch] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     __syncwarp();
 
@@ -268,7 +277,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
         const size_t tg = size_t(r) * a.g.num_tiles + tile;
         const unsigned int n = a.tile_cnt[tg];
         const size_t off = a.tile_off[tg];
-        const unsigned int nb = (n + kBatch - 1) / kBatch;
+        const unsigned int nb = (n + kFwdBatch - 1) / kFwdBatch;
         const int tx = tile % a.g.tiles_x, ty = tile / a.g.tiles_x;
         const int bx0 = tx * kTile + (blk & 1) * kBlockW, by0 = ty * kTile + (blk >> 1) * kBlockH;
         if (bx0 >= a.g.W || by0 >= a.g.H) {                        // block entirely outside the image
@@ -286,25 +295,25 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
         bool done = !inside;
         unsigned int b_issued = 0;
         while (b_issued < nb && b_issued < unsigned(kFwdStages - 1)) {
-            ring_issue(sm, issued, g0 + b_issued * kBatch, g1 + b_issued * kBatch, g2 + b_issued * kBatch,
-                       min(unsigned(kBatch), n - b_issued * kBatch), lane);
+            ring_issue(sm, issued, g0 + b_issued * kFwdBatch, g1 + b_issued * kFwdBatch, g2 + b_issued * kFwdBatch,
+                       min(unsigned(kFwdBatch), n - b_issued * kFwdBatch), lane);
             ++issued; ++b_issued;
         }
         for (unsigned int b = 0; b < nb; ++b) {
             if (b_issued < nb) {                 // refill the slot consumed in the previous iteration
-                ring_issue(sm, issued, g0 + b_issued * kBatch, g1 + b_issued * kBatch, g2 + b_issued * kBatch,
-                           min(unsigned(kBatch), n - b_issued * kBatch), lane);
+                ring_issue(sm, issued, g0 + b_issued * kFwdBatch, g1 + b_issued * kFwdBatch, g2 + b_issued * kFwdBatch,
+                           min(unsigned(kFwdBatch), n - b_issued * kFwdBatch), lane);
                 ++issued; ++b_issued;
             }
             const int s = consumed % kFwdStages;
             mbar_wait(&sm.full[s], (consumed / kFwdStages) & 1);
             ++consumed;
-            const unsigned int m = min(unsigned(kBatch), n - b * kBatch);
-            const unsigned int cbase = b * kBatch;
+            const unsigned int m = min(unsigned(kFwdBatch), n - b * kFwdBatch);
+            const unsigned int cbase = b * kFwdBatch;
             const float4* r0 = sm.r0[s];
             const float4* r1 = sm.r1[s];
             const float4* r2 = sm.r2[s];
-            const uint4 cnt = cull_batch<false>(r0, m, blk, sm.list, lane);
+            const uint4 cnt = cull_batch<false, kFwdBatch>(r0, m, blk, sm.list, lane);
             // quarters whose 8 pixels are all finished need no further evaluation
             const unsigned int dmask = __ballot_sync(kFull, done);
             const unsigned int my_n = ((dmask & qmask) == qmask) ? 0u : (qsel == 0 ? cnt.x : qsel == 1 ? cnt.y : qsel == 2 ? cnt.z : cnt.w);
@@ -364,7 +373,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
 #endif
                 const unsigned int* words = reinterpret_cast<const unsigned int*>(r0);
 #pragma unroll
-                for (unsigned int sub = 0; sub < unsigned(kBatch); sub += 32) {
+                for (unsigned int sub = 0; sub < unsigned(kFwdBatch); sub += 32) {
                     const unsigned int e = sub + lane;
                     if (e < m) {
                         const unsigned int nib = (words[4 * e + 2] >> (4 * blk)) & 0xfu;
@@ -380,8 +389,8 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
                 __syncwarp();
             }
             // lists longer than one backward segment: checkpoint the running state at every segment boundary
-            if (n > unsigned(kSegment) && ((b + 1) * kBatch) % kSegment == 0 && (b + 1) * kBatch < n) {
-                const size_t ci = ((off / (kSegment / 2) + (b + 1) * kBatch / kSegment - 1) * kBlocksPerTile + blk) * 32 + lane;
+            if (n > unsigned(kSegment) && ((b + 1) * kFwdBatch) % kSegment == 0 && (b + 1) * kFwdBatch < n) {
+                const size_t ci = ((off / (kSegment / 2) + (b + 1) * kFwdBatch / kSegment - 1) * kBlocksPerTile + blk) * 32 + lane;
                 a.ck0[ci] = make_float4(T, C0, C1, C2);
                 a.ck1[ci] = D;
             }
@@ -499,9 +508,9 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
     __syncwarp();
     const int qsel = ((lane >> 2) & 1) | ((lane >> 3) & 2);        // 4x2 pixel quarter of this lane: x half | 2 * y half
     if (lane < kBwdStages) {      // the sentinel record: threshold +inf -> never valid
-        sm.r0[lane][kBatch] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0x7f800000));
-        sm.r1[lane][kBatch] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        sm.r2[lane][kBatch] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        sm.r0[lane][kBwdBatch] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0x7f800000));
+        sm.r1[lane][kBwdBatch] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        sm.r2[lane][kBwdBatch] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     __syncwarp();
     float (*stA)[32] = sm.stash[0];             // phase A: alpha; phase B overwrites it with dL/dalpha
@@ -545,7 +554,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
         }
         sm.dpix[0][lane] = dp0; sm.dpix[1][lane] = dp1; sm.dpix[2][lane] = dp2; sm.dpix[3][lane] = ddep;
         __syncwarp();
-        const unsigned int nb = (hi - lo + kBatch - 1) / kBatch;
+        const unsigned int nb = (hi - lo + kBwdBatch - 1) / kBwdBatch;
         const float pxf = float(px), pyf = float(py);
         const float wx0 = float(bx0), wy0 = float(by0);
         const float4 *g0 = a.rec0 + off + lo, *g1 = a.rec1 + off + lo, *g2 = a.rec2 + off + lo;
@@ -573,26 +582,26 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
         unsigned int b_issued = 0;
         while (b_issued < nb && b_issued < unsigned(kBwdStages - 1)) {
             const unsigned int lb = nb - 1 - b_issued;
-            ring_issue(sm, issued, g0 + lb * kBatch, g1 + lb * kBatch, g2 + lb * kBatch,
-                       min(unsigned(kBatch), hi - lo - lb * kBatch), lane);
+            ring_issue(sm, issued, g0 + lb * kBwdBatch, g1 + lb * kBwdBatch, g2 + lb * kBwdBatch,
+                       min(unsigned(kBwdBatch), hi - lo - lb * kBwdBatch), lane);
             ++issued; ++b_issued;
         }
         for (unsigned int b = 0; b < nb; ++b) {
             if (b_issued < nb) {
                 const unsigned int lb = nb - 1 - b_issued;
-                ring_issue(sm, issued, g0 + lb * kBatch, g1 + lb * kBatch, g2 + lb * kBatch,
-                           min(unsigned(kBatch), hi - lo - lb * kBatch), lane);
+                ring_issue(sm, issued, g0 + lb * kBwdBatch, g1 + lb * kBwdBatch, g2 + lb * kBwdBatch,
+                           min(unsigned(kBwdBatch), hi - lo - lb * kBwdBatch), lane);
                 ++issued; ++b_issued;
             }
             const int s = consumed % kBwdStages;
             mbar_wait(&sm.full[s], (consumed / kBwdStages) & 1);
             ++consumed;
-            const unsigned int cbase = lo + (nb - 1 - b) * kBatch;     // list index of the batch's first record
-            const unsigned int m = min(unsigned(kBatch), hi - cbase);
+            const unsigned int cbase = lo + (nb - 1 - b) * kBwdBatch;     // list index of the batch's first record
+            const unsigned int m = min(unsigned(kBwdBatch), hi - cbase);
             const float4* r0 = sm.r0[s];
             const float4* r1 = sm.r1[s];
             const float4* r2 = sm.r2[s];
-            const uint4 cnt = cull_batch<true>(r0, m, blk, sm.list, lane);
+            const uint4 cnt = cull_batch<true, kBwdBatch>(r0, m, blk, sm.list, lane);
             const int total = int(max(max(cnt.x, cnt.y), max(cnt.z, cnt.w)));
             // trip t of the batch handles the quarter's survivor number (my_n - 1 - t): back to front
             const float nTb = -T_final * bg_dot;
