@@ -223,6 +223,7 @@ def run_ours(args):
     h2d_bytes = sum(v.numel() * 4 for v in host.values())
     d2h_bytes = sum(v.numel() * 4 for v in grads_host[0].values()) + 4
     e2e_k = [0]
+    held = [None, None]
 
     def upload(slot):
         with torch.cuda.stream(copy_stream), torch.no_grad():
@@ -242,9 +243,8 @@ def run_ours(args):
         computed[slot].record(main)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(computed[slot])
-            for name in host:
-                g = e2e_dev[slot][name].grad
-                g.record_stream(copy_stream)
+            held[slot] = [e2e_dev[slot][name].grad for name in host]     # kept alive until d2h_done[slot] was waited on
+            for name, g in zip(host, held[slot]):
                 grads_host[slot][name].copy_(g, non_blocking=True)
             loss_host[slot].copy_(loss.detach(), non_blocking=True)
             d2h_done[slot].record(copy_stream)
@@ -255,6 +255,8 @@ def run_ours(args):
     def e2e_finish():                                      # results of the last step
         torch.cuda.current_stream(dev).wait_event(d2h_done[(e2e_k[0] - 1) % 2])
 
+    host_ms = []
+
     def timed(fn, steps, warmup, finish=None):
         for _ in range(warmup):
             fn()
@@ -263,11 +265,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t_host = time.perf_counter()
         for s, e in evs:
             flush_buf.zero_()
             s.record()
             fn()
             e.record()
+        host_ms.append((time.perf_counter() - t_host) * 1e3 / steps)       # host time to enqueue one step
         if finish is not None:
             evs.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
             evs[-1][0].record()
@@ -356,6 +360,7 @@ def run_ours(args):
                 "pipeline": "pinned host -> device upload of step k+1 and device -> pinned host download of the "
                             "gradients + loss of step k on a copy stream, overlapped with the compute of step k"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        "host_enqueue_ms_per_step": {"value_leg": host_ms[0], "e2e_leg": host_ms[1]},
         "status": rasterizer.last_status(),
     }
     if world == 1 and not args.no_cpu_baseline:

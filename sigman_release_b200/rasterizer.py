@@ -64,21 +64,32 @@ def _status_from_bytes(t: torch.Tensor) -> dict:
                 nonempty_tiles=int(st.nonempty_tiles))
 
 
+_status_pool: list = []        # recycled (pinned 64-byte buffer, event) pairs of the deferred status copies
+
+
+def _status_slot():
+    if _status_pool:
+        return _status_pool.pop()
+    return torch.empty((64,), dtype=torch.uint8, pin_memory=True), torch.cuda.Event()
+
+
 def _drain_pending(block: bool) -> None:
     global _last_status
     keep = []
-    for ev, pinned, key, R in _pending:
+    todo = list(_pending)
+    for idx, (ev, pinned, key, R) in enumerate(todo):
         if not block and not ev.query():
             keep.append((ev, pinned, key, R))
             continue
         ev.synchronize()
         st = _status_from_bytes(pinned)
+        _status_pool.append((pinned, ev))
         _last_status = st
         _max_tile_hint[key[1:]] = max(_max_tile_hint.get(key[1:], 0), st["max_tile_instances"])
         per = int(st["instances_required"] / max(R, 1) * _HEADROOM) + 1024
         _est_per_render[key] = max(_est_per_render.get(key, 0), per)
         if st["overflow"]:
-            _pending[:] = keep
+            _pending[:] = keep + todo[idx + 1:]
             raise _native.SgrError(
                 _native.SGR_E_INSTANCE_OVERFLOW,
                 f"a previous deferred-check render overflowed its instance capacity "
@@ -170,9 +181,8 @@ class _RasterizeBatch(torch.autograd.Function):
                     a.loss_scale = 1.0 / float(B * V * 3 * H * W)
                 _native.check(L.sgr_forward(ctypes.byref(a)))
                 if not sync_check:
-                    pinned = torch.empty((64,), dtype=torch.uint8, pin_memory=True)
+                    pinned, ev = _status_slot()
                     pinned.copy_(state[:64], non_blocking=True)
-                    ev = torch.cuda.Event()
                     ev.record(stream)
                     _pending.append((ev, pinned, key, R))
                     break
