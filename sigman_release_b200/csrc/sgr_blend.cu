@@ -37,9 +37,15 @@ namespace {
 #define SGR_FWD_STAGES 2
 #endif
 constexpr int kFwdBatch = SGR_FWD_BATCH;       // records per ring stage (culled 32 at a time: lane = record), forward
-constexpr int kBwdBatch = 64;                  // ... backward
+#ifndef SGR_BWD_BATCH
+#define SGR_BWD_BATCH 128
+#endif
+#ifndef SGR_BWD_STAGES
+#define SGR_BWD_STAGES 1
+#endif
+constexpr int kBwdBatch = SGR_BWD_BATCH;       // ... backward
 constexpr int kFwdStages = SGR_FWD_STAGES;     // per-warp TMA ring depth, forward
-constexpr int kBwdStages = 2;                  // backward (larger stash; keeps two CTAs per SM)
+constexpr int kBwdStages = SGR_BWD_STAGES;     // backward: one 128-record stage (the stash takes the rest of the budget)
 constexpr int kWarpsPerCta = 8;
 constexpr int kBlendThreads = kWarpsPerCta * 32;
 constexpr int kBlocksPerTile = 8;              // a 16x16 tile = eight 8x4 pixel blocks = eight work items
