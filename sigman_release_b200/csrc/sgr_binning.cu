@@ -51,41 +51,48 @@ __device__ __forceinline__ int size_class(unsigned int c) {
 }
 
 __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
-    __shared__ unsigned int s_warp[32];
-    __shared__ unsigned int s_total, s_max, s_nonempty, s_dropped, s_segbase;
+    // Both scanned quantities travel in one 64-bit word: instances (high 40 bits) and empty tiles (low 24 bits) —
+    // most tiles of a human render are empty, so their list positions come from the scan, not from atomics.
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_total;
+    __shared__ unsigned int s_max, s_nonempty, s_dropped, s_segbase;
     __shared__ unsigned long long s_base;
     __shared__ unsigned int s_hist[kSizeClasses], s_start[kSizeClasses], s_hseg[kSizeClasses], s_sseg[kSizeClasses];
     const int t = threadIdx.x;
     const int ipt = (a.n + kScanThreads - 1) / kScanThreads;
     const int lo = min(a.n, t * ipt), hi = min(a.n, lo + ipt);
-    unsigned int sum = 0, mx = 0, ne = 0;
+    unsigned int mx = 0, ne = 0;
+    unsigned long long sum = 0;
     for (int k = lo; k < hi; ++k) {
         const unsigned int c = a.tile_cnt[k];
-        sum += c; mx = max(mx, c); ne += (c != 0);
+        sum += (static_cast<unsigned long long>(c) << 24) + (c == 0 ? 1ull : 0ull);
+        mx = max(mx, c); ne += (c != 0);
     }
     if (t == 0) { s_max = 0; s_nonempty = 0; }
     if (t < kSizeClasses) { s_hist[t] = 0; s_hseg[t] = 0; }
     // block exclusive scan of `sum`
-    unsigned int inc = sum;
+    unsigned long long inc = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const unsigned int v = __shfl_up_sync(0xffffffffu, inc, d);
+        const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, d);
         if ((t & 31) >= d) inc += v;
     }
     if ((t & 31) == 31) s_warp[t >> 5] = inc;
     __syncthreads();
     if (t < 32) {
-        unsigned int w = s_warp[t], wi = w;
+        unsigned long long w = s_warp[t], wi = w;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const unsigned int v = __shfl_up_sync(0xffffffffu, wi, d);
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, wi, d);
             if (t >= d) wi += v;
         }
         s_warp[t] = wi - w;                       // exclusive warp prefix
         if (t == 31) s_total = wi;
     }
     __syncthreads();
-    const unsigned int excl = inc - sum + s_warp[t >> 5];
+    const unsigned long long excl64 = inc - sum + s_warp[t >> 5];
+    const unsigned int excl = static_cast<unsigned int>(excl64 >> 24);
+    unsigned int empty_pos = static_cast<unsigned int>(excl64 & 0xffffffull);
     if (t == 0) {
         if (a.first_chunk) {
             a.header->inst_required = 0; a.header->capacity = a.capacity; a.header->overflow = 0;
@@ -93,7 +100,7 @@ __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
             a.header->inst_cursor = 0;
         }
         const unsigned long long base = a.header->inst_cursor;
-        const unsigned long long total = s_total;
+        const unsigned long long total = s_total >> 24;
         a.header->inst_required += total;
         const bool fits = base + total <= a.header->capacity;
         s_dropped = fits ? 0u : 1u;
@@ -116,8 +123,8 @@ __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
             a.tile_off[k] = run;
             run += c;
         }
-        atomicAdd(&s_hist[size_class(c)], 1u);
         if (c != 0) {
+            atomicAdd(&s_hist[size_class(c)], 1u);
             const unsigned int nfull = c / kSegment, rem = c - nfull * kSegment;
             if (nfull) atomicAdd(&s_hseg[full_class], nfull);
             if (rem) atomicAdd(&s_hseg[size_class(rem)], 1u);
@@ -127,7 +134,7 @@ __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
     atomicAdd(&s_nonempty, ne);
     __syncthreads();
     if (t == 0) {
-        a.wc->chunk_instances = dropped ? 0u : s_total;
+        a.wc->chunk_instances = dropped ? 0u : static_cast<unsigned int>(s_total >> 24);
         a.wc->chunk_dropped = s_dropped;
         if (!dropped) {
             a.header->max_tile_instances = max(a.header->max_tile_instances, s_max);
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
         a.wc->n_big = s_start[size_class(kSmallSortCap) - 1];    // tiles of the classes >= class(kSmallSortCap)
         a.wc->sort_cursor = 0;
         a.wc->n_blend = r1;
-        a.wc->n_empty = s_hist[0];
+        a.wc->n_empty = dropped ? unsigned(a.n) : static_cast<unsigned int>(s_total & 0xffffffull);
         a.wc->blend_cursor = 0;
         a.wc->empty_cursor = 0;
         a.plan->n_seg = r2;
@@ -153,9 +160,8 @@ __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
     uint2* work_seg = a.work_seg + s_segbase;
     for (int k = lo; k < hi; ++k) {
         const unsigned int c = dropped ? 0u : a.tile_cnt[k];
-        const unsigned int pos = atomicAdd(&s_start[size_class(c)], 1u);
-        if (c == 0) { a.work_empty[pos] = k; continue; }
-        a.work_blend[pos] = k;
+        if (c == 0) { a.work_empty[dropped ? unsigned(k) : empty_pos++] = k; continue; }
+        a.work_blend[atomicAdd(&s_start[size_class(c)], 1u)] = k;
         const unsigned int nfull = c / kSegment, rem = c - nfull * kSegment;
         if (nfull) {
             const unsigned int sp = atomicAdd(&s_sseg[full_class], nfull);
