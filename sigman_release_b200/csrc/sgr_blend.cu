@@ -24,6 +24,7 @@
 // Compiled with --fmad=false: the per-pixel expressions are the oracle's (oracle/sgr_oracle.cpp::blend_forward /
 // blend_backward) evaluated in the same order, which makes colour, depth, alpha and n_contrib bit-exact.
 #include <cstdio>
+#include <cstdlib>
 
 #include "sgr_common.cuh"
 
@@ -124,37 +125,42 @@ struct WarpSmem {
 // unused list entries point at the sentinel record.  Returns the four survivor counts.
 template <bool kReverse, int kBatch>
 __device__ __forceinline__ uint4 cull_batch(const float4* r0, unsigned int m, int blk, unsigned char (*list)[kBatch],
-                                            int lane) {
-    // lanes before (ascending) / after (descending) this one
-    const unsigned int lt = kReverse ? ~((2u << lane) - 1u) : (1u << lane) - 1u;
-    {                             // every list entry the compaction does not overwrite points at the sentinel record
-        unsigned int* lw = reinterpret_cast<unsigned int*>(&list[0][0]);
-        const unsigned int fill = kBatch * 0x01010101u;
-#pragma unroll
-        for (int w = 0; w < kBatch; w += 32) lw[w + lane] = fill;
-        __syncwarp();
-    }
+                                            int lane, unsigned int (&bits)[kBatch / 32]) {
+    // Straight-line code (the per-batch overhead is latency, not work): all mask words are loaded first, then all
+    // ballots, then the compaction stores.  bits[r] = this lane's 4-bit quarter mask of record 32 * r + lane.
+    constexpr int R = kBatch / 32;
+    const unsigned int lt = kReverse ? ~((2u << lane) - 1u) : (1u << lane) - 1u;   // lanes before / after this one
     const unsigned int* words = reinterpret_cast<const unsigned int*>(r0);
-    unsigned int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
 #pragma unroll
-    for (unsigned int round = 0; round < unsigned(kBatch) / 32; ++round) {
-        const unsigned int sub = kReverse ? unsigned(kBatch) - 32u * (round + 1u) : 32u * round;
-        if (sub >= m) { if (kReverse) continue; else break; }
-        const unsigned int e = sub + lane;
-        const unsigned int bits = (e < m) ? ((words[4 * e + 2] >> (4 * blk)) & 0xfu) : 0u;
-        if (__ballot_sync(kFull, bits != 0u) == 0u) continue;     // no record of the round touches this block
-        const unsigned int m0 = __ballot_sync(kFull, bits & 1u);
-        const unsigned int m1 = __ballot_sync(kFull, bits & 2u);
-        const unsigned int m2 = __ballot_sync(kFull, bits & 4u);
-        const unsigned int m3 = __ballot_sync(kFull, bits & 8u);
-        if (bits & 1u) list[0][n0 + __popc(m0 & lt)] = static_cast<unsigned char>(e);
-        if (bits & 2u) list[1][n1 + __popc(m1 & lt)] = static_cast<unsigned char>(e);
-        if (bits & 4u) list[2][n2 + __popc(m2 & lt)] = static_cast<unsigned char>(e);
-        if (bits & 8u) list[3][n3 + __popc(m3 & lt)] = static_cast<unsigned char>(e);
-        n0 += __popc(m0); n1 += __popc(m1); n2 += __popc(m2); n3 += __popc(m3);
+    for (int r = 0; r < R; ++r) {
+        const unsigned int e = 32u * r + lane;
+        bits[r] = (e < m) ? ((words[4 * e + 2] >> (4 * blk)) & 0xfu) : 0u;
+    }
+    {                             // every list entry the compaction does not overwrite points at the sentinel record
+        constexpr unsigned int fill = kBatch * 0x01010101u;
+        uint4* lw = reinterpret_cast<uint4*>(&list[0][0]);
+        if (lane < kBatch / 4) lw[lane] = make_uint4(fill, fill, fill, fill);
+    }
+    unsigned int mq[4][R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mq[q][r] = __ballot_sync(kFull, bits[r] & (1u << q));
+    }
+    __syncwarp();                 // the sentinel fill is ordered before the compaction stores
+    unsigned int n[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const int r = kReverse ? R - 1 - k : k;                 // descending lists walk the rounds from the back
+        const unsigned int e = 32u * r + lane;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (bits[r] & (1u << q)) list[q][n[q] + __popc(mq[q][r] & lt)] = static_cast<unsigned char>(e);
+            n[q] += __popc(mq[q][r]);
+        }
     }
     __syncwarp();
-    return make_uint4(n0, n1, n2, n3);
+    return make_uint4(n[0], n[1], n[2], n[3]);
 }
 
 // Per-warp TMA ring: `issued` / `consumed` count batches over the whole kernel (stage = k % stages,
@@ -180,6 +186,16 @@ __device__ __forceinline__ unsigned int pop_item(unsigned int* cursor, unsigned 
     w = __shfl_sync(kFull, w, 0);
     return w < n_items ? w : 0xffffffffu;
 }
+
+#ifdef SGR_PHASE_TIMING
+// Experiment build only: cycles spent per phase by lane 0 of (a) all items, (b) block 7 of the first (longest) tile.
+__device__ unsigned long long g_phase[16];
+#define PHASE_T0() const long long pt0__ = clock64()
+#define PHASE_ADD(k) do { const long long d__ = clock64() - pt0__; ph[k] += d__; } while (0)
+#else
+#define PHASE_T0()
+#define PHASE_ADD(k)
+#endif
 
 // ------------------------------------------------------------------------------------------------ forward
 struct FwdArgs {
@@ -300,6 +316,10 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
         unsigned int last = 0;
         bool done = !inside;
         unsigned int b_issued = 0;
+#ifdef SGR_PHASE_TIMING
+        long long ph[5] = {0, 0, 0, 0, 0};
+        unsigned long long ntrips = 0;
+#endif
         while (b_issued < nb && b_issued < unsigned(kFwdStages - 1)) {
             ring_issue(sm, issued, g0 + b_issued * kFwdBatch, g1 + b_issued * kFwdBatch, g2 + b_issued * kFwdBatch,
                        min(unsigned(kFwdBatch), n - b_issued * kFwdBatch), lane);
@@ -312,14 +332,16 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
                 ++issued; ++b_issued;
             }
             const int s = consumed % kFwdStages;
-            mbar_wait(&sm.full[s], (consumed / kFwdStages) & 1);
+            { PHASE_T0(); mbar_wait(&sm.full[s], (consumed / kFwdStages) & 1); PHASE_ADD(0); }
             ++consumed;
             const unsigned int m = min(unsigned(kFwdBatch), n - b * kFwdBatch);
             const unsigned int cbase = b * kFwdBatch;
             const float4* r0 = sm.r0[s];
             const float4* r1 = sm.r1[s];
             const float4* r2 = sm.r2[s];
-            const uint4 cnt = cull_batch<false, kFwdBatch>(r0, m, blk, sm.list, lane);
+            uint4 cnt;
+            unsigned int qbits[kFwdBatch / 32];
+            { PHASE_T0(); cnt = cull_batch<false, kFwdBatch>(r0, m, blk, sm.list, lane, qbits); PHASE_ADD(1); }
             // quarters whose 8 pixels are all finished need no further evaluation
             const unsigned int dmask = __ballot_sync(kFull, done);
             const unsigned int my_n = ((dmask & qmask) == qmask) ? 0u : (qsel == 0 ? cnt.x : qsel == 1 ? cnt.y : qsel == 2 ? cnt.z : cnt.w);
@@ -329,6 +351,10 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
             // recurrence.  List entries past a quarter's count point at the sentinel record (alpha = 0): no bounds
             // checks in the loop.  Quarters that are finished still walk (ok = false for all their lanes).
             unsigned int lastj = 0xffffffffu;
+#ifdef SGR_PHASE_TIMING
+            const long long pt_trips = clock64();
+            ntrips += total;
+#endif
             for (int t0 = 0; t0 < total; t0 += 4) {
                 const unsigned int packed = *reinterpret_cast<const unsigned int*>(mylist + t0);
                 float4 q0[4], q1[4], q2[4];
@@ -370,6 +396,10 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
             }
             if (lastj != 0xffffffffu) last = cbase + lastj + 1u;
             __syncwarp();
+#ifdef SGR_PHASE_TIMING
+            ph[2] += clock64() - pt_trips;
+            const long long pt_ref = clock64();
+#endif
             // Mask refinement for the backward pass: clear the (block, quarter) bits of the records that no pixel of
             // the quarter blended (alpha test, finished pixels) — the backward walk culls on the same word.
 #ifdef SGR_EXP_NO_BLOCK
@@ -377,20 +407,18 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
 #else
             if (refine && (cnt.x | cnt.y | cnt.z | cnt.w) != 0u) {
 #endif
-                const unsigned int* words = reinterpret_cast<const unsigned int*>(r0);
+                unsigned int hw[kFwdBatch / 32];
 #pragma unroll
-                for (unsigned int sub = 0; sub < unsigned(kFwdBatch); sub += 32) {
-                    const unsigned int e = sub + lane;
-                    if (e < m) {
-                        const unsigned int nib = (words[4 * e + 2] >> (4 * blk)) & 0xfu;
-                        const unsigned int h = sm.hit[e];
-                        const unsigned int exact = ((h & 0x01010101u) * 0x10204080u) >> 28;
-                        const unsigned int clear = nib & ~exact;
+                for (int rr = 0; rr < kFwdBatch / 32; ++rr) hw[rr] = sm.hit[32 * rr + lane];
+#pragma unroll
+                for (int rr = 0; rr < kFwdBatch / 32; ++rr) {
+                    const unsigned int e = 32u * rr + lane;
+                    const unsigned int exact = ((hw[rr] & 0x01010101u) * 0x10204080u) >> 28;
+                    const unsigned int clear = qbits[rr] & ~exact;          // qbits = 0 beyond the batch
 #ifndef SGR_EXP_NO_ATOMIC
-                        if (clear) atomicAnd(a.rec0_words + 4 * (off + cbase + e) + 2, ~(clear << (4 * blk)));
+                    if (clear) atomicAnd(a.rec0_words + 4 * (off + cbase + e) + 2, ~(clear << (4 * blk)));
 #endif
-                        sm.hit[e] = 0u;
-                    }
+                    if (hw[rr]) sm.hit[e] = 0u;
                 }
                 __syncwarp();
             }
@@ -400,8 +428,24 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
                 a.ck0[ci] = make_float4(T, C0, C1, C2);
                 a.ck1[ci] = D;
             }
+#ifdef SGR_PHASE_TIMING
+            ph[3] += clock64() - pt_ref;
+#endif
             if (__all_sync(kFull, done)) break;
         }
+#ifdef SGR_PHASE_TIMING
+        if (lane == 0) {
+            const long long tot = clock64() - (long long)0;
+            (void)tot;
+            for (int k = 0; k < 4; ++k) atomicAdd(&g_phase[k], (unsigned long long)ph[k]);
+            atomicAdd(&g_phase[4], ntrips);
+            atomicAdd(&g_phase[5], (unsigned long long)nb);
+            if (item / kBlocksPerTile == 0 && blk == 7) {
+                for (int k = 0; k < 4; ++k) g_phase[8 + k] = (unsigned long long)ph[k];
+                g_phase[12] = ntrips; g_phase[13] = nb; g_phase[14] = n;
+            }
+        }
+#endif
         if (n > unsigned(kSegment)) {                 // final state, read by the backward's non-final segments
             const size_t ci = ((off / (kSegment / 2) + (n + kSegment - 1) / kSegment - 1) * kBlocksPerTile + blk) * 32 + lane;
             a.ck0[ci] = make_float4(T, C0, C1, C2);
@@ -607,7 +651,8 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
             const float4* r0 = sm.r0[s];
             const float4* r1 = sm.r1[s];
             const float4* r2 = sm.r2[s];
-            const uint4 cnt = cull_batch<true, kBwdBatch>(r0, m, blk, sm.list, lane);
+            unsigned int qbits[kBwdBatch / 32];
+            const uint4 cnt = cull_batch<true, kBwdBatch>(r0, m, blk, sm.list, lane, qbits);
             const int total = int(max(max(cnt.x, cnt.y), max(cnt.z, cnt.w)));
             // trip t of the batch handles the quarter's survivor number (my_n - 1 - t): back to front
             const float nTb = -T_final * bg_dot;
@@ -804,7 +849,10 @@ cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out
         if (e != cudaSuccess) return e;
     }
     const long long items = (long long)c.num_renders * c.g.num_tiles * kBlocksPerTile;
-    const int grid = int(min((long long)num_sms() * per_sm, (items + kWarpsPerCta - 1) / kWarpsPerCta));
+    static int ctas_override = -1;               // experiment hook: SGR_FWD_CTAS_PER_SM
+    if (ctas_override < 0) { const char* v = getenv("SGR_FWD_CTAS_PER_SM"); ctas_override = v ? atoi(v) : 0; }
+    const int use_per_sm = ctas_override > 0 ? min(ctas_override, per_sm) : per_sm;
+    const int grid = int(min((long long)num_sms() * use_per_sm, (items + kWarpsPerCta - 1) / kWarpsPerCta));
     blend_forward_kernel<<<grid, kBlendThreads, smem, c.stream>>>(a);
     return cudaGetLastError();
 }
@@ -845,3 +893,12 @@ cudaError_t launch_blend_backward(const ChunkCtx& c, const float* out_alpha, con
 }
 
 }  // namespace sgr
+
+#ifdef SGR_PHASE_TIMING
+extern "C" int sgr_debug_phase_counters(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, sgr::g_phase, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(sgr::g_phase, z, sizeof(z)); }
+    return 0;
+}
+#endif

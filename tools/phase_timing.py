@@ -1,0 +1,24 @@
+"""Experiment: per-phase cycle counters of the forward blend (needs a library built with -DSGR_PHASE_TIMING)."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import torch
+from sigman_release_b200 import _native, scenes
+from gpu_utils import gpu_forward
+VIEWS = [30, 37, 45, 53, 65, 85, 0, 8]
+sc = scenes.body_gaussians(100_000, seed=0)
+L = _native.lib()
+out = (ctypes.c_ulonglong * 16)()
+for it in range(3):
+    gpu_forward(sc, VIEWS, 512, 512, requires_grad=True)
+L.sgr_debug_phase_counters(out, 1)
+gpu_forward(sc, VIEWS, 512, 512, requires_grad=True)
+L.sgr_debug_phase_counters(out, 1)
+v = list(out)
+names = ["tma wait", "cull", "trips", "refine+ckpt"]
+tot = sum(v[:4])
+print("all items: cycles", {n: f"{x/1e6:.1f}M ({100*x/tot:.0f}%)" for n, x in zip(names, v[:4])}, "trips", v[4], "batches", v[5],
+      f"cycles/trip {v[2]/max(v[4],1):.0f} cull cycles/batch {v[1]/max(v[5],1):.0f} refine/batch {v[3]/max(v[5],1):.0f} wait/batch {v[0]/max(v[5],1):.0f}")
+tot = sum(v[8:12])
+print("longest tile blk 7: n", v[14], "batches", v[13], "trips", v[12], {n: f"{x/1e3:.0f}K ({100*x/max(tot,1):.0f}%)" for n, x in zip(names, v[8:12])},
+      f"cycles/trip {v[10]/max(v[12],1):.0f} cull/batch {v[9]/max(v[13],1):.0f} refine/batch {v[11]/max(v[13],1):.0f} wait/batch {v[8]/max(v[13],1):.0f}")
