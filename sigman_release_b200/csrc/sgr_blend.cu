@@ -485,9 +485,16 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
     // ---------------- blocks of tiles without instances: background only
     float e0 = bg0, e1 = bg1, e2 = bg2;
     if (a.clamp_color) { e0 = fminf(fmaxf(e0, 0.0f), 1.0f); e1 = fminf(fmaxf(e1, 0.0f), 1.0f); e2 = fminf(fmaxf(e2, 0.0f), 1.0f); }
-    for (;;) {
-        const unsigned int item = pop_item(&a.wc->empty_cursor, n_empty_items, lane);
-        if (item == 0xffffffffu) break;
+    // whole tiles are popped (8 uniform items per global atomic round trip)
+    for (unsigned int item = 0xffffffffu;;) {
+        if (item == 0xffffffffu || (item % kBlocksPerTile) == kBlocksPerTile - 1) {
+            unsigned int w = 0;
+            if (lane == 0) w = atomicAdd(&a.wc->empty_cursor, unsigned(kBlocksPerTile));
+            item = __shfl_sync(kFull, w, 0);
+        } else {
+            ++item;
+        }
+        if (item >= n_empty_items) break;
         const unsigned int tile_local = a.work_empty[item / kBlocksPerTile];
         const int blk = item % kBlocksPerTile;
         const int rl = tile_local / a.g.num_tiles;
