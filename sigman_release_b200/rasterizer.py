@@ -79,8 +79,9 @@ def _drain_pending(block: bool) -> None:
     todo = list(_pending)
     for idx, (ev, pinned, key, R) in enumerate(todo):
         if not block and not ev.query():
-            keep.append((ev, pinned, key, R))
-            continue
+            # status copies complete in launch order: everything behind the first unfinished one is left unpolled
+            keep.extend(todo[idx:])
+            break
         ev.synchronize()
         st = _status_from_bytes(pinned)
         _status_pool.append((pinned, ev))
