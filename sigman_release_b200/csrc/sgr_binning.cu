@@ -362,7 +362,10 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
     }
 }
 
-__global__ void __launch_bounds__(kSmallSortThreads) sort_small_kernel(SortArgs a) {
+#ifndef SGR_SORT_SMALL_MIN_CTAS
+#define SGR_SORT_SMALL_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(kSmallSortThreads, SGR_SORT_SMALL_MIN_CTAS) sort_small_kernel(SortArgs a) {
     __shared__ unsigned long long kb[kSmallSortCap];
     __shared__ unsigned int hist[kSmallSortBuckets];
     __shared__ unsigned int s_warp[32];

@@ -25,6 +25,7 @@
 // blend_backward) evaluated in the same order, which makes colour, depth, alpha and n_contrib bit-exact.
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "sgr_common.cuh"
 
@@ -253,6 +254,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 using FwdSmem = WarpSmem<1, 1, kFwdStages, kFwdBatch>;      // the forward needs no stash
 using BwdSmem = WarpSmem<3, kBwdSlots, kBwdStages, kBwdBatch>;
 
+#ifndef SGR_FWD_GROUP8
+#define SGR_FWD_GROUP8 1
+#endif
 #ifndef SGR_FWD_MIN_CTAS
 #define SGR_FWD_MIN_CTAS 2
 #endif
@@ -355,20 +359,27 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
             const long long pt_trips = clock64();
             ntrips += total;
 #endif
-            for (int t0 = 0; t0 < total; t0 += 4) {
-                const unsigned int packed = *reinterpret_cast<const unsigned int*>(mylist + t0);
-                float4 q0[4], q1[4], q2[4];
-                unsigned int jj[4];
+            // A group of G trips: G independent alpha chains (loads first), then the compositing recurrence with the
+            // colour records fetched as they are needed.  Groups of 8 while at least 5 trips remain (a single warp's
+            // issue rate is bounded by the dependent-issue latency, so the long lists that run alone at the end of the
+            // launch need the extra instruction-level parallelism), a group of 4 for the rest.
+            auto trip_group = [&](int t0, auto G_tag) {
+                constexpr int G = decltype(G_tag)::value;
+                float4 q0[G], q1[G];
+                unsigned int jj[G];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    jj[u] = (packed >> (8 * u)) & 0xffu;
-                    q0[u] = r0[jj[u]];
-                    q1[u] = r1[jj[u]];
-                    q2[u] = r2[jj[u]];
+                for (int w4 = 0; w4 < G / 4; ++w4) {
+                    const unsigned int packed = *reinterpret_cast<const unsigned int*>(mylist + t0 + 4 * w4);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        jj[4 * w4 + u] = (packed >> (8 * u)) & 0xffu;
+                        q0[4 * w4 + u] = r0[jj[4 * w4 + u]];
+                        q1[4 * w4 + u] = r1[jj[4 * w4 + u]];
+                    }
                 }
-                float al[4];
+                float al[G];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < G; ++u) {
                     const float dx = q0[u].x - pxf, dy = q0[u].y - pyf;
                     const float power = gauss_power(q1[u].x, q1[u].y, q1[u].z, dx, dy);
                     const bool valid = !(power > 0.0f) && !(power < q0[u].w);
@@ -376,23 +387,31 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
                     al[u] = valid ? alpha : 0.0f;
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < G; ++u) {
+                    const float4 q2 = r2[jj[u]];
                     const bool ok = !done && !(al[u] < kAlphaMin);
                     const float test_T = __fmaf_rn(-al[u], T, T);
                     const bool stop = ok && (test_T < kTMin);
                     const bool blend = ok && !stop;
                     const float w = blend ? al[u] * T : 0.0f;      // adding c * 0 leaves the sums bit-unchanged
-                    C0 = __fmaf_rn(q2[u].x, w, C0);
-                    C1 = __fmaf_rn(q2[u].y, w, C1);
-                    C2 = __fmaf_rn(q2[u].z, w, C2);
+                    C0 = __fmaf_rn(q2.x, w, C0);
+                    C1 = __fmaf_rn(q2.y, w, C1);
+                    C2 = __fmaf_rn(q2.z, w, C2);
                     Wt += w;
-                    D = __fmaf_rn(q2[u].w, w, D);
+                    D = __fmaf_rn(q2.w, w, D);
                     T = blend ? test_T : T;
                     lastj = blend ? jj[u] : lastj;
                     done = done || stop;
                     // same-value stores of the quarter's lanes to one byte: benign
                     if (refine && blend) hit_bytes[4u * jj[u]] = 1;
                 }
+            };
+            {
+                int t0 = 0;
+#if SGR_FWD_GROUP8
+                for (; total - t0 > 4; t0 += 8) trip_group(t0, std::integral_constant<int, 8>{});
+#endif
+                for (; t0 < total; t0 += 4) trip_group(t0, std::integral_constant<int, 4>{});
             }
             if (lastj != 0xffffffffu) last = cbase + lastj + 1u;
             __syncwarp();

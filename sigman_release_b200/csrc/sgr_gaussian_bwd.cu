@@ -27,7 +27,10 @@ struct PreBwdArgs {
 constexpr int kPreBwdSlots = 8;
 constexpr int kPreBwdVals = 13;              // means3D 3, cov3D 6, colors 3, opacity 1
 
-__global__ void __launch_bounds__(32 * kPreBwdSlots) preprocess_backward_kernel(PreBwdArgs a) {
+#ifndef SGR_PREBWD_MIN_CTAS
+#define SGR_PREBWD_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(32 * kPreBwdSlots, SGR_PREBWD_MIN_CTAS) preprocess_backward_kernel(PreBwdArgs a) {
     __shared__ float s_part[kPreBwdSlots][kPreBwdVals][32];
     const int N = a.g.N, V = a.g.V;
     const int lane = threadIdx.x, slot = threadIdx.y;

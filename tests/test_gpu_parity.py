@@ -352,3 +352,41 @@ def test_renderer_dropin_matches_reference_shaped_loop():
                              (out["alpha"][b, v].cpu().numpy(), ora.alpha)):
                 err = np.abs(got - ref)
                 assert (err > 1e-4).mean() < 2e-3 and err.max() < 2e-2, (float((err > 1e-4).mean()), float(err.max()))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_randomised_scenes_forward_and_backward(seed):
+    """Randomised sweep (scene density, anisotropy, opacity range, image size, chunking, fused loss): forward bit-exact,
+    index state bit-exact, gradients within tolerance — the guard for every kernel restructuring of the blend path."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(50, 4000))
+    H, W = int(rng.integers(17, 150)), int(rng.integers(17, 150))
+    sc = small_scene(n=n, seed=seed, spread=float(rng.uniform(0.1, 0.6)), smin=0.002,
+                     smax=float(rng.uniform(0.01, 0.15)), omax=float(rng.uniform(0.3, 1.0)))
+    if seed % 2:                                           # near-opaque layers: early termination + long dense lists
+        sc["opacities"] = np.clip(sc["opacities"] * 3, 0, 1)
+    views = [int(v) for v in rng.choice(90, size=int(rng.integers(1, 5)), replace=False)]
+    bg = tuple(float(x) for x in rng.uniform(0, 1, 3))
+    rpc = int(rng.integers(0, 3))
+    out, t, (vm, pm) = gpu_forward(sc, views, H, W, bg=bg, requires_grad=True, renders_per_chunk=rpc)
+    color, radii, depth, alpha = out
+    gc = rng.normal(size=(len(views), 3, H, W)).astype(np.float32)
+    gd = rng.normal(size=(len(views), 1, H, W)).astype(np.float32) * 0.1
+    ga = rng.normal(size=(len(views), 1, H, W)).astype(np.float32) * 0.1
+    state, dims = saved_state(color)                       # before backward() frees the saved tensors
+    ((color[0] * to_dev(gc)).sum() + (depth[0] * to_dev(gd)).sum() + (alpha[0] * to_dev(ga)).sum()).backward()
+    ref = None
+    for v in range(len(views)):
+        r, ora = oracle_forward(sc, vm[v], pm[v], H, W, bg=bg)
+        _assert_forward_equal(out, ora, render=v)
+        ranges, ncon, pl = debug_state(state, 1, len(views), n, H, W, dims[7], v)
+        b = r.binning()
+        np.testing.assert_array_equal(ranges, b["ranges"])
+        np.testing.assert_array_equal(pl, b["point_list"])
+        np.testing.assert_array_equal(ncon, b["n_contrib"])
+        g = r.backward(gc[v], gd[v], ga[v])
+        ref = g if ref is None else {k: ref[k] + g[k] for k in g}
+    for k in ("means3D", "cov3D", "colors", "opacities"):
+        got = t[k].grad[0].cpu().numpy().astype(np.float64)
+        want = ref[k].astype(np.float64)
+        assert np.abs(got - want).max() <= 3e-4 * np.abs(want).max() + 1e-7, k
