@@ -392,6 +392,9 @@ __global__ void __launch_bounds__(kBigSortThreads) sort_big_kernel(SortArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* kb_s = reinterpret_cast<unsigned long long*>(smem_raw);                 // kBigSortSmemCap
     unsigned int* hist = reinterpret_cast<unsigned int*>(kb_s + a.big_smem_keys);               // kBigSortBuckets
+    // Programmatic dependent launch: the short-list kernel behind this one in the stream may start as soon as every
+    // CTA of this grid is resident (it does not consume this kernel's output) — see launch_sort_tiles.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __shared__ unsigned int s_warp[32];
     __shared__ unsigned long long s_red[2 * (kBigSortThreads / 32) + 2];
     const unsigned int nw = a.wc->n_big;
@@ -477,15 +480,33 @@ cudaError_t launch_sort_tiles(const ChunkCtx& c) {
         if ((e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
         if ((e = cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming)) != cudaSuccess) return e;
     }
-    static int mode = -1;      // experiment switch: 0 concurrent (default), 1 serial, 2 small only, 3 big only
+    static int mode = -1;      // experiment switch: 0 PDL overlap (default), 1 serial, 2 small only, 3 big only, 4 two streams
     if (mode < 0) { const char* m = getenv("SGR_SORT_MODE"); mode = m ? atoi(m) : 0; }
-    if (mode != 0) {
+    if (mode >= 1 && mode <= 3) {
         if (mode != 2) sort_big_kernel<<<min(num_sms, total_tiles), kBigSortThreads, big_smem, c.stream>>>(a);
         if (mode != 3) sort_small_kernel<<<min(num_sms * small_per_sm, total_tiles), kSmallSortThreads, 0, c.stream>>>(a);
         return cudaGetLastError();
     }
-    // The long-list kernel goes first on the caller's stream (it is the longer pole and must not queue behind the
-    // short-list CTAs for SM resources); the short-list kernel follows on the side stream and fills the rest.
+    // The long-list kernel goes first (it is the longer pole and a 1024-thread CTA cannot share an SM with the
+    // short-list CTAs, so it must not queue behind them); the short-list kernel follows in the SAME stream as a
+    // programmatic dependent launch: it starts once all long-list CTAs are resident and fills the remaining SMs.  The
+    // next normal launch in the stream (the blend) waits for both.
+    if (mode == 0) {
+        sort_big_kernel<<<min(num_sms, total_tiles), kBigSortThreads, big_smem, c.stream>>>(a);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(min(num_sms * small_per_sm, total_tiles));
+        cfg.blockDim = dim3(kSmallSortThreads);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = c.stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, sort_small_kernel, a);
+    }
+    // mode 4: the same overlap with a side stream and events
     if ((e = cudaEventRecord(ev_fork, c.stream)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(side, ev_fork, 0)) != cudaSuccess) return e;
     sort_big_kernel<<<min(num_sms, total_tiles), kBigSortThreads, big_smem, c.stream>>>(a);
