@@ -15,6 +15,22 @@ def step():
     rasterizer.render_l1_loss(t["means3D"], t["cov3D"], t["colors"], t["opacities"], vmt, pmt, bg, H, W, tan, tan, target)[0].backward()
 for _ in range(20): step()
 torch.cuda.synchronize()
+ts = []
+for rep in range(10):                       # 20 steps from an empty queue: no launch-queue back-pressure
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(20): step()
+    ts.append((time.perf_counter() - t0) / 20); torch.cuda.synchronize()
+print(f"host enqueue without back-pressure: {1e3*min(ts):.3f} ms/step (min of 10 x 20 steps), median {1e3*sorted(ts)[5]:.3f}")
+import ctypes
+from sigman_release_b200 import _native
+L = _native.lib()
+t0 = time.perf_counter()
+for _ in range(2000): L.sgr_abi_version()
+print(f"ctypes call overhead {1e6*(time.perf_counter()-t0)/2000:.2f} us")
+t0 = time.perf_counter()
+for _ in range(2000): torch.empty((1000,), device="cuda")
+print(f"torch.empty {1e6*(time.perf_counter()-t0)/2000:.2f} us")
+torch.cuda.synchronize()
 t0 = time.perf_counter()
 for _ in range(300): step()
 t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
