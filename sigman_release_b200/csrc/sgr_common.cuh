@@ -171,21 +171,15 @@ __device__ __forceinline__ float2 unpack_extent(float packed) {
 // NaN coordinates give an empty mask (all comparisons false): such a record can never pass the alpha test.
 __device__ __forceinline__ unsigned int quarter_mask(float x, float y, float packed_ext, float X0, float Y0) {
     const float2 ext = unpack_extent(packed_ext);
-    // quarter columns c (4 pixels wide) with  x + ex >= X0 + 4c  and  x - ex <= X0 + 4c + 3, as an index interval;
-    // likewise quarter rows r (2 pixels high).  (Interval arithmetic instead of 12 pairs of comparisons: borderline
-    // ulp differences are covered by the slack built into the extents.)
-    const int c0 = max(0, __float2int_ru((x - ext.x - X0 - 3.0f) * 0.25f));
-    const int c1 = min(3, __float2int_rd((x + ext.x - X0) * 0.25f));
-    const int r0 = max(0, __float2int_ru((y - ext.y - Y0 - 1.0f) * 0.5f));
-    const int r1 = min(7, __float2int_rd((y + ext.y - Y0) * 0.5f));
-    if (!(x == x) || !(y == y) || c1 < c0 || r1 < r0) return 0u;
-    const unsigned int cols = (2u << c1) - (1u << c0);                      // bits c0..c1 of 4
-    const unsigned int row = (cols & 3u) | ((cols & 12u) << 2);             // -> bits (x half) + 4 * (x block)
-    unsigned int rows = (2u << r1) - (1u << r0);                            // bits r0..r1 of 8
-    rows = (rows | (rows << 12)) & 0x000f000fu;                             // spread: row r -> bit 8 * (r >> 1) + 2 * (r & 1)
-    rows = (rows | (rows << 6)) & 0x03030303u;
-    rows = (rows & 0x01010101u) | ((rows & 0x02020202u) << 1);
-    return row * rows;                                                      // disjoint partial products: no carries
+    const float xl = x - ext.x, xh = x + ext.x, yl = y - ext.y, yh = y + ext.y;
+    unsigned int row = 0, mask = 0;
+#pragma unroll
+    for (int qc = 0; qc < 4; ++qc)
+        if (xh >= X0 + float(4 * qc) && xl <= X0 + float(4 * qc + 3)) row |= 1u << ((qc & 1) | ((qc >> 1) << 2));
+#pragma unroll
+    for (int qr = 0; qr < 8; ++qr)
+        if (yh >= Y0 + float(2 * qr) && yl <= Y0 + float(2 * qr + 1)) mask |= row << ((qr >> 1) * 8 + (qr & 1) * 2);
+    return mask;
 }
 
 constexpr float kAlphaMin = 1.0f / 255.0f;

@@ -108,6 +108,21 @@ def check_status() -> Optional[dict]:
     return _last_status
 
 
+_bytes_cache: dict = {}
+
+
+def _buffer_bytes(L, B, V, N, H, W, cap, rpc):
+    """(state bytes, scratch bytes) of a problem shape (cached: the launch path is host-latency sensitive)."""
+    key = (B, V, N, H, W, cap, rpc)
+    got = _bytes_cache.get(key)
+    if got is None:
+        if len(_bytes_cache) > 256:
+            _bytes_cache.clear()
+        got = (int(L.sgr_state_bytes(B, V, N, H, W, cap)), int(L.sgr_scratch_bytes(B, V, N, H, W, cap, rpc)))
+        _bytes_cache[key] = got
+    return got
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -165,8 +180,7 @@ class _RasterizeBatch(torch.autograd.Function):
             sync_check = first or _OVERFLOW_MODE == "sync"
             while True:
                 cap = min(int(per) * R, (1 << 32) - 2)
-                state_bytes = int(L.sgr_state_bytes(B, V, N, H, W, cap))
-                scratch_bytes = int(L.sgr_scratch_bytes(B, V, N, H, W, cap, renders_per_chunk))
+                state_bytes, scratch_bytes = _buffer_bytes(L, B, V, N, H, W, cap, renders_per_chunk)
                 state = torch.empty((state_bytes,), dtype=torch.uint8, device=dev)
                 scratch = torch.empty((scratch_bytes,), dtype=torch.uint8, device=dev)
                 a = _native.SgrForwardArgs()
@@ -245,7 +259,7 @@ class _RasterizeBatch(torch.autograd.Function):
             d_colors = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
             d_opac = torch.empty((B, N), dtype=torch.float32, device=dev)
             d_means2D = torch.empty((B, V, N, 3), dtype=torch.float32, device=dev) if ctx.want_means2D else None
-            scratch_bytes = int(L.sgr_scratch_bytes(B, V, N, H, W, cap, rpc))
+            scratch_bytes = _buffer_bytes(L, B, V, N, H, W, cap, rpc)[1]
             scratch = torch.empty((scratch_bytes,), dtype=torch.uint8, device=dev)
             a = _native.SgrBackwardArgs()
             _fill_problem(a.p, B, V, N, H, W, tanfovx, tanfovy, means3D, cov3D, colors, opacities, viewmatrix,
