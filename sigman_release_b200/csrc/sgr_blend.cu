@@ -106,6 +106,8 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
+constexpr int kListPad = 16;                   // keeps the rows 16-byte aligned
+
 template <int kStashes, int kDepth, int kNumStages, int kBatch>
 struct WarpSmem {
     static constexpr int stages = kNumStages;
@@ -114,7 +116,9 @@ struct WarpSmem {
     float4 r2[kNumStages][kBatch + 1];
     float stash[kStashes][kDepth][32];
     float dpix[4][32];                          // backward: dL/dcolor (3) and dL/ddepth of the block's pixels
-    unsigned char list[4][kBatch];              // per quarter: batch-local indices of the survivors (ascending)
+    // per quarter: batch-local indices of the survivors, sentinel-filled; the trip loops read whole groups of 4 / 8
+    // entries starting at multiples of their size, which stays inside kBatch — the pad is a safety margin
+    unsigned char list[4][kBatch + kListPad];
     unsigned int hit[kBatch + 1];               // forward: byte q of word j != 0 <=> quarter q blended record j
     uint64_t full[kNumStages];
 };
@@ -125,7 +129,8 @@ struct WarpSmem {
 // batch-local indices into list[quarter][...] (ascending; descending with kReverse — the backward walks back to front);
 // unused list entries point at the sentinel record.  Returns the four survivor counts.
 template <bool kReverse, int kBatch>
-__device__ __forceinline__ uint4 cull_batch(const float4* r0, unsigned int m, int blk, unsigned char (*list)[kBatch],
+__device__ __forceinline__ uint4 cull_batch(const float4* r0, unsigned int m, int blk,
+                                            unsigned char (*list)[kBatch + kListPad],
                                             int lane, unsigned int (&bits)[kBatch / 32]) {
     // Straight-line code (the per-batch overhead is latency, not work): all mask words are loaded first, then all
     // ballots, then the compaction stores.  bits[r] = this lane's 4-bit quarter mask of record 32 * r + lane.
@@ -140,7 +145,10 @@ __device__ __forceinline__ uint4 cull_batch(const float4* r0, unsigned int m, in
     {                             // every list entry the compaction does not overwrite points at the sentinel record
         constexpr unsigned int fill = kBatch * 0x01010101u;
         uint4* lw = reinterpret_cast<uint4*>(&list[0][0]);
-        if (lane < kBatch / 4) lw[lane] = make_uint4(fill, fill, fill, fill);
+        constexpr int kVecs = 4 * (kBatch + kListPad) / 16;       // the four rows including their pads
+#pragma unroll
+        for (int v = 0; v < kVecs; v += 32)
+            if (v + lane < kVecs) lw[v + lane] = make_uint4(fill, fill, fill, fill);
     }
     unsigned int mq[4][R];
 #pragma unroll

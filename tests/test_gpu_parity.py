@@ -390,3 +390,26 @@ def test_randomised_scenes_forward_and_backward(seed):
         got = t[k].grad[0].cpu().numpy().astype(np.float64)
         want = ref[k].astype(np.float64)
         assert np.abs(got - want).max() <= 3e-4 * np.abs(want).max() + 1e-7, k
+
+
+def test_dense_quarter_lists_fill_whole_batches():
+    """Large, nearly transparent Gaussians stacked on one spot: every record of a 128-record batch survives the cull in
+    every quarter of the central tiles, so the trip loops run through completely full survivor lists."""
+    n = 700
+    rng = np.random.default_rng(5)
+    xyz = rng.normal(scale=0.01, size=(n, 3))
+    scale = np.full((n, 3), 0.3)
+    rot = scenes.quat_to_rotmat(rng.normal(size=(n, 4)))
+    sc = dict(means3D=xyz, cov3D=scenes.covariance6(scale, rot), colors=rng.uniform(0, 1, (n, 3)),
+              opacities=np.full((n,), 0.02))
+    out, t, (vm, pm) = gpu_forward(sc, [30], 64, 64, requires_grad=True)
+    r, ora = oracle_forward(sc, vm[0], pm[0], 64, 64)
+    _assert_forward_equal(out, ora)
+    assert int(ora.radii.min()) >= 16                        # every Gaussian covers the whole tile neighbourhood
+    g = rng.normal(size=(3, 64, 64)).astype(np.float32)
+    (out[0][0, 0] * to_dev(g)).sum().backward()
+    ref = r.backward(g)
+    for k in ("means3D", "cov3D", "colors", "opacities"):
+        got = t[k].grad[0].cpu().numpy().astype(np.float64)
+        want = ref[k].astype(np.float64)
+        assert np.abs(got - want).max() <= 3e-4 * np.abs(want).max() + 1e-7, k
