@@ -413,3 +413,30 @@ def test_dense_quarter_lists_fill_whole_batches():
         got = t[k].grad[0].cpu().numpy().astype(np.float64)
         want = ref[k].astype(np.float64)
         assert np.abs(got - want).max() <= 3e-4 * np.abs(want).max() + 1e-7, k
+
+
+def test_full_hd_image_uses_the_global_histogram_path():
+    """1080 x 1920: 8160 tiles per render (> the 4096 tiles whose counters fit the per-CTA shared-memory histogram of
+    the preprocess / scatter kernels), two views, chunked one render at a time."""
+    H, W = 1080, 1920
+    sc = small_scene(n=2500, seed=9, spread=0.9, smin=0.004, smax=0.05)
+    out, t, (vm, pm) = gpu_forward(sc, [30, 8], H, W, requires_grad=True, renders_per_chunk=1)
+    state, dims = saved_state(out[0])
+    for v in range(2):
+        r, ora = oracle_forward(sc, vm[v], pm[v], H, W)
+        _assert_forward_equal(out, ora, render=v)
+        ranges, ncon, pl = debug_state(state, 1, 2, 2500, H, W, dims[7], v)
+        b = r.binning()
+        np.testing.assert_array_equal(ranges, b["ranges"])
+        np.testing.assert_array_equal(pl, b["point_list"])
+    g = np.random.default_rng(1).normal(size=(2, 3, H, W)).astype(np.float32)
+    (out[0][0] * to_dev(g)).sum().backward()
+    ref = None
+    for v in range(2):
+        r, ora = oracle_forward(sc, vm[v], pm[v], H, W)
+        gr = r.backward(g[v])
+        ref = gr if ref is None else {k: ref[k] + gr[k] for k in gr}
+    for k in ("means3D", "cov3D", "colors", "opacities"):
+        got = t[k].grad[0].cpu().numpy().astype(np.float64)
+        want = ref[k].astype(np.float64)
+        assert np.abs(got - want).max() <= 3e-4 * np.abs(want).max() + 1e-7, k

@@ -16,12 +16,13 @@ def _fake_render(views):
     return torch.stack([torch.full((5, 4, 6), float(v)) + torch.arange(5.0).view(5, 1, 1) * 0.01 for v in views])
 
 
-def _worker(rank, world, port, num_views, ret):
+def _worker(rank, world, port, num_views, ret, wire=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        out = render_orbit_sharded(_fake_render, num_views)
+        fn = _fake_render if wire is None else (lambda v: _fake_render(v) / 100.0)
+        out = render_orbit_sharded(fn, num_views, wire_dtype=wire)
         ret[rank] = out
     finally:
         dist.destroy_process_group()
@@ -55,3 +56,13 @@ def test_two_rank_gather_equals_single_process(num_views):
 
 def test_single_process_passthrough():
     assert torch.equal(render_orbit_sharded(_fake_render, 5), _fake_render(range(5)))
+
+
+@pytest.mark.parametrize("wire,tol", [(torch.float16, 1e-3), (torch.uint8, 0.5 / 255 + 1e-6)])
+def test_two_rank_gather_with_compact_wire_format(wire, tol):
+    world, num_views = 2, 7
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), num_views, ret, wire), nprocs=world, join=True)
+    want = _fake_render(list(range(num_views))) / 100.0
+    for r in range(world):
+        assert ret[r].dtype == torch.float32 and float((ret[r] - want).abs().max()) <= tol
