@@ -3,23 +3,27 @@
 // Replaces upstream renderCUDA forward/backward (third-party diff_gaussian_rasterization; call site
 // /root/reference/core/gaussians/gs.py:99-106).  Design (DESIGN.md "blend"):
 //   * the unit of work is one 8x4 pixel block of one tile of one render.  Every WARP is autonomous: it pops work items
-//     from a device-side queue ordered longest-list-first (sgr_binning.cu::worklist_kernel), streams the tile's
+//     from a device-side queue ordered longest-list-first (sgr_binning.cu::plan_kernel), streams the tile's
 //     depth-ordered 48-byte records (three float4 streams, contiguous per tile because the per-tile sort gathers them)
 //     through its own shared-memory ring with 1-D TMA bulk copies (cp.async.bulk) completing on its own mbarriers, and
 //     never waits for another warp — no block-wide barrier, no producer/consumer hand-off, early exit as soon as its
 //     32 pixels are finished;
-//   * a block is four 4x2 quarters.  The warp tests 32 records at a time (lane = record) against each quarter with the
-//     conservative alpha >= 1/255 extent computed in the preprocess kernel (four ballots), compacts the survivors'
-//     indices per quarter, and then every quarter walks only its own survivors (lane = pixel), so up to four different
-//     Gaussians are evaluated per trip.  Culled records would have been skipped by the alpha test, so the per-pixel
-//     arithmetic, the contributor index and every output bit equal the straightforward kernel's;
-//   * the walk is split into phases through a per-warp shared-memory stash so that only the inherently sequential
-//     part sits on the dependent chain: phase A evaluates alpha for up to 16 trips (independent, written load-first in
-//     blocks of four so the chains interleave), phase B composites front to back reading the stashed alphas;
-//   * backward: the same walk in reverse with three phases — A: alpha, B: the per-pixel transmittance / colour
-//     recurrences producing dL/dalpha and the blend weight, C: the roles flip to lane = (Gaussian, quarter) pair, each
-//     lane summing the gradient terms of its quarter's 8 pixels in registers (XOR-swizzled stash, no shuffles) before
-//     one atomic per component.  Gradient arithmetic is free to use FMA (compared with a tolerance, not bit-exact).
+//   * a block is four 4x2 quarters.  A batch of 128 records is culled in straight-line code (lane = record): the
+//     per-instance quarter masks built by the tile sort are loaded, one ballot per (round, quarter), and the
+//     survivors' batch-local indices are compacted into one sentinel-padded list per quarter; every quarter then
+//     walks only its own survivors (lane = pixel), so up to four different Gaussians are evaluated per trip.  Culled
+//     records would have been skipped by the alpha test, so the per-pixel arithmetic, the contributor index and every
+//     output bit equal the straightforward kernel's;
+//   * forward trips run in groups of eight (four at the end of a list): eight independent alpha chains written
+//     load-first, then the sequential compositing recurrence; per batch the forward clears the mask bits of the
+//     (quarter, record) pairs that did not blend (one RED.AND per changed record) so that the backward culls on the
+//     exact set, and checkpoints the running state every 1024 records;
+//   * backward: work items are (tile, 1024-record segment, block), resumed from the forward's checkpoints; the same
+//     walk in reverse over descending lists with phases A+B (alpha, G, then the per-pixel transmittance / colour
+//     recurrences producing dL/dalpha and the blend weight, stashed) and C: the roles flip to lane = (Gaussian,
+//     quarter) pair, each lane summing the gradient terms of its quarter's 8 pixels in registers (XOR-swizzled stash,
+//     no shuffles) before one atomic per component.  Gradient arithmetic is free to use FMA (tolerance, not bit-exact);
+//   * optional epilogue: clamp + masked L1 loss + dL/dcolour (SgrForwardArgs::loss_*).
 //
 // Compiled with --fmad=false: the per-pixel expressions are the oracle's (oracle/sgr_oracle.cpp::blend_forward /
 // blend_backward) evaluated in the same order, which makes colour, depth, alpha and n_contrib bit-exact.
@@ -429,11 +433,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
 #endif
             // Mask refinement for the backward pass: clear the (block, quarter) bits of the records that no pixel of
             // the quarter blended (alpha test, finished pixels) — the backward walk culls on the same word.
-#ifdef SGR_EXP_NO_BLOCK
-            if (false) {
-#else
             if (refine && (cnt.x | cnt.y | cnt.z | cnt.w) != 0u) {
-#endif
                 unsigned int hw[kFwdBatch / 32];
 #pragma unroll
                 for (int rr = 0; rr < kFwdBatch / 32; ++rr) hw[rr] = sm.hit[32 * rr + lane];
@@ -442,9 +442,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
                     const unsigned int e = 32u * rr + lane;
                     const unsigned int exact = ((hw[rr] & 0x01010101u) * 0x10204080u) >> 28;
                     const unsigned int clear = qbits[rr] & ~exact;          // qbits = 0 beyond the batch
-#ifndef SGR_EXP_NO_ATOMIC
                     if (clear) atomicAnd(a.rec0_words + 4 * (off + cbase + e) + 2, ~(clear << (4 * blk)));
-#endif
                     if (hw[rr]) sm.hit[e] = 0u;
                 }
                 __syncwarp();
