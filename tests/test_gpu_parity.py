@@ -440,3 +440,38 @@ def test_full_hd_image_uses_the_global_histogram_path():
         got = t[k].grad[0].cpu().numpy().astype(np.float64)
         want = ref[k].astype(np.float64)
         assert np.abs(got - want).max() <= 3e-4 * np.abs(want).max() + 1e-7, k
+
+
+def test_module_call_inside_autocast_and_with_strided_inputs():
+    """The reference calls the rasteriser inside ``torch.cuda.amp.autocast`` (gs.py:98) with matrices sliced from
+    [B,V,4,4] batches (gs.py:78-80): results must stay fp32 and identical; strided inputs are made contiguous."""
+    from sigman_release_b200 import GaussianRasterizationSettings, GaussianRasterizer
+    sc = small_scene(n=500, seed=2, spread=0.3, smin=0.01, smax=0.06)
+    vm, pm, cp = cameras.orbit_cameras([30, 45])
+    cam_view = to_dev(vm)[None]; cam_vp = to_dev(pm)[None]; cam_pos = to_dev(cp)[None]
+    wide = to_dev(np.concatenate([sc["means3D"], np.zeros_like(sc["means3D"])], axis=1))       # [N,6]: strided view below
+    means = wide[:, :3].clone().requires_grad_(True)
+    strided = wide[:, :3]
+    assert not strided.is_contiguous()
+    cov = to_dev(sc["cov3D"]); col = to_dev(sc["colors"]); op = to_dev(sc["opacities"]).reshape(-1, 1)
+
+    def call(m, autocast):
+        s = GaussianRasterizationSettings(image_height=72, image_width=56, tanfovx=np.float64(TAN), tanfovy=np.float64(TAN),
+                                          bg=torch.ones(3, device="cuda"), scale_modifier=0.5, viewmatrix=cam_view[0, 1],
+                                          projmatrix=cam_vp[0, 1], sh_degree=0, campos=cam_pos[0, 1], prefiltered=False,
+                                          debug=False)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            return GaussianRasterizer(raster_settings=s)(means3D=m, means2D=torch.zeros_like(m), shs=None,
+                                                         colors_precomp=col, opacities=op, cov3D_precomp=cov)
+
+    ref = call(means, False)
+    got = call(means, True)
+    got_strided = call(strided, True)
+    for a, b, c in zip(ref, got, got_strided):
+        assert a.dtype == b.dtype and torch.equal(a, b) and torch.equal(a, c)
+    assert ref[0].dtype == torch.float32 and ref[1].dtype == torch.int32
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        got[0].sum().backward()
+    assert means.grad is not None and means.grad.dtype == torch.float32 and bool(torch.isfinite(means.grad).all())
+    _, ora = oracle_forward(sc, vm[1], pm[1], 72, 56)
+    np.testing.assert_array_equal(ref[0].detach().cpu().numpy(), ora.color)
