@@ -123,22 +123,23 @@ __global__ void __launch_bounds__(32 * kPreBwdSlots, SGR_PREBWD_MIN_CTAS) prepro
 #pragma unroll
     for (int k = 0; k < kPreBwdVals; ++k) s_part[slot][k][lane] = vals[k];
     __syncthreads();
-    if (slot != 0 || !live) return;
-#pragma unroll
-    for (int k = 0; k < kPreBwdVals; ++k) {
-        float v = vals[k];
-#pragma unroll
-        for (int y = 1; y < kPreBwdSlots; ++y) v += s_part[y][k][lane];
-        vals[k] = v;
-    }
+    if (!live) return;
+    // the 13 per-Gaussian sums are spread over the CTA's warps: warp y sums values y and y + 8 over the view slots
+    // (in slot order: deterministic) and stores them
     const bool first = r_lo == b * V;            // this chunk holds the subject's first view: store, else accumulate
 #pragma unroll
-    for (int k = 0; k < 3; ++k) a.d_means3D[3 * gi + k] = (first ? 0.0f : a.d_means3D[3 * gi + k]) + vals[k];
+    for (int kk = 0; kk < 2; ++kk) {
+        const int k = slot + kk * kPreBwdSlots;
+        if (k >= kPreBwdVals) break;
+        float v = s_part[0][k][lane];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) a.d_cov3D[6 * gi + k] = (first ? 0.0f : a.d_cov3D[6 * gi + k]) + vals[3 + k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) a.d_colors[3 * gi + k] = (first ? 0.0f : a.d_colors[3 * gi + k]) + vals[9 + k];
-    a.d_opac[gi] = (first ? 0.0f : a.d_opac[gi]) + vals[12];
+        for (int y = 1; y < kPreBwdSlots; ++y) v += s_part[y][k][lane];
+        float* dst = k < 3 ? a.d_means3D + 3 * gi + k
+                   : k < 9 ? a.d_cov3D + 6 * gi + (k - 3)
+                   : k < 12 ? a.d_colors + 3 * gi + (k - 9)
+                            : a.d_opac + gi;
+        *dst = (first ? 0.0f : *dst) + v;
+    }
 }
 
 
