@@ -1,7 +1,7 @@
 """CPU-side statistics over a whole view: (Gaussian, 4x2 quarter) pairs kept by the bbox cull vs. pairs in which at
 least one pixel passes the alpha test (the floor of any conservative cull) — sizing tool for the quarter masks."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import oracle
 from sigman_release_b200 import cameras, scenes

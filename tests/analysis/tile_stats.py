@@ -1,7 +1,7 @@
 """CPU-side statistics of one tile's list (oracle geometry): how many records survive the per-warp bbox cull,
 how many pass the alpha test, when warps finish."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import oracle
 from sigman_release_b200 import cameras, scenes
