@@ -442,12 +442,15 @@ cudaError_t launch_sort_tiles(const ChunkCtx& c) {
     a.tile_off = c.tile_off; a.tile_cnt = c.tile_cnt; a.keys = c.keys; a.sorted_ids = c.sorted_ids;
     a.rec0 = c.rec0; a.rec1 = c.rec1; a.rec2 = c.rec2; a.g0 = c.g0; a.g1 = c.g1; a.g2 = c.g2;
     a.work = c.work_blend; a.wc = c.work_counts;
-    static int num_sms = 0;
-    static bool attr_set = false;
+    const int dslot = current_device_slot();
+    static int num_sms_dev[kMaxDevices] = {};
+    static bool attr_set_dev[kMaxDevices] = {};
+    static int small_per_sm_dev[kMaxDevices] = {};
+    int& num_sms = num_sms_dev[dslot];
+    bool& attr_set = attr_set_dev[dslot];
+    int& small_per_sm = small_per_sm_dev[dslot];
     if (num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dslot);
         if (num_sms <= 0) num_sms = 148;
     }
     // Shared-memory key buffer of the big kernel: sized from the caller's hint of the longest list (a CTA that takes
@@ -459,7 +462,6 @@ cudaError_t launch_sort_tiles(const ChunkCtx& c) {
     }
     a.big_smem_keys = big_keys;
     const size_t big_smem = size_t(big_keys) * 8 + size_t(kBigSortBuckets) * 4;
-    static int small_per_sm = 0;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              int(size_t(kBigSortSmemCap) * 8 + size_t(kBigSortBuckets) * 4));
@@ -470,16 +472,7 @@ cudaError_t launch_sort_tiles(const ChunkCtx& c) {
         attr_set = true;
     }
     const int total_tiles = c.num_renders * c.g.num_tiles;
-    // The few long lists (one 1024-thread CTA each, latency bound) run concurrently with the many short ones on a
-    // side stream: fork after the scatter, join before the blend.
-    static cudaStream_t side = nullptr;
-    static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaError_t e;
-    if (!side) {
-        if ((e = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking)) != cudaSuccess) return e;
-        if ((e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
-        if ((e = cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming)) != cudaSuccess) return e;
-    }
     static int mode = -1;      // experiment switch: 0 PDL overlap (default), 1 serial, 2 small only, 3 big only, 4 two streams
     if (mode < 0) { const char* m = getenv("SGR_SORT_MODE"); mode = m ? atoi(m) : 0; }
     if (mode >= 1 && mode <= 3) {
@@ -506,7 +499,16 @@ cudaError_t launch_sort_tiles(const ChunkCtx& c) {
         cfg.numAttrs = 1;
         return cudaLaunchKernelEx(&cfg, sort_small_kernel, a);
     }
-    // mode 4: the same overlap with a side stream and events
+    // mode 4 (experiment): the same overlap with a side stream and events instead of the dependent launch
+    static cudaStream_t side_dev[kMaxDevices] = {};
+    static cudaEvent_t ev_fork_dev[kMaxDevices] = {}, ev_join_dev[kMaxDevices] = {};
+    cudaStream_t& side = side_dev[dslot];
+    cudaEvent_t &ev_fork = ev_fork_dev[dslot], &ev_join = ev_join_dev[dslot];
+    if (!side) {
+        if ((e = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
     if ((e = cudaEventRecord(ev_fork, c.stream)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(side, ev_fork, 0)) != cudaSuccess) return e;
     sort_big_kernel<<<min(num_sms, total_tiles), kBigSortThreads, big_smem, c.stream>>>(a);

@@ -836,15 +836,14 @@ __global__ void __launch_bounds__(1024) loss_reduce_kernel(const float* part, un
     if (threadIdx.x == 0) *loss_out = (first ? 0.0f : *loss_out) + float(sh[0] * double(scale));
 }
 
-int g_num_sms = 0;
+int g_num_sms[kMaxDevices] = {};
 int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
+    const int d = current_device_slot();
+    if (g_num_sms[d] == 0) {
+        cudaDeviceGetAttribute(&g_num_sms[d], cudaDevAttrMultiProcessorCount, d);
+        if (g_num_sms[d] <= 0) g_num_sms[d] = 148;
     }
-    return g_num_sms;
+    return g_num_sms[d];
 }
 
 // Opts the kernel into its dynamic shared memory size and returns the resident CTAs per SM (cached per kernel).
@@ -875,7 +874,8 @@ cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out
     a.loss_target = c.loss_target; a.loss_mask = c.loss_mask; a.loss_dL_dcolor = c.loss_dL_dcolor;
     a.loss_part = c.loss_part; a.loss_scale = c.loss_scale;
     constexpr size_t smem = sizeof(FwdSmem) * kWarpsPerCta;
-    static int per_sm = 0;
+    static int per_sm_dev[kMaxDevices] = {};
+    int& per_sm = per_sm_dev[current_device_slot()];
     if (per_sm == 0) {
         cudaError_t e = prepare_kernel(blend_forward_kernel, smem, &per_sm);
         if (e != cudaSuccess) return e;
@@ -907,14 +907,16 @@ cudaError_t launch_blend_backward(const ChunkCtx& c, const float* out_alpha, con
     const long long items = (long long)c.num_renders * c.g.num_tiles * kBlocksPerTile;
     const long long want = (items + kWarpsPerCta - 1) / kWarpsPerCta;
     if (dL_ddepth || dL_dalpha) {
-        static int per_sm = 0;
+        static int per_sm_dev[kMaxDevices] = {};
+        int& per_sm = per_sm_dev[current_device_slot()];
         if (per_sm == 0) {
             cudaError_t e = prepare_kernel(blend_backward_kernel<true>, smem, &per_sm);
             if (e != cudaSuccess) return e;
         }
         blend_backward_kernel<true><<<int(min((long long)num_sms() * per_sm, want)), kBlendThreads, smem, c.stream>>>(a);
     } else {
-        static int per_sm = 0;
+        static int per_sm_dev[kMaxDevices] = {};
+        int& per_sm = per_sm_dev[current_device_slot()];
         if (per_sm == 0) {
             cudaError_t e = prepare_kernel(blend_backward_kernel<false>, smem, &per_sm);
             if (e != cudaSuccess) return e;

@@ -189,6 +189,14 @@ constexpr float kTMin = 0.0001f;
 // streaming 128-bit loads/stores
 __device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
 
+// Per-device launch caches (function attributes and occupancy are per device; one process may drive several GPUs).
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
 // host-side launch wrappers implemented in the .cu files -------------------------------------------
 struct ChunkCtx {
     RenderGeom g;

@@ -475,3 +475,26 @@ def test_module_call_inside_autocast_and_with_strided_inputs():
     assert means.grad is not None and means.grad.dtype == torch.float32 and bool(torch.isfinite(means.grad).all())
     _, ora = oracle_forward(sc, vm[1], pm[1], 72, 56)
     np.testing.assert_array_equal(ref[0].detach().cpu().numpy(), ora.color)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process():
+    """Kernel attributes / occupancy caches are per device: the same process renders on cuda:0 and cuda:1 and gets
+    identical, oracle-exact images (the library takes the device from the current context set by the shim)."""
+    sc = small_scene(n=3000, seed=4, spread=0.4, smin=0.005, smax=0.07)
+    vm, pm, _ = cameras.orbit_cameras([30, 65])
+    outs = []
+    for d in (0, 1, 0):
+        dev = torch.device("cuda", d)
+        f = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device=dev)
+        t = {k: f(sc[k])[None].requires_grad_(True) for k in ("means3D", "cov3D", "colors")}
+        op = f(sc["opacities"]).reshape(1, -1).requires_grad_(True)
+        color, radii, depth, alpha = rasterizer.rasterize_batch(t["means3D"], t["cov3D"], t["colors"], op, f(vm)[None],
+                                                                f(pm)[None], torch.ones(3, device=dev), 96, 96, TAN, TAN)
+        color.sum().backward()
+        assert color.device == dev and t["means3D"].grad.device == dev
+        outs.append((color.detach().cpu(), t["means3D"].grad.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][0], outs[2][0])
+    assert float((outs[0][1] - outs[1][1]).abs().max()) <= 3e-4 * float(outs[0][1].abs().max())
+    _, ora = oracle_forward(sc, vm[0], pm[0], 96, 96)
+    np.testing.assert_array_equal(outs[1][0][0, 0].numpy(), ora.color)
