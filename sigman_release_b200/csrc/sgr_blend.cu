@@ -676,8 +676,15 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
                 ++issued; ++b_issued;
             }
             const int s = consumed % kBwdStages;
+#ifdef SGR_PHASE_TIMING
+            long long bt = clock64();
+#define BPH(k) do { const long long n__ = clock64(); if (lane == 0) atomicAdd(&g_phase[k], (unsigned long long)(n__ - bt)); bt = n__; } while (0)
+#else
+#define BPH(k)
+#endif
             mbar_wait(&sm.full[s], (consumed / kBwdStages) & 1);
             ++consumed;
+            BPH(0);
             const unsigned int cbase = lo + (nb - 1 - b) * kBwdBatch;     // list index of the batch's first record
             const unsigned int m = min(unsigned(kBwdBatch), hi - cbase);
             const float4* r0 = sm.r0[s];
@@ -686,6 +693,10 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
             unsigned int qbits[kBwdBatch / 32];
             const uint4 cnt = cull_batch<true, kBwdBatch>(r0, m, blk, sm.list, lane, qbits);
             const int total = int(max(max(cnt.x, cnt.y), max(cnt.z, cnt.w)));
+            BPH(1);
+#ifdef SGR_PHASE_TIMING
+            if (lane == 0) { atomicAdd(&g_phase[4], (unsigned long long)total); atomicAdd(&g_phase[5], 1ull); }
+#endif
             // trip t of the batch handles the quarter's survivor number (my_n - 1 - t): back to front
             const float nTb = -T_final * bg_dot;
             for (int base = 0; base < total; base += kBwdSlots) {
@@ -756,6 +767,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
                     }
                 }
                 __syncwarp();
+                BPH(2);
                 // ---- phase C: the roles flip to lane = (trip, quarter) pair, i.e. one Gaussian of one quarter; the
                 // lane sums the gradient terms of the quarter's 8 pixels in registers (no shuffles) and issues the
                 // atomics.  The pass's pairs are enumerated quarter by quarter and taken 32 at a time.
@@ -815,6 +827,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
                     }
                 }
                 __syncwarp();
+                BPH(3);
             }
         }
         __syncwarp();
