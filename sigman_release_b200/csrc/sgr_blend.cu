@@ -56,7 +56,10 @@ constexpr int kWarpsPerCta = 8;
 constexpr int kBlendThreads = kWarpsPerCta * 32;
 constexpr int kBlocksPerTile = 8;              // a 16x16 tile = eight 8x4 pixel blocks = eight work items
 constexpr int kBlockW = 8, kBlockH = 4;        // pixel block of one warp (four 4x2 quarters walk separate lists)
-constexpr int kBwdSlots = 16;                  // backward: trips per phase pass
+#ifndef SGR_BWD_SLOTS
+#define SGR_BWD_SLOTS 16
+#endif
+constexpr int kBwdSlots = SGR_BWD_SLOTS;       // backward: trips per phase pass (8 or 16: the stash swizzle)
 constexpr unsigned int kFull = 0xffffffffu;
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
