@@ -1,10 +1,10 @@
 """Experiment: per-phase cycle counters of the forward blend (needs a library built with -DSGR_PHASE_TIMING)."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import torch
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from sigman_release_b200 import _native, scenes
-from gpu_utils import gpu_forward
+from common import gpu_forward
 VIEWS = [30, 37, 45, 53, 65, 85, 0, 8]
 sc = scenes.body_gaussians(100_000, seed=0)
 L = _native.lib()

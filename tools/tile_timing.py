@@ -2,11 +2,11 @@
 import ctypes
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 import torch
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from sigman_release_b200 import _native, scenes
-from gpu_utils import gpu_forward, saved_state
+from common import gpu_forward, saved_state
 
 VIEWS = [30, 37, 45, 53, 65, 85, 0, 8]
 sc = scenes.body_gaussians(100_000, seed=0)
