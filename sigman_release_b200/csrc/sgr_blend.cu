@@ -68,15 +68,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
-    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -665,11 +659,13 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
 
         // walk step k handles list batch (nb - 1 - k)
         unsigned int b_issued = 0;
-        while (b_issued < nb && b_issued < unsigned(kBwdStages - 1)) {
-            const unsigned int lb = nb - 1 - b_issued;
-            ring_issue(sm, issued, g0 + lb * kBwdBatch, g1 + lb * kBwdBatch, g2 + lb * kBwdBatch,
-                       min(unsigned(kBwdBatch), hi - lo - lb * kBwdBatch), lane);
-            ++issued; ++b_issued;
+        if constexpr (kBwdStages > 1) {              // prefetch depth of the ring (none with a single stage)
+            while (b_issued < nb && b_issued < unsigned(kBwdStages - 1)) {
+                const unsigned int lb = nb - 1 - b_issued;
+                ring_issue(sm, issued, g0 + lb * kBwdBatch, g1 + lb * kBwdBatch, g2 + lb * kBwdBatch,
+                           min(unsigned(kBwdBatch), hi - lo - lb * kBwdBatch), lane);
+                ++issued; ++b_issued;
+            }
         }
         for (unsigned int b = 0; b < nb; ++b) {
             if (b_issued < nb) {
