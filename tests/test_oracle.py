@@ -306,3 +306,19 @@ def test_prep_cov3d_oracle_matches_reference_ops():
     got = oracle.prep_cov3d(s.numpy(), R.numpy(), d2.numpy(), np.float64)
     # off-diagonal entries cancel: tolerance relative to the Gaussian's largest covariance entry
     assert float((np.abs(got - want) / np.abs(want).max(axis=1, keepdims=True)).max()) <= 1e-12
+
+
+def test_oracle_reproduces_its_golden_fixture():
+    """tests/golden/oracle_scene_v1.npz (made by tests/golden/make_oracle_fixture.py): the fp32 spec is bit-stable —
+    images, radii, lists and n_contrib are reproduced exactly, gradients to fp32 rounding (OpenMP summation order)."""
+    import importlib.util, os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_oracle_fixture", os.path.join(here, "make_oracle_fixture.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    gold = np.load(os.path.join(here, "oracle_scene_v1.npz"))
+    o, b, g, grads = mod.render(mod.scene())
+    for k, v in (("color", o.color), ("depth", o.depth), ("alpha", o.alpha), ("radii", o.radii),
+                 ("point_list", b["point_list"]), ("ranges", b["ranges"]), ("n_contrib", b["n_contrib"])):
+        np.testing.assert_array_equal(v, gold[k], err_msg=k)
+    for k, v in grads.items():
+        np.testing.assert_allclose(v, gold["grad_" + k], rtol=1e-5, atol=1e-6 * np.abs(gold["grad_" + k]).max())
