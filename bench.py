@@ -195,7 +195,7 @@ def run_ours(args):
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     gathered = torch.zeros(world, device=dev) if world > 1 else None
 
-    def render_step(t):
+    def render_step(t, gather=True):
         for v in t.values():
             v.grad = None
         if args.unfused_loss:
@@ -206,7 +206,7 @@ def run_ours(args):
             loss = rasterizer.render_l1_loss(t["means3D"], t["cov3D"], t["colors"], t["opacities"], vmt, pmt, bg, H, W,
                                              tan, tan, target)[0]
         loss.backward()
-        if world > 1:
+        if world > 1 and gather:
             dist.all_gather_into_tensor(gathered, loss.detach().reshape(1))
         return loss
 
@@ -236,6 +236,30 @@ def run_ours(args):
     d2h_bytes = host_out[0].numel() * 4
     e2e_k = [0]
 
+    def compute_and_pack(slot, gather):
+        loss = render_step(e2e_dev[slot], gather)
+        with torch.no_grad():                              # gradients + loss packed for one download
+            torch.cat([e2e_dev[slot][name].grad.reshape(-1) for name in names] + [loss.detach().reshape(1)],
+                      out=dev_out[slot])
+
+    # The launch path has no host read and no blocking wait, so the whole step is captured once per buffer slot in a
+    # CUDA graph (sigman_release_b200.GraphedStep) and replayed: the host cost per step drops from ~0.3 ms of Python /
+    # autograd / launch calls to one graph launch, which is what keeps 8 ranks on one host from becoming host-bound.
+    e2e_graphs = [None, None]
+
+    def build_e2e_graphs():
+        if args.no_graph:
+            return
+        from sigman_release_b200 import GraphedStep
+        try:
+            for slot in range(2):
+                with torch.no_grad():
+                    dev_in[slot].copy_(host_in.to(dev))
+                e2e_graphs[slot] = GraphedStep(lambda slot=slot: compute_and_pack(slot, False), device=dev)
+        except Exception as exc:                           # capture is an optimisation: fall back to eager launches
+            e2e_graphs[0] = e2e_graphs[1] = None
+            print(f"bench.py: CUDA graph capture failed, e2e runs eagerly: {exc}", file=sys.stderr)
+
     def e2e_step():
         k = e2e_k[0]
         slot = k % 2
@@ -245,10 +269,12 @@ def run_ours(args):
                 dev_in[0].copy_(host_in, non_blocking=True)
                 h2d_done[0].record(copy_stream)
         main.wait_event(h2d_done[slot])
-        loss = render_step(e2e_dev[slot])
-        with torch.no_grad():                              # gradients + loss packed for one download
-            torch.cat([e2e_dev[slot][name].grad.reshape(-1) for name in names] + [loss.detach().reshape(1)],
-                      out=dev_out[slot])
+        if e2e_graphs[slot] is not None:
+            e2e_graphs[slot].replay()                      # forward + backward + packing as one CUDA graph launch
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, dev_out[slot][-1:])
+        else:
+            compute_and_pack(slot, True)
         computed[slot].record(main)
         with torch.cuda.stream(copy_stream):
             dev_in[1 - slot].copy_(host_in, non_blocking=True)   # inputs of step k+1 travel while step k computes
@@ -306,6 +332,7 @@ def run_ours(args):
     launches0 = int(L.sgr_launch_count())
     ms_step = timed(lambda: render_step(d), args.steps, 0)
     launches = int(L.sgr_launch_count()) - launches0         # kernels of libsgr_b200.so launched in the timed region
+    build_e2e_graphs()
     ms_e2e = timed(e2e_step, args.steps, 2, finish=e2e_finish)
     clocks = sampler.stop()
 
@@ -367,7 +394,9 @@ def run_ours(args):
                 "ms_per_step": ms_e2e, "views_per_sec": V * world / (ms_e2e * 1e-3),
                 "pipeline": "pinned host -> device upload of step k+1 and device -> pinned host download of the "
                             "gradients + loss of step k (one packed buffer per direction) on a copy stream, "
-                            "overlapped with the compute of step k"},
+                            "overlapped with the compute of step k; the step itself (forward + backward + packing) "
+                            + ("is replayed as one CUDA graph per buffer slot (sigman_release_b200.GraphedStep)"
+                               if e2e_graphs[0] is not None else "is launched eagerly")},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "host_enqueue_ms_per_step": {"value_leg": host_ms[0], "e2e_leg": host_ms[1]},
         "status": rasterizer.last_status(),
@@ -400,6 +429,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the e2e step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--unfused-loss", action="store_true",
                     help="compute the L1 loss with torch ops on the rendered images instead of the fused epilogue")
     args = ap.parse_args()

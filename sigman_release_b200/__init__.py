@@ -11,7 +11,9 @@ from .rasterizer import (  # noqa: E402,F401
     cov3d_from_scale_rot,
     last_status,
     check_status,
+    graph_status,
     render_l1_loss,
     sh_colors,
 )
+from .graphs import GraphedStep  # noqa: E402,F401
 from .renderer import GaussianRenderer, distCUDA2, get_covariance, prep_cov3d  # noqa: E402,F401

@@ -21,7 +21,7 @@ import torch
 from . import _native
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_batch", "render_l1_loss", "rasterize_gaussians",
-           "cov3d_from_scale_rot", "sh_colors", "last_status", "check_status"]
+           "cov3d_from_scale_rot", "sh_colors", "last_status", "check_status", "graph_status"]
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -100,6 +100,33 @@ def _drain_pending(block: bool) -> None:
     _pending[:] = keep
 
 
+_graph_status: dict = {}       # device index -> persistent pinned status buffer of graph-captured forwards
+
+
+def _graph_status_buffer(dev) -> torch.Tensor:
+    buf = _graph_status.get(dev.index)
+    if buf is None:
+        buf = torch.zeros((64,), dtype=torch.uint8).pin_memory()
+        _graph_status[dev.index] = buf
+    return buf
+
+
+def graph_status(device=None) -> Optional[dict]:
+    """Status block written by the most recent replay of a CUDA graph that captured a forward on ``device`` (call after
+    synchronising the replay stream); raises ``SgrError`` if that replay ran out of instance capacity — re-run the
+    step eagerly once (the estimate grows) and capture again."""
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    buf = _graph_status.get(idx)
+    if buf is None:
+        return None
+    st = _status_from_bytes(buf)
+    if st["overflow"]:
+        raise _native.SgrError(_native.SGR_E_INSTANCE_OVERFLOW,
+                               f"a graph replay overflowed its instance capacity ({st['instances_required']} needed, "
+                               f"{st['instances_capacity']} available); re-run eagerly and re-capture")
+    return st
+
+
 def check_status() -> Optional[dict]:
     """Waits for every deferred overflow check (``SGR_OVERFLOW_CHECK=deferred``) and raises ``SgrError`` if a
     forward since the last check ran out of instance capacity; returns the latest status block.  Call it where the
@@ -174,10 +201,16 @@ class _RasterizeBatch(torch.autograd.Function):
             loss = torch.empty((), dtype=torch.float32, device=dev) if fused else None
             g_fused = torch.empty((B, V, 3, H, W), dtype=torch.float32, device=dev) if fused else None
             key = (dev.index, N, H, W)
-            _drain_pending(block=False)
+            capturing = torch.cuda.is_current_stream_capturing()
+            if not capturing:
+                _drain_pending(block=False)
+                _graph_status_buffer(dev)                # pinned allocation must not happen inside a later capture
             first = key not in _est_per_render
+            if capturing and first:
+                raise RuntimeError("run the step at least once before capturing it in a CUDA graph: the first call for "
+                                   "a problem shape sizes the instance buffers with a synchronous status read")
             per = _est_per_render.get(key, max(3 * N, 4096))
-            sync_check = first or _OVERFLOW_MODE == "sync"
+            sync_check = (first or _OVERFLOW_MODE == "sync") and not capturing
             while True:
                 cap = min(int(per) * R, (1 << 32) - 2)
                 state_bytes, scratch_bytes = _buffer_bytes(L, B, V, N, H, W, cap, renders_per_chunk)
@@ -195,6 +228,11 @@ class _RasterizeBatch(torch.autograd.Function):
                     a.loss_dL_dcolor, a.loss_out = _ptr(g_fused), _ptr(loss)
                     a.loss_scale = 1.0 / float(B * V * 3 * H * W)
                 _native.check(L.sgr_forward(ctypes.byref(a)))
+                if capturing:
+                    # inside a CUDA graph capture: no events, no host reads.  The status block of every replay lands
+                    # in a persistent pinned buffer that graph_status() decodes after the caller has synchronised.
+                    _graph_status_buffer(dev).copy_(state[:64], non_blocking=True)
+                    break
                 if not sync_check:
                     pinned, ev = _status_slot()
                     pinned.copy_(state[:64], non_blocking=True)
@@ -246,7 +284,8 @@ class _RasterizeBatch(torch.autograd.Function):
         # Deferred overflow checks never block the launch path (a blocking wait here would idle the GPU for the whole
         # launch latency of the backward): an overflow surfaces at the first rasteriser call after its status copy
         # has landed, or at check_status().
-        _drain_pending(block=False)
+        if not torch.cuda.is_current_stream_capturing():
+            _drain_pending(block=False)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev)
             if g_color is None:

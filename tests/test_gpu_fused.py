@@ -165,3 +165,41 @@ def test_rasterizer_module_accepts_shs():
     assert torch.equal(img, img2)
     img.sum().backward()
     assert sh.grad is not None and float(sh.grad[:, :9].abs().sum()) > 0 and float(sh.grad[:, 9:].abs().sum()) == 0
+
+
+def test_step_captured_in_a_cuda_graph_replays_correctly():
+    """The launch path has no host read / blocking wait, so forward + backward can be captured in a CUDA graph
+    (sigman_release_b200.GraphedStep): replays with refreshed static inputs reproduce the eager results."""
+    from sigman_release_b200 import GraphedStep, graph_status
+    H = W = 96
+    views = [30, 65]
+    vmt, pmt, _, _ = view_tensors(views)
+    bg = torch.ones(3, device="cuda")
+    target = torch.rand((1, len(views), 3, H, W), device="cuda")
+    scenes_np = [scenes.body_gaussians(5000, seed=s) for s in (1, 2)]
+    static = scene_tensors(scenes_np[0], requires_grad=True)
+
+    def step():
+        for v in static.values():                              # backward must ASSIGN the (static) .grad tensors, not add to them
+            v.grad = None
+        loss = rasterizer.render_l1_loss(static["means3D"], static["cov3D"], static["colors"], static["opacities"], vmt, pmt,
+                                         bg, H, W, TAN, TAN, target)[0]
+        loss.backward()
+        return loss
+
+    graphed = GraphedStep(step)
+    for sc in scenes_np[::-1] + scenes_np:                   # refresh the static inputs in place, replay, compare to eager
+        fresh = scene_tensors(sc, requires_grad=True)
+        with torch.no_grad():
+            for k in static:
+                static[k].copy_(fresh[k])
+        loss_g = graphed.replay()
+        torch.cuda.synchronize()
+        assert graph_status()["overflow"] == 0
+        loss_e = rasterizer.render_l1_loss(fresh["means3D"], fresh["cov3D"], fresh["colors"], fresh["opacities"], vmt, pmt,
+                                           bg, H, W, TAN, TAN, target)[0]
+        loss_e.backward()
+        assert abs(float(loss_g) - float(loss_e)) <= 1e-6 * abs(float(loss_e))
+        for k in static:
+            ge, gg = fresh[k].grad, static[k].grad
+            assert float((ge - gg).abs().max()) <= 3e-4 * float(ge.abs().max()) + 1e-12, k
