@@ -30,6 +30,10 @@ __all__ = ["GraphedStep"]
 class GraphedStep:
     def __init__(self, fn: Callable[[], object], warmup: int = 3, device=None):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        try:        # the warm-up runs on a side stream on purpose; the leaves were created on the caller's stream
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        except AttributeError:
+            pass
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):                       # eager warm-up on a side stream (torch's capture recipe)
