@@ -7,7 +7,8 @@ Gaussian human at 512x512).
 Workload at N = 1 (BASELINE.json configs[1]): one ~100K-Gaussian human-shaped subject, 8 views of 512x512,
 forward + backward (L1 loss on the clamped RGB, SIGMAN's case).  A step is one such pass.  With N > 1 every rank
 renders its own subject (independent (subject, view) pairs shard with no data-path collective; the per-rank loss is
-all-gathered, mirroring /root/reference/train_vae.py:256-257) -> weak scaling.
+accumulated on the device and all-gathered once per timed region, like the reference's per-epoch
+``accelerator.gather_for_metrics(total_loss)``, /root/reference/train_vae.py:256-257) -> weak scaling.
 
 ``--impl reference`` times the CPU oracle (the only executable restatement of the reference's rasteriser: the
 third-party package itself is absent from the reference tree) on the host cores, on a bounded sample of the same
@@ -194,8 +195,9 @@ def run_ours(args):
     target = torch.rand((1, V, 3, H, W), device=dev, generator=torch.Generator(device=dev).manual_seed(1 + rank))
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     gathered = torch.zeros(world, device=dev) if world > 1 else None
+    total_loss = torch.zeros((), device=dev)
 
-    def render_step(t, gather=True):
+    def render_step(t):
         for v in t.values():
             v.grad = None
         if args.unfused_loss:
@@ -206,8 +208,7 @@ def run_ours(args):
             loss = rasterizer.render_l1_loss(t["means3D"], t["cov3D"], t["colors"], t["opacities"], vmt, pmt, bg, H, W,
                                              tan, tan, target)[0]
         loss.backward()
-        if world > 1 and gather:
-            dist.all_gather_into_tensor(gathered, loss.detach().reshape(1))
+        total_loss.add_(loss.detach())           # train_vae.py:233-235 accumulates; the gather is once per epoch (:256)
         return loss
 
     # e2e: host buffers in, gradients + loss out, through the public API
@@ -215,7 +216,8 @@ def run_ours(args):
     # gradients + loss of step k while the launch stream computes; every step still moves its own inputs and results.
     # One pinned staging buffer per direction and slot (13 floats per Gaussian in, 13 + the loss out): one H2D and one
     # D2H copy per step keep the host-side enqueue cost low when 8 ranks share the host.
-    copy_stream = torch.cuda.Stream(device=dev)
+    copy_stream = torch.cuda.Stream(device=dev)            # uploads
+    down_stream = torch.cuda.Stream(device=dev)            # downloads (PCIe is full duplex: one stream per direction)
     names = list(host)
     sizes = [host[k].numel() for k in names]
     host_in = torch.cat([host[k].reshape(-1) for k in names]).pin_memory()
@@ -236,8 +238,8 @@ def run_ours(args):
     d2h_bytes = host_out[0].numel() * 4
     e2e_k = [0]
 
-    def compute_and_pack(slot, gather):
-        loss = render_step(e2e_dev[slot], gather)
+    def compute_and_pack(slot):
+        loss = render_step(e2e_dev[slot])
         with torch.no_grad():                              # gradients + loss packed for one download
             torch.cat([e2e_dev[slot][name].grad.reshape(-1) for name in names] + [loss.detach().reshape(1)],
                       out=dev_out[slot])
@@ -255,7 +257,7 @@ def run_ours(args):
             for slot in range(2):
                 with torch.no_grad():
                     dev_in[slot].copy_(host_in.to(dev))
-                e2e_graphs[slot] = GraphedStep(lambda slot=slot: compute_and_pack(slot, False), device=dev)
+                e2e_graphs[slot] = GraphedStep(lambda slot=slot: compute_and_pack(slot), device=dev)
         except Exception as exc:                           # capture is an optimisation: fall back to eager launches
             e2e_graphs[0] = e2e_graphs[1] = None
             print(f"bench.py: CUDA graph capture failed, e2e runs eagerly: {exc}", file=sys.stderr)
@@ -271,23 +273,31 @@ def run_ours(args):
         main.wait_event(h2d_done[slot])
         if e2e_graphs[slot] is not None:
             e2e_graphs[slot].replay()                      # forward + backward + packing as one CUDA graph launch
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, dev_out[slot][-1:])
         else:
-            compute_and_pack(slot, True)
+            compute_and_pack(slot)
         computed[slot].record(main)
         with torch.cuda.stream(copy_stream):
+            if k > 0:
+                copy_stream.wait_event(computed[1 - slot])       # step k-1 has finished reading that input slot
             dev_in[1 - slot].copy_(host_in, non_blocking=True)   # inputs of step k+1 travel while step k computes
             h2d_done[1 - slot].record(copy_stream)
-            copy_stream.wait_event(computed[slot])
+        with torch.cuda.stream(down_stream):
+            down_stream.wait_event(computed[slot])
             host_out[slot].copy_(dev_out[slot], non_blocking=True)
-            d2h_done[slot].record(copy_stream)
+            d2h_done[slot].record(down_stream)
         if k > 0:
             main.wait_event(d2h_done[1 - slot])            # results of step k-1 are on the host before step k ends
         e2e_k[0] = k + 1
 
-    def e2e_finish():                                      # results of the last step
+    def gather_losses():
+        # the per-rank accumulated loss is all-gathered once per timed region, like the reference gathers its epoch
+        # total (accelerator.gather_for_metrics(total_loss), /root/reference/train_vae.py:256) — not once per step
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, total_loss.reshape(1))
+
+    def e2e_finish():                                      # results of the last step, then the loss gather
         torch.cuda.current_stream(dev).wait_event(d2h_done[(e2e_k[0] - 1) % 2])
+        gather_losses()
 
     host_ms = []
 
@@ -330,7 +340,7 @@ def run_ours(args):
     sampler.start()
     time.sleep(0.25)                                          # let the sampler take a first reading under no load
     launches0 = int(L.sgr_launch_count())
-    ms_eager = timed(lambda: render_step(d), args.steps, 0)
+    ms_eager = timed(lambda: render_step(d), args.steps, 0, finish=gather_losses)
     launches = int(L.sgr_launch_count()) - launches0         # kernels of libsgr_b200.so launched in the timed region
     # The same step replayed as a CUDA graph (the launch path is capturable: no host reads, no blocking waits): the
     # kernels and their order are identical (`launches` per `steps` above, counted on the eager pass — the library's
@@ -340,14 +350,8 @@ def run_ours(args):
     if not args.no_graph:
         from sigman_release_b200 import GraphedStep
         try:
-            value_graph = GraphedStep(lambda: render_step(d, False), device=dev)
-
-            def graph_step():
-                value_graph.replay()
-                if world > 1:
-                    dist.all_gather_into_tensor(gathered, value_graph.result.detach().reshape(1))
-
-            ms_step = timed(graph_step, args.steps, 3)
+            value_graph = GraphedStep(lambda: render_step(d), device=dev)
+            ms_step = timed(value_graph.replay, args.steps, 3, finish=gather_losses)
         except Exception as exc:
             value_graph = None
             print(f"bench.py: CUDA graph capture failed, value runs eagerly: {exc}", file=sys.stderr)
