@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SGR_ABI_VERSION 2
+#define SGR_ABI_VERSION 3
 
 typedef enum SgrError {
     SGR_OK = 0,
@@ -45,7 +45,13 @@ enum {
     SGR_FLAG_CLAMP_COLOR = 2,      /* fuse gs.py:107 `rendered_image.clamp(0, 1)` into the blend epilogue */
     SGR_FLAG_FORWARD_ONLY = 4,     /* no backward will follow: skip the forward's bookkeeping for it (the refinement
                                       of the per-instance cull masks to the quarters that actually blended) */
-    SGR_FLAG_TILE_TIMING = 8       /* record per-tile forward blend timings (sgr_debug_copy_state: tile_timing) */
+    SGR_FLAG_TILE_TIMING = 8,      /* record per-tile forward blend timings (sgr_debug_copy_state: tile_timing) */
+    SGR_FLAG_EXACT_EXP = 16        /* evaluate exp(power) with the oracle's fixed IEEE fp32 sequence (exp_spec) instead of
+                                      the SFU's ex2: colour / depth / alpha / n_contrib become bit-identical to
+                                      oracle/sgr_oracle.cpp at ~1.4x the blend time.  Default (flag clear): exp(power) =
+                                      ex2.approx(power * log2 e) like upstream's own `exp()`; results agree with the oracle
+                                      to ~1e-6 (the north-star tolerance is 1e-4), index outputs that do not depend on
+                                      exp (radii, tile ranges, sorted lists) stay bit-exact */
 };
 
 /* Problem description shared by forward and backward.
@@ -67,6 +73,9 @@ typedef struct SgrProblem {
     const float* projmatrix;     /* [B,V,16] gs.py:90  (flat column-major P*W2C) */
     const float* bg;             /* [3]      gs.py:87 */
     uint64_t max_instances;      /* capacity of the instance arrays inside `state` (all renders together) */
+    uint64_t max_block_records;  /* capacity of the per-8x4-pixel-block record lists inside `state` (an instance appears
+                                    once in the list of every block of its tile that its extent touches: typically
+                                    1.3-2x max_instances, at most 8x); ignored with SGR_FLAG_SIMPLE_BLEND */
     int32_t renders_per_chunk;   /* 0 = library default; renders processed per launch set */
     int32_t flags;               /* SGR_FLAG_* */
     uint32_t max_tile_instances_hint; /* longest per-tile list seen for this kind of scene (SgrStatus of an earlier
@@ -87,28 +96,41 @@ typedef struct SgrForwardArgs {
     void* scratch;  uint64_t scratch_bytes;
     void* stream;
     /* Optional fused reconstruction loss: replaces gs.py:107 `clamp(0, 1)` followed by
-     * /root/reference/core/loss/whole_loss.py:126-130 `l1(pred * mask, gt * mask)` (mean reduction) and its autograd
-     * backward.  When loss_target != NULL the blend epilogue writes the CLAMPED colour, accumulates
+     * /root/reference/core/loss/whole_loss.py:130 `loss_l1 = l1(pred * mask, gt * mask)` (an UNREDUCED |x - y|) and its
+     * reduction `torch.sum(loss_l1) / loss_l1.shape[0]` (whole_loss.py:139; shape[0] = B*V) and autograd backward.
+     * When loss_target != NULL the blend epilogue writes the CLAMPED colour, accumulates
      * sum |clamp(c) * m - t * m| * loss_scale into *loss_out (device scalar, deterministic summation order) and
      * writes d loss / d colour (w.r.t. the unclamped colour: zero where the clamp saturated) to loss_dL_dcolor,
-     * which sgr_backward takes as its dL_dcolor.  Not available with SGR_FLAG_SIMPLE_BLEND. */
+     * which sgr_backward takes as its loss_dL_dcolor.  Not available with SGR_FLAG_SIMPLE_BLEND. */
     const float* loss_target;    /* [B,V,3,H,W] or NULL (no fused loss) */
     const float* loss_mask;      /* [B,V,1,H,W] or NULL (mask of ones) */
     float* loss_dL_dcolor;       /* [B,V,3,H,W] */
     float* loss_out;             /* device scalar */
-    float loss_scale;            /* e.g. 1 / (B*V*3*H*W) for the mean */
+    float loss_scale;            /* 1 / (B*V) for the reference's reduction; 1 / (B*V*3*H*W) for a mean */
+    /* Optional LPIPS feed: replaces `F.interpolate(pred * 2 - 1, (H/2, W/2), mode='bilinear',
+     * align_corners=False)` of whole_loss.py:132-136 for even H, W (a factor-2 bilinear resize is the 2x2 box mean):
+     * out_lpips_feed[b,v,c,y,x] = mean of clamp(colour, 0, 1) over the 2x2 pixels * 2 - 1.  Needs SGR_FLAG_CLAMP_COLOR
+     * or the fused loss (the clamped colour is what the reference resizes).  NULL = not wanted. */
+    float* out_lpips_feed;       /* [B,V,3,H/2,W/2] or NULL */
 } SgrForwardArgs;
 
 /* Replaces `_C.rasterize_gaussians_backward`.  Gradient slots follow the tuple returned by upstream's
  * autograd Function: means3D, means2D, colors_precomp, opacities, cov3D_precomp.
- * dL_ddepth / dL_dalpha may be NULL (treated as zeros — SIGMAN's case, gs.py:107-112 uses colour only).
+ * dL_ddepth / dL_dalpha may be NULL (treated as zeros - SIGMAN's case, gs.py:107-112 uses colour only).
+ * The gradient w.r.t. the (unclamped) colour is assembled per pixel from up to three sources:
+ *   dL_dcolor        the caller's gradient w.r.t. the colour image the forward returned (NULL = zeros);
+ *   dL_dlpips_feed   the caller's gradient w.r.t. out_lpips_feed (NULL = none): adds 0.5 * g[y/2, x/2];
+ *   loss_dL_dcolor   what the forward's fused loss wrote, times the device scalar *dL_dcolor_scale (NULL = none).
+ * With SGR_FLAG_CLAMP_COLOR (or the fused loss) the first two are gradients w.r.t. the CLAMPED image and are zeroed
+ * where the forward's clamp saturated (torch's clamp rule; the mask is kept in `state`) - gs.py:107 needs no
+ * separate clamp kernel or saved tensor.
  * Gradients of one subject are summed over its V views; dL_dmeans2D (optional, may be NULL) is per
  * render: [B,V,N,3] with z = 0, in NDC units like upstream's viewspace-point gradient. */
 typedef struct SgrBackwardArgs {
     SgrProblem p;
     const float* out_alpha;      /* [B,V,1,H,W] as produced by the forward */
     const int32_t* radii;        /* [B,V,N] as produced by the forward */
-    const float* dL_dcolor;      /* [B,V,3,H,W] */
+    const float* dL_dcolor;      /* [B,V,3,H,W] or NULL */
     const float* dL_ddepth;      /* [B,V,1,H,W] or NULL */
     const float* dL_dalpha;      /* [B,V,1,H,W] or NULL */
     float* dL_dmeans3D;          /* [B,N,3] */
@@ -119,8 +141,12 @@ typedef struct SgrBackwardArgs {
     void* state;    uint64_t state_bytes;
     void* scratch;  uint64_t scratch_bytes;
     void* stream;
-    const float* dL_dcolor_scale; /* device scalar multiplying dL_dcolor (the upstream gradient of a fused loss), or
-                                     NULL (= 1).  Not available with SGR_FLAG_SIMPLE_BLEND. */
+    const float* loss_dL_dcolor;  /* [B,V,3,H,W] written by the forward's fused loss, or NULL */
+    const float* dL_dcolor_scale; /* device scalar multiplying loss_dL_dcolor (the upstream gradient of the fused loss),
+                                     or NULL (= 1) */
+    const float* dL_dlpips_feed;  /* [B,V,3,H/2,W/2] or NULL */
+    int32_t fused_clamp;          /* != 0: the forward ran with a fused loss (its colour output is clamped) */
+    int32_t reserved;
 } SgrBackwardArgs;
 
 /* Device-side status of the last forward that used `state` (read with sgr_read_status).  It is stored in the first
@@ -129,10 +155,13 @@ typedef struct SgrBackwardArgs {
 typedef struct SgrStatus {
     uint64_t instances_required;   /* total (Gaussian, tile) instances of all renders */
     uint64_t instances_capacity;   /* max_instances the forward ran with */
-    uint32_t overflow;             /* != 0: some renders were dropped (background only) */
+    uint32_t overflow;             /* != 0: some renders / tiles were dropped (background only);
+                                      bit 0: max_instances too small, bit 1: max_block_records too small */
     uint32_t max_tile_instances;   /* longest per-tile list */
     uint32_t nonempty_tiles;       /* tiles with at least one instance (all renders) */
     uint32_t reserved;
+    uint64_t block_records_required; /* block records of all renders (0 with SGR_FLAG_SIMPLE_BLEND) */
+    uint64_t block_records_capacity; /* max_block_records the forward ran with */
 } SgrStatus;
 
 int sgr_abi_version(void);
@@ -140,7 +169,8 @@ const char* sgr_last_error(void);
 
 /* Buffer sizes for a problem shape (bytes; 256-byte aligned). */
 uint64_t sgr_state_bytes(int32_t num_subjects, int32_t views_per_subject, int32_t num_gaussians,
-                         int32_t image_height, int32_t image_width, uint64_t max_instances);
+                         int32_t image_height, int32_t image_width, uint64_t max_instances,
+                         uint64_t max_block_records, int32_t flags);
 uint64_t sgr_scratch_bytes(int32_t num_subjects, int32_t views_per_subject, int32_t num_gaussians,
                            int32_t image_height, int32_t image_width, uint64_t max_instances,
                            int32_t renders_per_chunk);
@@ -217,7 +247,8 @@ uint64_t sgr_launch_count(void);
  *                                  (low 32 bits; load-balance diagnostics; needs SGR_FLAG_TILE_TIMING)
  * The shape arguments must be those of the forward that filled `state`. */
 int sgr_debug_copy_state(const void* state, int32_t num_subjects, int32_t views_per_subject, int32_t num_gaussians,
-                         int32_t image_height, int32_t image_width, uint64_t max_instances, int32_t render,
+                         int32_t image_height, int32_t image_width, uint64_t max_instances,
+                         uint64_t max_block_records, int32_t flags, int32_t render,
                          uint32_t* tile_ranges, uint32_t* n_contrib, uint32_t* point_list,
                          uint64_t point_list_capacity, uint32_t* tile_timing, void* stream);
 

@@ -89,6 +89,13 @@ def set_num_threads(n: int) -> None:
     lib().oracle_set_num_threads(ctypes.c_int(int(n)))
 
 
+def set_exp_mode(mode: str) -> None:
+    """"spec": the fixed IEEE sequence exp_spec (default; what SGR_FLAG_EXACT_EXP reproduces bit for bit);
+    "libm": the C library's expf — an independent exponential, used to measure how many alpha >= 1/255 /
+    T >= 1e-4 decisions depend on the last bits of exp()."""
+    lib().oracle_set_exp_mode(ctypes.c_int({"spec": 0, "libm": 1}[mode]))
+
+
 @dataclass
 class ForwardResult:
     color: np.ndarray          # [3,H,W]

@@ -55,7 +55,13 @@ constexpr int kBlockY = 16;
 // degree-7 Taylor polynomial of e^r in Horner form with fma; scale by 2^n through the exponent
 // field.  Inputs below -87 return 0 (the result would be subnormal; callers reject it anyway),
 // inputs above 88 return +inf.  NaN propagates.
+// g_exp_mode = 1 swaps the fp32 exponential for the C library's expf (correctly rounded in glibc): the honest
+// statement of how far the fixed exp_spec sequence — and the kernels' SFU exponential — sit from "the" exponential
+// that an upstream build evaluates (tests/test_oracle.py, tests/test_gpu_fast_exp.py count the pixels whose
+// alpha >= 1/255 / T >= 1e-4 branch flips).
+int g_exp_mode = 0;
 inline float exp_spec(float x) {
+    if (g_exp_mode == 1) return std::exp(x);
     if (x != x) return x;
     if (x < -87.0f) return 0.0f;
     if (x > 88.0f) return INFINITY;
@@ -380,9 +386,14 @@ void blend_backward(int N, int H, int W, const Geom<R>& g, const Binning& b, con
                 }
         }
     }
-    for (int t = 0; t < nthreads; ++t) {
-        if (priv[t].empty()) continue;
-        for (size_t k = 0; k < acc.size(); ++k) acc[k] += priv[t][k];
+    // fixed-order (thread 0, 1, ...) sum of the per-thread accumulators, parallel over the entries
+    const long long nacc = static_cast<long long>(acc.size());
+#pragma omp parallel for schedule(static)
+    for (long long k = 0; k < nacc; ++k) {
+        double sum = 0.0;
+        for (int t = 0; t < nthreads; ++t)
+            if (!priv[t].empty()) sum += priv[t][size_t(k)];
+        acc[size_t(k)] = sum;
     }
 }
 
@@ -621,6 +632,9 @@ struct OracleCtxF32 { Ctx<float> c; };
 struct OracleCtxF64 { Ctx<double> c; };
 
 float oracle_expf(float x) { return exp_spec(x); }
+// 0 = exp_spec (the bit-exact specification shared with the kernels' SGR_FLAG_EXACT_EXP mode), 1 = libm expf
+void oracle_set_exp_mode(int mode) { g_exp_mode = mode; }
+int oracle_get_exp_mode(void) { return g_exp_mode; }
 int oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

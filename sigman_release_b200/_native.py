@@ -11,7 +11,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SGR_LIB_PATH") or os.path.join(_HERE, "libsgr_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 SGR_OK = 0
 SGR_E_INVALID_ARGUMENT = -1
@@ -23,6 +23,7 @@ FLAG_SIMPLE_BLEND = 1
 FLAG_CLAMP_COLOR = 2
 FLAG_FORWARD_ONLY = 4
 FLAG_TILE_TIMING = 8
+FLAG_EXACT_EXP = 16
 
 _vp = ctypes.c_void_p
 
@@ -44,6 +45,7 @@ class SgrProblem(ctypes.Structure):
         ("projmatrix", _vp),
         ("bg", _vp),
         ("max_instances", ctypes.c_uint64),
+        ("max_block_records", ctypes.c_uint64),
         ("renders_per_chunk", ctypes.c_int32),
         ("flags", ctypes.c_int32),
         ("max_tile_instances_hint", ctypes.c_uint32),
@@ -68,6 +70,7 @@ class SgrForwardArgs(ctypes.Structure):
         ("loss_dL_dcolor", _vp),
         ("loss_out", _vp),
         ("loss_scale", ctypes.c_float),
+        ("out_lpips_feed", _vp),
     ]
 
 
@@ -89,7 +92,11 @@ class SgrBackwardArgs(ctypes.Structure):
         ("scratch", _vp),
         ("scratch_bytes", ctypes.c_uint64),
         ("stream", _vp),
+        ("loss_dL_dcolor", _vp),
         ("dL_dcolor_scale", _vp),
+        ("dL_dlpips_feed", _vp),
+        ("fused_clamp", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
 
@@ -101,6 +108,8 @@ class SgrStatus(ctypes.Structure):
         ("max_tile_instances", ctypes.c_uint32),
         ("nonempty_tiles", ctypes.c_uint32),
         ("reserved", ctypes.c_uint32),
+        ("block_records_required", ctypes.c_uint64),
+        ("block_records_capacity", ctypes.c_uint64),
     ]
 
 
@@ -109,7 +118,7 @@ _i32, _u64, _f32 = ctypes.c_int32, ctypes.c_uint64, ctypes.c_float
 SYMBOLS = {
     "sgr_abi_version": (ctypes.c_int, []),
     "sgr_last_error": (ctypes.c_char_p, []),
-    "sgr_state_bytes": (_u64, [_i32, _i32, _i32, _i32, _i32, _u64]),
+    "sgr_state_bytes": (_u64, [_i32, _i32, _i32, _i32, _i32, _u64, _u64, _i32]),
     "sgr_scratch_bytes": (_u64, [_i32, _i32, _i32, _i32, _i32, _u64, _i32]),
     "sgr_forward": (ctypes.c_int, [ctypes.POINTER(SgrForwardArgs)]),
     "sgr_backward": (ctypes.c_int, [ctypes.POINTER(SgrBackwardArgs)]),
@@ -128,7 +137,8 @@ SYMBOLS = {
     "sgr_profile_enable": (None, [ctypes.c_int]),
     "sgr_profile_collect": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint32)]),
     "sgr_launch_count": (_u64, []),
-    "sgr_debug_copy_state": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _u64, _i32, _vp, _vp, _vp, _u64, _vp, _vp]),
+    "sgr_debug_copy_state": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _u64, _u64, _i32, _i32, _vp, _vp, _vp, _u64,
+                                            _vp, _vp]),
 }
 
 STAGES = ("preprocess", "plan", "scatter", "sort", "blend_forward", "blend_backward", "preprocess_backward")

@@ -61,6 +61,12 @@ struct StageTimer {
         SGR_CUDA(expr);                         \
     } while (0)
 
+int chunk_size(const SgrProblem& p) {
+    const long long R = (long long)p.num_subjects * p.views_per_subject;
+    long long rpc = p.renders_per_chunk > 0 ? p.renders_per_chunk : kDefaultRendersPerChunk;
+    return int(rpc < R ? rpc : R);
+}
+
 int check_problem(const SgrProblem& p) {
     if (p.num_subjects <= 0 || p.views_per_subject <= 0) return fail(SGR_E_INVALID_ARGUMENT, "num_subjects and views_per_subject must be positive");
     if (p.num_gaussians < 0) return fail(SGR_E_INVALID_ARGUMENT, "num_gaussians must be >= 0");
@@ -71,19 +77,22 @@ int check_problem(const SgrProblem& p) {
     if (!p.viewmatrix || !p.projmatrix || !p.bg) return fail(SGR_E_INVALID_ARGUMENT, "null camera / background pointer");
     if (p.renders_per_chunk < 0) return fail(SGR_E_INVALID_ARGUMENT, "renders_per_chunk must be >= 0");
     if (p.max_instances >= (1ull << 32)) return fail(SGR_E_INVALID_ARGUMENT, "max_instances must be below 2^32");
+    if (p.max_block_records >= (1ull << 32)) return fail(SGR_E_INVALID_ARGUMENT, "max_block_records must be below 2^32");
+    // plan_kernel scans (instances << 24 | empty tiles) in one 64-bit word: a chunk must hold fewer than 2^24 tiles
+    const long long chunk_tiles = (long long)chunk_size(p) * tiles_x(p.image_width) * tiles_y(p.image_height);
+    if (chunk_tiles >= (1ll << 24))
+        return fail(SGR_E_INVALID_ARGUMENT, "renders_per_chunk * tiles per render must stay below 2^24 (got %lld); lower renders_per_chunk", chunk_tiles);
     return SGR_OK;
 }
 
-int chunk_size(const SgrProblem& p) {
-    const long long R = (long long)p.num_subjects * p.views_per_subject;
-    long long rpc = p.renders_per_chunk > 0 ? p.renders_per_chunk : kDefaultRendersPerChunk;
-    return int(rpc < R ? rpc : R);
+StateLayout state_layout(const SgrProblem& p) {
+    return make_state_layout(p.num_subjects, p.views_per_subject, p.num_gaussians, p.image_height, p.image_width,
+                             p.max_instances, p.max_block_records, (p.flags & SGR_FLAG_SIMPLE_BLEND) != 0);
 }
 
 void fill_ctx(ChunkCtx& c, const SgrProblem& p, void* state, void* scratch, cudaStream_t stream) {
     const int rpc = chunk_size(p);
-    const StateLayout S = make_state_layout(p.num_subjects, p.views_per_subject, p.num_gaussians, p.image_height,
-                                            p.image_width, p.max_instances);
+    const StateLayout S = state_layout(p);
     const ScratchLayout X = make_scratch_layout(p.num_subjects, p.views_per_subject, p.num_gaussians, p.image_height,
                                                 p.image_width, p.max_instances, rpc);
     char* s = static_cast<char*>(state);
@@ -102,12 +111,23 @@ void fill_ctx(ChunkCtx& c, const SgrProblem& p, void* state, void* scratch, cuda
     c.rec0 = reinterpret_cast<float4*>(s + S.rec0);
     c.rec1 = reinterpret_cast<float4*>(s + S.rec1);
     c.rec2 = reinterpret_cast<float4*>(s + S.rec2);
+    c.clamp_mask = reinterpret_cast<unsigned char*>(s + S.clamp_mask);
+    c.blk_off = reinterpret_cast<unsigned int*>(s + S.blk_off);
+    c.blk_cnt = reinterpret_cast<unsigned int*>(s + S.blk_cnt);
+    c.blk_eff = reinterpret_cast<unsigned int*>(s + S.blk_eff);
+    c.brec0 = reinterpret_cast<float4*>(s + S.brec0);
+    c.brec1 = reinterpret_cast<float4*>(s + S.brec1);
+    c.brec2 = reinterpret_cast<float4*>(s + S.brec2);
+    c.bids = reinterpret_cast<unsigned int*>(s + S.bids);
+    c.blk_capacity = (p.flags & SGR_FLAG_SIMPLE_BLEND) ? 0ull : p.max_block_records;
     c.ck0 = reinterpret_cast<float4*>(s + S.ck0);
     c.ck1 = reinterpret_cast<float*>(s + S.ck1);
     c.plan = reinterpret_cast<ChunkPlan*>(s + S.plan);
-    c.work_seg = reinterpret_cast<uint2*>(s + S.work_seg);
+    c.bwd_items = reinterpret_cast<uint2*>(s + S.bwd_items);
+    c.bwd_items_stride = S.bwd_items_stride;
     c.chunk_index = 0;
     c.keys = reinterpret_cast<unsigned long long*>(x + X.keys);
+    c.keys_tmp = reinterpret_cast<unsigned long long*>(x + X.keys_tmp);
     c.g0 = reinterpret_cast<float4*>(x + X.g0);
     c.g1 = reinterpret_cast<float4*>(x + X.g1);
     c.g2 = reinterpret_cast<float4*>(x + X.g2);
@@ -119,7 +139,6 @@ void fill_ctx(ChunkCtx& c, const SgrProblem& p, void* state, void* scratch, cuda
     c.loss_part = reinterpret_cast<float*>(x + X.loss_part);
     c.accum = reinterpret_cast<float*>(x + X.accum);
     c.loss_target = nullptr; c.loss_mask = nullptr; c.loss_dL_dcolor = nullptr; c.loss_scale = 0.0f;
-    c.dL_scale = nullptr;
     c.stream = stream;
 }
 
@@ -155,9 +174,10 @@ void sgr_count_launches_(unsigned int n) { g_launches += n; }
 int sgr_abi_version(void) { return SGR_ABI_VERSION; }
 const char* sgr_last_error(void) { return g_err; }
 
-uint64_t sgr_state_bytes(int32_t B, int32_t V, int32_t N, int32_t H, int32_t W, uint64_t max_instances) {
+uint64_t sgr_state_bytes(int32_t B, int32_t V, int32_t N, int32_t H, int32_t W, uint64_t max_instances,
+                         uint64_t max_block_records, int32_t flags) {
     if (B <= 0 || V <= 0 || N < 0 || H <= 0 || W <= 0) return 0;
-    return make_state_layout(B, V, N, H, W, max_instances).total;
+    return make_state_layout(B, V, N, H, W, max_instances, max_block_records, (flags & SGR_FLAG_SIMPLE_BLEND) != 0).total;
 }
 
 uint64_t sgr_scratch_bytes(int32_t B, int32_t V, int32_t N, int32_t H, int32_t W, uint64_t max_instances,
@@ -181,9 +201,13 @@ int sgr_forward(const SgrForwardArgs* args) {
         return fail(SGR_E_INVALID_ARGUMENT, "fused loss needs loss_dL_dcolor and loss_out");
     if (fused_loss && (p.flags & SGR_FLAG_SIMPLE_BLEND))
         return fail(SGR_E_INVALID_ARGUMENT, "the fused loss is not available with SGR_FLAG_SIMPLE_BLEND");
+    if (args->out_lpips_feed) {
+        if (p.flags & SGR_FLAG_SIMPLE_BLEND) return fail(SGR_E_INVALID_ARGUMENT, "out_lpips_feed is not available with SGR_FLAG_SIMPLE_BLEND");
+        if ((p.image_height | p.image_width) & 1) return fail(SGR_E_INVALID_ARGUMENT, "out_lpips_feed needs even image_height / image_width");
+        if (!fused_loss && !(p.flags & SGR_FLAG_CLAMP_COLOR)) return fail(SGR_E_INVALID_ARGUMENT, "out_lpips_feed needs SGR_FLAG_CLAMP_COLOR or the fused loss (the reference resizes the clamped image)");
+    }
     const int rpc = chunk_size(p);
-    const uint64_t need_state = make_state_layout(p.num_subjects, p.views_per_subject, p.num_gaussians, p.image_height,
-                                                  p.image_width, p.max_instances).total;
+    const uint64_t need_state = state_layout(p).total;
     const uint64_t need_scratch = make_scratch_layout(p.num_subjects, p.views_per_subject, p.num_gaussians,
                                                       p.image_height, p.image_width, p.max_instances, rpc).total;
     if (args->state_bytes < need_state)
@@ -217,7 +241,7 @@ int sgr_forward(const SgrForwardArgs* args) {
         if (p.flags & SGR_FLAG_SIMPLE_BLEND) {
             SGR_STAGE(kStBlendFwd, launch_blend_forward_simple(c, args->out_color, args->out_depth, args->out_alpha));
         } else {
-            SGR_STAGE(kStBlendFwd, launch_blend_forward(c, args->out_color, args->out_depth, args->out_alpha));
+            SGR_STAGE(kStBlendFwd, launch_blend_forward(c, args->out_color, args->out_depth, args->out_alpha, args->out_lpips_feed));
             if (fused_loss) {
                 SGR_CUDA(launch_loss_reduce(c, args->loss_out));
                 g_launches += 1;
@@ -231,14 +255,15 @@ int sgr_backward(const SgrBackwardArgs* args) {
     if (!args) return fail(SGR_E_INVALID_ARGUMENT, "null args");
     const SgrProblem& p = args->p;
     if (int rc = check_problem(p)) return rc;
-    if (!args->out_alpha || !args->dL_dcolor || (p.num_gaussians > 0 && !args->radii))
-        return fail(SGR_E_INVALID_ARGUMENT, "null forward-result / gradient input pointer");
+    if (!args->out_alpha || (p.num_gaussians > 0 && !args->radii))
+        return fail(SGR_E_INVALID_ARGUMENT, "null forward-result pointer");
+    if (!args->dL_dcolor && !args->loss_dL_dcolor && !args->dL_dlpips_feed && !args->dL_ddepth && !args->dL_dalpha)
+        return fail(SGR_E_INVALID_ARGUMENT, "no image-space gradient given (dL_dcolor, loss_dL_dcolor, dL_dlpips_feed, dL_ddepth, dL_dalpha all NULL)");
     if (p.num_gaussians > 0 && (!args->dL_dmeans3D || !args->dL_dcov3D || !args->dL_dcolors || !args->dL_dopacities))
         return fail(SGR_E_INVALID_ARGUMENT, "null gradient output pointer");
     if (!args->state || !args->scratch) return fail(SGR_E_INVALID_ARGUMENT, "null state / scratch");
     const int rpc = chunk_size(p);
-    const uint64_t need_state = make_state_layout(p.num_subjects, p.views_per_subject, p.num_gaussians, p.image_height,
-                                                  p.image_width, p.max_instances).total;
+    const uint64_t need_state = state_layout(p).total;
     const uint64_t need_scratch = make_scratch_layout(p.num_subjects, p.views_per_subject, p.num_gaussians,
                                                       p.image_height, p.image_width, p.max_instances, rpc).total;
     if (args->state_bytes < need_state)
@@ -246,13 +271,14 @@ int sgr_backward(const SgrBackwardArgs* args) {
     if (args->scratch_bytes < need_scratch)
         return fail(SGR_E_BUFFER_TOO_SMALL, "scratch buffer too small: %llu < %llu bytes", (unsigned long long)args->scratch_bytes, (unsigned long long)need_scratch);
     if (p.num_gaussians == 0) return SGR_OK;
-    if (args->dL_dcolor_scale && (p.flags & SGR_FLAG_SIMPLE_BLEND))
-        return fail(SGR_E_INVALID_ARGUMENT, "dL_dcolor_scale is not available with SGR_FLAG_SIMPLE_BLEND");
+    if ((p.flags & SGR_FLAG_SIMPLE_BLEND) && (!args->dL_dcolor || args->loss_dL_dcolor || args->dL_dlpips_feed || args->fused_clamp))
+        return fail(SGR_E_INVALID_ARGUMENT, "SGR_FLAG_SIMPLE_BLEND takes dL_dcolor only (no fused loss / LPIPS feed gradients)");
+    if (args->dL_dlpips_feed && ((p.image_height | p.image_width) & 1))
+        return fail(SGR_E_INVALID_ARGUMENT, "dL_dlpips_feed needs even image_height / image_width");
 
     cudaStream_t stream = static_cast<cudaStream_t>(args->stream);
     ChunkCtx c;
     fill_ctx(c, p, args->state, args->scratch, stream);
-    c.dL_scale = args->dL_dcolor_scale;
     const int R = p.num_subjects * p.views_per_subject;
     const size_t BN = size_t(p.num_subjects) * p.num_gaussians;
     (void)BN;   // the per-subject gradients are stored (not accumulated) by the chunk holding the subject's first view
@@ -266,9 +292,9 @@ int sgr_backward(const SgrBackwardArgs* args) {
         if (p.flags & SGR_FLAG_SIMPLE_BLEND) {
             SGR_STAGE(kStBlendBwd, launch_blend_backward_simple(c, args->out_alpha, args->dL_dcolor, args->dL_ddepth, args->dL_dalpha));
         } else {
-            // the (tile, segment) work list was planned by the forward; only its queue head is reset here
-            SGR_CUDA(cudaMemsetAsync(&c.plan->seg_cursor, 0, 4, stream));
-            SGR_STAGE(kStBlendBwd, launch_blend_backward(c, args->out_alpha, args->dL_dcolor, args->dL_ddepth, args->dL_dalpha));
+            // the (block, segment) work lists were filled by the forward; only the queue head is reset here
+            SGR_CUDA(cudaMemsetAsync(&c.plan->cursor, 0, 4, stream));
+            SGR_STAGE(kStBlendBwd, launch_blend_backward(c, *args));
         }
         SGR_STAGE(kStPreBwd, launch_preprocess_backward(c, *args));
     }
@@ -281,8 +307,10 @@ int sgr_read_status(const void* state, void* stream, SgrStatus* host_status) {
     SGR_CUDA(cudaMemcpyAsync(host_status, state, sizeof(SgrStatus), cudaMemcpyDeviceToHost, s));
     SGR_CUDA(cudaStreamSynchronize(s));
     if (host_status->overflow)
-        return fail(SGR_E_INSTANCE_OVERFLOW, "instance overflow: %llu (Gaussian, tile) instances needed, capacity %llu",
-                    (unsigned long long)host_status->instances_required, (unsigned long long)host_status->instances_capacity);
+        return fail(SGR_E_INSTANCE_OVERFLOW, "instance overflow: %llu (Gaussian, tile) instances needed, capacity %llu; "
+                    "%llu block records needed, capacity %llu",
+                    (unsigned long long)host_status->instances_required, (unsigned long long)host_status->instances_capacity,
+                    (unsigned long long)host_status->block_records_required, (unsigned long long)host_status->block_records_capacity);
     return SGR_OK;
 }
 
@@ -372,11 +400,12 @@ int sgr_sh_colors_backward(const float* means3D, const float* shs, const float* 
 }
 
 int sgr_debug_copy_state(const void* state, int32_t B, int32_t V, int32_t N, int32_t H, int32_t W,
-                         uint64_t max_instances, int32_t render, uint32_t* tile_ranges, uint32_t* n_contrib,
+                         uint64_t max_instances, uint64_t max_block_records, int32_t flags, int32_t render,
+                         uint32_t* tile_ranges, uint32_t* n_contrib,
                          uint32_t* point_list, uint64_t point_list_capacity, uint32_t* tile_timing, void* stream) {
     if (!state || B <= 0 || V <= 0 || N < 0 || H <= 0 || W <= 0 || render < 0 || render >= B * V)
         return fail(SGR_E_INVALID_ARGUMENT, "bad debug_copy_state arguments");
-    const StateLayout S = make_state_layout(B, V, N, H, W, max_instances);
+    const StateLayout S = make_state_layout(B, V, N, H, W, max_instances, max_block_records, (flags & SGR_FLAG_SIMPLE_BLEND) != 0);
     const char* s = static_cast<const char*>(state);
     const int T = tiles_x(W) * tiles_y(H);
     const unsigned int* off = reinterpret_cast<const unsigned int*>(s + S.tile_off) + size_t(render) * T;

@@ -23,13 +23,14 @@ namespace {
 //   2. + 3. ONE work list of the non-empty tiles by descending size class: the forward blend kernel walks it longest-
 //      processing-time first, the sort kernels split it at n_big (tiles with >= kSmallSortCap instances come first);
 //      plus the list of empty tiles (background only);
-//   4. backward work list (kept in `state`): every tile list cut into segments of kSegment records, items
-//      (tile, segment) by descending size class of the segment length.
+//   4. the chunk's slice of the backward item lists (kept in `state`; the items themselves are pushed by the forward
+//      blend, which knows how many records of every block segment really blended).
 struct PlanArgs {
     int n;                        // tiles in the chunk (renders * tiles per render)
     int first_chunk;              // != 0: initialise the status header
     unsigned long long capacity;
-    unsigned int seg_region;      // first work_seg slot this chunk may use, before adding instances / kSegment
+    unsigned int item_region;     // first backward-item slot this chunk may use, before adding block records / kSegB
+    unsigned long long blk_capacity;
     unsigned int* tile_cnt;       // chunk slice
     unsigned int* tile_off;       // chunk slice
     unsigned int* cursor;         // chunk scatter cursors (zeroed here)
@@ -37,7 +38,6 @@ struct PlanArgs {
     WorkCounts* wc;
     ChunkPlan* plan;
     unsigned int *work_blend, *work_empty;
-    uint2* work_seg;
 };
 
 constexpr int kScanThreads = 1024;
@@ -55,9 +55,9 @@ __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
     // most tiles of a human render are empty, so their list positions come from the scan, not from atomics.
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_total;
-    __shared__ unsigned int s_max, s_nonempty, s_dropped, s_segbase;
+    __shared__ unsigned int s_max, s_nonempty, s_dropped;
     __shared__ unsigned long long s_base;
-    __shared__ unsigned int s_hist[kSizeClasses], s_start[kSizeClasses], s_hseg[kSizeClasses], s_sseg[kSizeClasses];
+    __shared__ unsigned int s_hist[kSizeClasses], s_start[kSizeClasses];
     const int t = threadIdx.x;
     const int ipt = (a.n + kScanThreads - 1) / kScanThreads;
     const int lo = min(a.n, t * ipt), hi = min(a.n, lo + ipt);
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
         mx = max(mx, c); ne += (c != 0);
     }
     if (t == 0) { s_max = 0; s_nonempty = 0; }
-    if (t < kSizeClasses) { s_hist[t] = 0; s_hseg[t] = 0; }
+    if (t < kSizeClasses) s_hist[t] = 0;
     // block exclusive scan of `sum`
     unsigned long long inc = sum;
 #pragma unroll
@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
             a.header->inst_required = 0; a.header->capacity = a.capacity; a.header->overflow = 0;
             a.header->max_tile_instances = 0; a.header->nonempty_tiles = 0; a.header->pad = 0;
             a.header->inst_cursor = 0;
+            a.header->blk_required = 0; a.header->blk_capacity = a.blk_capacity;
         }
         const unsigned long long base = a.header->inst_cursor;
         const unsigned long long total = s_total >> 24;
@@ -105,12 +106,10 @@ __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
         const bool fits = base + total <= a.header->capacity;
         s_dropped = fits ? 0u : 1u;
         s_base = base;
-        s_segbase = a.seg_region + static_cast<unsigned int>(base / kSegment);
-        if (fits) a.header->inst_cursor = base + total; else a.header->overflow = 1u;
+        if (fits) a.header->inst_cursor = base + total; else a.header->overflow |= 1u;
     }
     __syncthreads();
     const bool dropped = s_dropped != 0;
-    const int full_class = size_class(kSegment);
     unsigned int run = static_cast<unsigned int>(s_base) + excl;
     for (int k = lo; k < hi; ++k) {
         unsigned int c = a.tile_cnt[k];
@@ -123,12 +122,7 @@ __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
             a.tile_off[k] = run;
             run += c;
         }
-        if (c != 0) {
-            atomicAdd(&s_hist[size_class(c)], 1u);
-            const unsigned int nfull = c / kSegment, rem = c - nfull * kSegment;
-            if (nfull) atomicAdd(&s_hseg[full_class], nfull);
-            if (rem) atomicAdd(&s_hseg[size_class(rem)], 1u);
-        }
+        if (c != 0) atomicAdd(&s_hist[size_class(c)], 1u);
     }
     atomicMax(&s_max, mx);
     atomicAdd(&s_nonempty, ne);
@@ -140,11 +134,8 @@ __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
             a.header->max_tile_instances = max(a.header->max_tile_instances, s_max);
             a.header->nonempty_tiles += s_nonempty;
         }
-        unsigned int r1 = 0, r2 = 0;
-        for (int c = kSizeClasses - 1; c >= 1; --c) {
-            s_start[c] = r1; r1 += s_hist[c];
-            s_sseg[c] = r2; r2 += s_hseg[c];
-        }
+        unsigned int r1 = 0;
+        for (int c = kSizeClasses - 1; c >= 1; --c) { s_start[c] = r1; r1 += s_hist[c]; }
         s_start[0] = 0;
         a.wc->n_big = s_start[size_class(kSmallSortCap) - 1];    // tiles of the classes >= class(kSmallSortCap)
         a.wc->sort_cursor = 0;
@@ -152,22 +143,18 @@ __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
         a.wc->n_empty = dropped ? unsigned(a.n) : static_cast<unsigned int>(s_total & 0xffffffull);
         a.wc->blend_cursor = 0;
         a.wc->empty_cursor = 0;
-        a.plan->n_seg = r2;
-        a.plan->seg_base = s_segbase;
-        a.plan->seg_cursor = 0;
+        // the block-record cursor is final for all earlier chunks here (their sorts precede this kernel in the stream)
+#pragma unroll
+        for (int c = 0; c < kBwdClasses; ++c) a.plan->n_items[c] = 0;
+        const unsigned long long used = min(a.header->blk_required, a.header->blk_capacity);   // records really stored
+        a.plan->item_base = a.item_region + static_cast<unsigned int>(used / kSegB);
+        a.plan->cursor = 0;
     }
     __syncthreads();
-    uint2* work_seg = a.work_seg + s_segbase;
     for (int k = lo; k < hi; ++k) {
         const unsigned int c = dropped ? 0u : a.tile_cnt[k];
         if (c == 0) { a.work_empty[dropped ? unsigned(k) : empty_pos++] = k; continue; }
         a.work_blend[atomicAdd(&s_start[size_class(c)], 1u)] = k;
-        const unsigned int nfull = c / kSegment, rem = c - nfull * kSegment;
-        if (nfull) {
-            const unsigned int sp = atomicAdd(&s_sseg[full_class], nfull);
-            for (unsigned int sgi = 0; sgi < nfull; ++sgi) work_seg[sp + sgi] = make_uint2(unsigned(k), sgi);
-        }
-        if (rem) work_seg[atomicAdd(&s_sseg[size_class(rem)], 1u)] = make_uint2(unsigned(k), nfull);
     }
 }
 
@@ -177,12 +164,20 @@ struct SortArgs {
     const unsigned int* tile_off;    // global arrays
     const unsigned int* tile_cnt;
     const unsigned long long* keys;
+    unsigned long long* keys_tmp;    // second key buffer [cap]: bucket-ordered keys of lists beyond the shared memory
     unsigned int* sorted_ids;
-    float4 *rec0, *rec1, *rec2;
+    float4 *rec0, *rec1, *rec2;      // tile-level records (simple != 0 only)
     const float4 *g0, *g1, *g2;
     const unsigned int* work;        // chunk-local indices of the non-empty tiles, longest list first
     WorkCounts* wc;                  // n_big: the first n_big tiles go to the big kernel; sort_cursor: small queue
     unsigned int big_smem_keys;      // key capacity of the big kernel's shared-memory buffer
+    int simple;                      // SGR_FLAG_SIMPLE_BLEND: emit tile-level records instead of block lists
+    // block lists (simple == 0)
+    StateHeader* header;
+    unsigned int *blk_off, *blk_cnt;
+    float4 *brec0, *brec1, *brec2;
+    unsigned int* bids;
+    unsigned long long blk_capacity;
 };
 
 template <int THREADS>
@@ -249,14 +244,14 @@ __device__ __forceinline__ void block_exclusive_scan(unsigned int* hist, unsigne
     __syncthreads();
 }
 
-// Sorts the n keys of one tile, writes ids + gathered records.  kb: n-element key buffer (shared or global).
+// Sorts the n keys of one tile: writes the depth-ordered ids (upstream's point_list) and then either the tile's
+// gathered 48-byte records (simple) or the eight per-block record lists.  kb: n-element key buffer (shared or global).
 // KPT > 0: the tile has at most THREADS * KPT keys and every thread keeps its keys in registers, so the three passes
 // over the unsorted keys (range, histogram, scatter) cost ONE exposed global-memory latency instead of three (the
 // per-tile sort is a latency chain, not a bandwidth problem); KPT == 0 re-reads the keys from global memory.
 template <int THREADS, int NB, int KPT>
 __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local, unsigned long long* kb,
-                                              bool kb_in_rec0, unsigned int* hist, unsigned int* s_warp,
-                                              unsigned long long* s_red) {
+                                              unsigned int* hist, unsigned int* s_warp, unsigned long long* s_red) {
     const int t = threadIdx.x;
     const int rl = tile_local / a.num_tiles;
     const size_t tg = size_t(a.render_base) * a.num_tiles + tile_local;      // global tile index
@@ -318,9 +313,9 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
         }
     }
     __syncthreads();
-    // 4. exact rank inside the bucket -> final position; the owner of an element immediately gathers its 48-byte
-    //    record into depth order (the stream the blend kernels read).  Unrolled so that several independent
-    //    key -> record -> store chains are in flight per thread (the step is L2-latency bound).
+    // 4. exact rank inside the bucket -> final position of the id (upstream's point_list).  Unrolled so that several
+    //    independent chains are in flight per thread (the step is L2-latency bound).  With `simple` the owner of an
+    //    element also gathers its 48-byte record into depth order (tile-level stream of the upstream-shaped kernels).
     unsigned int* ids = a.sorted_ids + off;
     const size_t gb = size_t(rl) * a.N;
     const int tile = tile_local - rl * a.num_tiles;
@@ -335,31 +330,109 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
         for (unsigned int j = s; j < e; ++j) cnt += (kb[j] < key) ? 1u : 0u;
         const unsigned int id = static_cast<unsigned int>(key & 0xffffffffull);
         const size_t pos = off + s + cnt;
-        float4 v0 = __ldg(a.g0 + gb + id);
-        const float4 v1 = __ldg(a.g1 + gb + id);
-        const float4 v2 = __ldg(a.g2 + gb + id);
-        v0.z = __uint_as_float(quarter_mask(v0.x, v0.y, v0.z, X0, Y0));   // the instance's cull mask for this tile
         a.sorted_ids[pos] = id;
-        if (!kb_in_rec0) {
+        if (a.simple) {
+            float4 v0 = __ldg(a.g0 + gb + id);
+            v0.z = __uint_as_float(quarter_mask(v0.x, v0.y, v0.z, X0, Y0));
             a.rec0[pos] = v0;
-            a.rec1[pos] = v1;
-            a.rec2[pos] = v2;
+            a.rec1[pos] = __ldg(a.g1 + gb + id);
+            a.rec2[pos] = __ldg(a.g2 + gb + id);
         }
     }
     __syncthreads();
-    if (kb_in_rec0) {
-        // the key buffer lives in the tile's own rec0 segment (lists beyond the shared-memory capacity): records are
-        // gathered in a second sweep once no thread reads the keys any more
-        for (unsigned int q = t; q < n; q += THREADS) {
-            const unsigned int id = ids[q];
-            float4 v0 = __ldg(a.g0 + gb + id);
-            v0.z = __uint_as_float(quarter_mask(v0.x, v0.y, v0.z, X0, Y0));
-            a.rec0[off + q] = v0;
-            a.rec1[off + q] = __ldg(a.g1 + gb + id);
-            a.rec2[off + q] = __ldg(a.g2 + gb + id);
+    if (a.simple) return;
+
+    // 5. block lists.  Every instance is appended to the list of each 8x4 pixel block of the tile that its
+    //    conservative alpha >= 1/255 extent touches (quarter_mask), keeping the depth order: two sweeps over the sorted
+    //    ids in chunks of 32 (lane = record) around a scan of the per-chunk, per-block counts.  The key buffer is dead
+    //    after the ranking and is reused for the masks and the counts.  Block record = the instance's record with
+    //    word 2 of rec0 = (position in the tile list << 4 | the block's 4-bit quarter mask) + the Gaussian id.
+    const size_t tgb = tg * kBlocksPerTile;
+    const unsigned int nchunks = (n + 31u) >> 5;
+    unsigned int* mbuf = reinterpret_cast<unsigned int*>(kb);              // [32 * nchunks] quarter masks, sorted order
+    unsigned int* cpre = mbuf + 32u * nchunks;                             // [nchunks][8] counts -> exclusive prefixes
+    const int warp = t >> 5, lane = t & 31;
+    constexpr int kWarps = THREADS / 32;
+    for (unsigned int c = warp; c < nchunks; c += kWarps) {
+        const unsigned int p = 32u * c + lane;
+        unsigned int mask = 0;
+        if (p < n) {
+            const float4 v0 = __ldg(a.g0 + gb + ids[p]);
+            mask = quarter_mask(v0.x, v0.y, v0.z, X0, Y0);
         }
-        __syncthreads();
+        mbuf[p] = mask;
+        unsigned int mine = 0;
+#pragma unroll
+        for (int b = 0; b < kBlocksPerTile; ++b) {
+            const unsigned int bal = __ballot_sync(0xffffffffu, (mask >> (4 * b)) & 0xfu);
+            if (lane == b) mine = __popc(bal);
+        }
+        if (lane < kBlocksPerTile) cpre[c * kBlocksPerTile + lane] = mine;
     }
+    __syncthreads();
+    if (warp < kBlocksPerTile) {                 // warp w: exclusive scan of block w's chunk counts
+        unsigned int running = 0;
+        for (unsigned int c0 = 0; c0 < nchunks; c0 += 32) {
+            const unsigned int c = c0 + lane;
+            const unsigned int v = c < nchunks ? cpre[c * kBlocksPerTile + warp] : 0u;
+            unsigned int inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned int u = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += u;
+            }
+            if (c < nchunks) cpre[c * kBlocksPerTile + warp] = running + inc - v;
+            running += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) s_warp[warp] = running;
+    }
+    __syncthreads();
+    if (t == 0) {                                // reserve the tile's block records (bump allocation)
+        unsigned int total = 0;
+#pragma unroll
+        for (int b = 0; b < kBlocksPerTile; ++b) total += s_warp[b];
+        const unsigned long long base = atomicAdd(&a.header->blk_required, static_cast<unsigned long long>(total));
+        const bool fits = base + total <= a.blk_capacity;
+        if (!fits) atomicOr(&a.header->overflow, 2u);     // the tile's blocks stay empty; reported via the status
+        unsigned int run = static_cast<unsigned int>(base);
+#pragma unroll
+        for (int b = 0; b < kBlocksPerTile; ++b) {
+            a.blk_off[tgb + b] = fits ? run : 0u;
+            a.blk_cnt[tgb + b] = fits ? s_warp[b] : 0u;
+            s_warp[8 + b] = run;
+            run += s_warp[b];
+        }
+        s_warp[16] = fits ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_warp[16]) {
+        const unsigned int lt = (1u << lane) - 1u;
+        for (unsigned int c = warp; c < nchunks; c += kWarps) {
+            const unsigned int p = 32u * c + lane;
+            const unsigned int mask = mbuf[p];
+            unsigned int id = 0;
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;
+            if (mask) {
+                id = ids[p];
+                v0 = __ldg(a.g0 + gb + id);
+                v1 = __ldg(a.g1 + gb + id);
+                v2 = __ldg(a.g2 + gb + id);
+            }
+#pragma unroll
+            for (int b = 0; b < kBlocksPerTile; ++b) {
+                const unsigned int nib = (mask >> (4 * b)) & 0xfu;
+                const unsigned int bal = __ballot_sync(0xffffffffu, nib);
+                if (nib) {
+                    const size_t dst = size_t(s_warp[8 + b]) + cpre[c * kBlocksPerTile + b] + __popc(bal & lt);
+                    a.brec0[dst] = make_float4(v0.x, v0.y, __uint_as_float((p << 4) | nib), v0.w);
+                    a.brec1[dst] = v1;
+                    a.brec2[dst] = v2;
+                    a.bids[dst] = id;
+                }
+            }
+        }
+    }
+    __syncthreads();                             // the key buffer is reused by the CTA's next tile
 }
 
 #ifndef SGR_SORT_SMALL_MIN_CTAS
@@ -381,11 +454,17 @@ __global__ void __launch_bounds__(kSmallSortThreads, SGR_SORT_SMALL_MIN_CTAS) so
         const int tile_local = a.work[w];
         const unsigned int n = a.tile_cnt[size_t(a.render_base) * a.num_tiles + tile_local];
         if (n <= 4u * kSmallSortThreads)
-            sort_one_tile<kSmallSortThreads, kSmallSortBuckets, 4>(a, tile_local, kb, false, hist, s_warp, s_red);
+            sort_one_tile<kSmallSortThreads, kSmallSortBuckets, 4>(a, tile_local, kb, hist, s_warp, s_red);
         else
             sort_one_tile<kSmallSortThreads, kSmallSortBuckets, kSmallSortCap / kSmallSortThreads>(
-                a, tile_local, kb, false, hist, s_warp, s_red);
+                a, tile_local, kb, hist, s_warp, s_red);
     }
+    // Programmatic dependent launch (launch_sort_tiles): this grid started before sort_big_kernel finished.  The
+    // blend behind it in the stream is ordered after THIS grid only, so every CTA waits here for the long-list
+    // grid to complete and flush before it exits: completion of sort_small then implies completion of sort_big
+    // (also under graph capture, where the pair becomes a programmatic edge followed by a plain edge).  Without the
+    // attribute (SGR_SORT_MODE experiments) the wait returns immediately.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(kBigSortThreads) sort_big_kernel(SortArgs a) {
@@ -402,13 +481,13 @@ __global__ void __launch_bounds__(kBigSortThreads) sort_big_kernel(SortArgs a) {
         const int tile_local = a.work[w];
         const size_t tg = size_t(a.render_base) * a.num_tiles + tile_local;
         const unsigned int n = a.tile_cnt[tg];
-        // lists that do not fit in shared memory borrow the tile's own rec0 segment (16 B/instance, not yet written)
+        // lists that do not fit in shared memory use their segment of the second global key buffer
         const bool spill = n > a.big_smem_keys;
-        unsigned long long* kb = spill ? reinterpret_cast<unsigned long long*>(a.rec0 + a.tile_off[tg]) : kb_s;
+        unsigned long long* kb = spill ? a.keys_tmp + a.tile_off[tg] : kb_s;
         if (n <= 8u * kBigSortThreads && !spill)
-            sort_one_tile<kBigSortThreads, kBigSortBuckets, 8>(a, tile_local, kb, false, hist, s_warp, s_red);
+            sort_one_tile<kBigSortThreads, kBigSortBuckets, 8>(a, tile_local, kb, hist, s_warp, s_red);
         else
-            sort_one_tile<kBigSortThreads, kBigSortBuckets, 0>(a, tile_local, kb, spill, hist, s_warp, s_red);
+            sort_one_tile<kBigSortThreads, kBigSortBuckets, 0>(a, tile_local, kb, hist, s_warp, s_red);
     }
 }
 
@@ -420,9 +499,10 @@ cudaError_t launch_plan(const ChunkCtx& c) {
     a.n = c.num_renders * c.g.num_tiles;
     a.first_chunk = c.render_base == 0 ? 1 : 0;
     a.capacity = c.p->max_instances;
-    // every chunk owns the slots [render_base * T + chunk_index + instances before it / kSegment, ...): a chunk with
-    // n tiles and m instances emits at most n + m / kSegment items
-    a.seg_region = static_cast<unsigned int>(base + size_t(c.chunk_index));
+    // every chunk owns the item slots [8 * render_base * T + chunk_index + block records before it / kSegB, ...) of
+    // every class: a chunk with n tiles and m block records emits at most 8 n + m / kSegB items
+    a.item_region = static_cast<unsigned int>(base * kBlocksPerTile + size_t(c.chunk_index));
+    a.blk_capacity = c.blk_capacity;
     a.tile_cnt = c.tile_cnt + base;
     a.tile_off = c.tile_off + base;
     a.cursor = c.cursor;
@@ -431,7 +511,6 @@ cudaError_t launch_plan(const ChunkCtx& c) {
     a.plan = c.plan;
     a.work_blend = c.work_blend;
     a.work_empty = c.work_empty;
-    a.work_seg = c.work_seg;
     plan_kernel<<<1, kScanThreads, 0, c.stream>>>(a);
     return cudaGetLastError();
 }
@@ -442,6 +521,10 @@ cudaError_t launch_sort_tiles(const ChunkCtx& c) {
     a.tile_off = c.tile_off; a.tile_cnt = c.tile_cnt; a.keys = c.keys; a.sorted_ids = c.sorted_ids;
     a.rec0 = c.rec0; a.rec1 = c.rec1; a.rec2 = c.rec2; a.g0 = c.g0; a.g1 = c.g1; a.g2 = c.g2;
     a.work = c.work_blend; a.wc = c.work_counts;
+    a.keys_tmp = c.keys_tmp;
+    a.simple = (c.p->flags & SGR_FLAG_SIMPLE_BLEND) ? 1 : 0;
+    a.header = c.header; a.blk_off = c.blk_off; a.blk_cnt = c.blk_cnt;
+    a.brec0 = c.brec0; a.brec1 = c.brec1; a.brec2 = c.brec2; a.bids = c.bids; a.blk_capacity = c.blk_capacity;
     const int dslot = current_device_slot();
     static int num_sms_dev[kMaxDevices] = {};
     static bool attr_set_dev[kMaxDevices] = {};
@@ -482,8 +565,9 @@ cudaError_t launch_sort_tiles(const ChunkCtx& c) {
     }
     // The long-list kernel goes first (it is the longer pole and a 1024-thread CTA cannot share an SM with the
     // short-list CTAs, so it must not queue behind them); the short-list kernel follows in the SAME stream as a
-    // programmatic dependent launch: it starts once all long-list CTAs are resident and fills the remaining SMs.  The
-    // next normal launch in the stream (the blend) waits for both.
+    // programmatic dependent launch: it starts once all long-list CTAs are resident and fills the remaining SMs.  Its
+    // CTAs execute griddepcontrol.wait before they exit, so the next launch in the stream (the blend), which is
+    // ordered behind the short-list grid, is transitively ordered behind the long-list grid as well.
     if (mode == 0) {
         sort_big_kernel<<<min(num_sms, total_tiles), kBigSortThreads, big_smem, c.stream>>>(a);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;

@@ -3,22 +3,23 @@
 // Replaces upstream renderCUDA forward/backward (third-party diff_gaussian_rasterization; call site
 // /root/reference/core/gaussians/gs.py:99-106).  Design (DESIGN.md "blend"):
 //   * the unit of work is one 8x4 pixel block of one tile of one render.  Every WARP is autonomous: it pops work items
-//     from a device-side queue ordered longest-list-first (sgr_binning.cu::plan_kernel), streams the tile's
-//     depth-ordered 48-byte records (three float4 streams, contiguous per tile because the per-tile sort gathers them)
-//     through its own shared-memory ring with 1-D TMA bulk copies (cp.async.bulk) completing on its own mbarriers, and
-//     never waits for another warp — no block-wide barrier, no producer/consumer hand-off, early exit as soon as its
-//     32 pixels are finished;
+//     from a device-side queue ordered longest-list-first (sgr_binning.cu::plan_kernel), streams the BLOCK's
+//     depth-ordered 48-byte records (three float4 streams; the per-tile sort emits one contiguous list per block that
+//     holds only the instances whose extent touches the block) through its own shared-memory ring with 1-D TMA bulk
+//     copies (cp.async.bulk) completing on its own mbarriers, and never waits for another warp — no block-wide
+//     barrier, no producer/consumer hand-off, early exit as soon as its 32 pixels are finished;
 //   * a block is four 4x2 quarters.  A batch of 128 records is culled in straight-line code (lane = record): the
-//     per-instance quarter masks built by the tile sort are loaded, one ballot per (round, quarter), and the
+//     per-record 4-bit quarter masks built by the tile sort are read, one ballot per (round, quarter), and the
 //     survivors' batch-local indices are compacted into one sentinel-padded list per quarter; every quarter then
 //     walks only its own survivors (lane = pixel), so up to four different Gaussians are evaluated per trip.  Culled
 //     records would have been skipped by the alpha test, so the per-pixel arithmetic, the contributor index and every
 //     output bit equal the straightforward kernel's;
 //   * forward trips run in groups of eight (four at the end of a list): eight independent alpha chains written
 //     load-first, then the sequential compositing recurrence; per batch the forward clears the mask bits of the
-//     (quarter, record) pairs that did not blend (one RED.AND per changed record) so that the backward culls on the
-//     exact set, and checkpoints the running state every 1024 records;
-//   * backward: work items are (tile, 1024-record segment, block), resumed from the forward's checkpoints; the same
+//     (quarter, record) pairs that did not blend (a plain store: the block owns its records) so that the backward
+//     culls on the exact set, checkpoints the running state every kSegB records and pushes one backward work item
+//     per segment that blended anything, classed by the number of records that blended;
+//   * backward: work items are (block, kSegB-record segment), resumed from the forward's checkpoints; the same
 //     walk in reverse over descending lists with phases A+B (alpha, G, then the per-pixel transmittance / colour
 //     recurrences producing dL/dalpha and the blend weight, stashed) and C: the roles flip to lane = (Gaussian,
 //     quarter) pair, each lane summing the gradient terms of its quarter's 8 pixels in registers (XOR-swizzled stash,
@@ -26,7 +27,9 @@
 //   * optional epilogue: clamp + masked L1 loss + dL/dcolour (SgrForwardArgs::loss_*).
 //
 // Compiled with --fmad=false: the per-pixel expressions are the oracle's (oracle/sgr_oracle.cpp::blend_forward /
-// blend_backward) evaluated in the same order, which makes colour, depth, alpha and n_contrib bit-exact.
+// blend_backward) evaluated in the same order.  exp(power) is a template switch: kExact = the oracle's exp_spec
+// sequence (SGR_FLAG_EXACT_EXP: colour, depth, alpha and n_contrib bit-exact), default = the SFU's ex2 like upstream's
+// own exp() (sgr_common.cuh::exp_fast; ~1e-6 from the oracle).
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
@@ -54,13 +57,14 @@ constexpr int kFwdStages = SGR_FWD_STAGES;     // per-warp TMA ring depth, forwa
 constexpr int kBwdStages = SGR_BWD_STAGES;     // backward: one 128-record stage (the stash takes the rest of the budget)
 constexpr int kWarpsPerCta = 8;
 constexpr int kBlendThreads = kWarpsPerCta * 32;
-constexpr int kBlocksPerTile = 8;              // a 16x16 tile = eight 8x4 pixel blocks = eight work items
 constexpr int kBlockW = 8, kBlockH = 4;        // pixel block of one warp (four 4x2 quarters walk separate lists)
 #ifndef SGR_BWD_SLOTS
 #define SGR_BWD_SLOTS 16
 #endif
 constexpr int kBwdSlots = SGR_BWD_SLOTS;       // backward: trips per phase pass (8 or 16: the stash swizzle)
 constexpr unsigned int kFull = 0xffffffffu;
+template <bool kExact>
+__device__ __forceinline__ float blend_exp(float x) { return kExact ? exp_core(x) : exp_fast(x); }
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -124,13 +128,13 @@ struct WarpSmem {
     uint64_t full[kNumStages];
 };
 
-// Cull a batch of m <= kBatch records against the four 4x2 quarters of the warp's 8x4 pixel block `blk` of the tile:
-// 32 records per round (lane = record) read their precomputed quarter mask (rec0.z, built once per instance by the
-// tile sort, sgr_common.cuh::quarter_mask), one ballot per quarter, warp-parallel compaction of the survivors'
+// Cull a batch of m <= kBatch block records against the four 4x2 quarters of the warp's 8x4 pixel block:
+// 32 records per round (lane = record) read their 4-bit quarter mask (low bits of rec0.z, built by the tile sort
+// from sgr_common.cuh::quarter_mask), one ballot per quarter, warp-parallel compaction of the survivors'
 // batch-local indices into list[quarter][...] (ascending; descending with kReverse — the backward walks back to front);
 // unused list entries point at the sentinel record.  Returns the four survivor counts.
 template <bool kReverse, int kBatch>
-__device__ __forceinline__ uint4 cull_batch(const float4* r0, unsigned int m, int blk,
+__device__ __forceinline__ uint4 cull_batch(const float4* r0, unsigned int m,
                                             unsigned char (*list)[kBatch + kListPad],
                                             int lane, unsigned int (&bits)[kBatch / 32]) {
     // Straight-line code (the per-batch overhead is latency, not work): all mask words are loaded first, then all
@@ -141,7 +145,7 @@ __device__ __forceinline__ uint4 cull_batch(const float4* r0, unsigned int m, in
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const unsigned int e = 32u * r + lane;
-        bits[r] = (e < m) ? ((words[4 * e + 2] >> (4 * blk)) & 0xfu) : 0u;
+        bits[r] = (e < m) ? (words[4 * e + 2] & 0xfu) : 0u;
     }
     {                             // every list entry the compaction does not overwrite points at the sentinel record
         constexpr unsigned int fill = kBatch * 0x01010101u;
@@ -211,17 +215,23 @@ __device__ unsigned long long g_phase[16];
 struct FwdArgs {
     RenderGeom g;
     int render_base;
-    const unsigned int* tile_off;
-    const unsigned int* tile_cnt;
-    const float4 *rec0, *rec1, *rec2;
+    const unsigned int* blk_off;  // [R*T*8] block lists (sgr_binning.cu step 5)
+    const unsigned int* blk_cnt;
+    unsigned int* blk_eff;        // out: records of the block list the backward has to replay
+    const float4 *rec0, *rec1, *rec2;   // block records
     unsigned int* rec0_words;     // rec0 as words: the forward refines the quarter masks (word 2 of every record)
     int refine_masks;
     const float* bg;
     unsigned int* n_contrib;
+    unsigned char* clamp_mask;    // [R*P] written when clamp_color
     uint2* tile_time;
     float *out_color, *out_depth, *out_alpha;
+    float* out_feed;              // optional LPIPS feed [R,3,H/2,W/2]
     float4* ck0;                  // per-pixel checkpoints (T, C0, C1, C2) at segment boundaries of long lists
     float* ck1;                   // ... and D
+    ChunkPlan* plan;              // backward items are pushed here (refine_masks only)
+    uint2* bwd_items;
+    unsigned long long bwd_items_stride;
     const unsigned int *work_blend, *work_empty;
     WorkCounts* wc;
     int clamp_color;
@@ -231,6 +241,11 @@ struct FwdArgs {
     float* loss_part;
     float loss_scale;
 };
+
+// Backward item classes by the number of records of the segment that blended in at least one quarter.
+__device__ __forceinline__ int bwd_class(unsigned int hits) {
+    return hits >= 3u * kSegB / 4 ? 0 : hits >= 3u * kSegB / 8 ? 1 : hits >= kSegB / 8 ? 2 : 3;
+}
 
 // Fused loss epilogue of one pixel: |clamp(c) * m - t * m| summed over the three channels; writes
 // d loss / d (unclamped colour) = sign(diff) * m * scale where the clamp did not saturate (torch's clamp / abs rules).
@@ -260,6 +275,40 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Output epilogue of one pixel (all 32 lanes of the block call it; lane = pixel (x = lane & 7, y = lane >> 3)).
+// clamp_color: gs.py:107 `clamp(0, 1)` fused, with the clamp mask kept for the backward (bit c = channel c saturated,
+// torch's rule: the gradient passes where 0 <= c <= 1).  out_feed: the LPIPS input of whole_loss.py:132-136 — a
+// factor-2 bilinear resize (align_corners=False) is the mean over 2x2 pixels, here two shuffles inside the block.
+__device__ __forceinline__ void write_pixel(const FwdArgs& a, int r, size_t P, int px, int py, bool inside, int lane,
+                                            float c0, float c1, float c2, float D, float Wt, unsigned int last) {
+    (void)lane;
+    const size_t pix = size_t(py) * a.g.W + px;
+    if (a.clamp_color) {
+        const unsigned int m = (c0 >= 0.0f && c0 <= 1.0f ? 0u : 1u) | (c1 >= 0.0f && c1 <= 1.0f ? 0u : 2u) |
+                               (c2 >= 0.0f && c2 <= 1.0f ? 0u : 4u);
+        c0 = fminf(fmaxf(c0, 0.0f), 1.0f); c1 = fminf(fmaxf(c1, 0.0f), 1.0f); c2 = fminf(fmaxf(c2, 0.0f), 1.0f);
+        if (inside) a.clamp_mask[size_t(r) * P + pix] = static_cast<unsigned char>(m);
+    }
+    if (a.out_feed) {                           // even H, W: a 2x2 cell is entirely inside or outside the image
+        float s0 = c0 + __shfl_xor_sync(kFull, c0, 1), s1 = c1 + __shfl_xor_sync(kFull, c1, 1),
+              s2 = c2 + __shfl_xor_sync(kFull, c2, 1);
+        s0 += __shfl_xor_sync(kFull, s0, 8); s1 += __shfl_xor_sync(kFull, s1, 8); s2 += __shfl_xor_sync(kFull, s2, 8);
+        if (inside && (px & 1) == 0 && (py & 1) == 0) {
+            const size_t Pq = P >> 2;
+            const size_t q = size_t(py >> 1) * (a.g.W >> 1) + (px >> 1);
+            float* of = a.out_feed + size_t(r) * 3 * Pq;
+            of[q] = 0.5f * s0 - 1.0f; of[Pq + q] = 0.5f * s1 - 1.0f; of[2 * Pq + q] = 0.5f * s2 - 1.0f;
+        }
+    }
+    if (inside) {
+        float* oc = a.out_color + size_t(r) * 3 * P;
+        oc[pix] = c0; oc[P + pix] = c1; oc[2 * P + pix] = c2;
+        a.out_depth[size_t(r) * P + pix] = D;
+        a.out_alpha[size_t(r) * P + pix] = Wt;
+        a.n_contrib[size_t(r) * P + pix] = last;
+    }
+}
+
 using FwdSmem = WarpSmem<1, 1, kFwdStages, kFwdBatch>;      // the forward needs no stash
 using BwdSmem = WarpSmem<3, kBwdSlots, kBwdStages, kBwdBatch>;
 
@@ -272,6 +321,7 @@ using BwdSmem = WarpSmem<3, kBwdSlots, kBwdStages, kBwdBatch>;
 #ifndef SGR_BWD_MIN_CTAS
 #define SGR_BWD_MIN_CTAS 2
 #endif
+template <bool kExact>
 __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward_kernel(FwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -310,13 +360,17 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
         const int tile = tile_local - rl * a.g.num_tiles;
         const int r = a.render_base + rl;
         const size_t tg = size_t(r) * a.g.num_tiles + tile;
-        const unsigned int n = a.tile_cnt[tg];
-        const size_t off = a.tile_off[tg];
+        const size_t bi = tg * kBlocksPerTile + blk;
+        const unsigned int n = a.blk_cnt[bi];                       // records of this block's list
+        const size_t off = a.blk_off[bi];
         const unsigned int nb = (n + kFwdBatch - 1) / kFwdBatch;
         const int tx = tile % a.g.tiles_x, ty = tile / a.g.tiles_x;
         const int bx0 = tx * kTile + (blk & 1) * kBlockW, by0 = ty * kTile + (blk >> 1) * kBlockH;
         if (bx0 >= a.g.W || by0 >= a.g.H) {                        // block entirely outside the image
-            if (a.loss_target && lane == 0) a.loss_part[size_t(tile_local) * kBlocksPerTile + blk] = 0.0f;
+            if (lane == 0) {
+                if (a.loss_target) a.loss_part[size_t(tile_local) * kBlocksPerTile + blk] = 0.0f;
+                if (refine) a.blk_eff[bi] = 0u;
+            }
             continue;
         }
         const unsigned long long t_begin = global_timer_ns();
@@ -329,6 +383,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
         unsigned int last = 0;
         bool done = !inside;
         unsigned int b_issued = 0;
+        unsigned int seg_hits = 0, eff = 0;      // records of the current segment that blended; last such record + 1
 #ifdef SGR_PHASE_TIMING
         long long ph[5] = {0, 0, 0, 0, 0};
         unsigned long long ntrips = 0;
@@ -354,7 +409,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
             const float4* r2 = sm.r2[s];
             uint4 cnt;
             unsigned int qbits[kFwdBatch / 32];
-            { PHASE_T0(); cnt = cull_batch<false, kFwdBatch>(r0, m, blk, sm.list, lane, qbits); PHASE_ADD(1); }
+            { PHASE_T0(); cnt = cull_batch<false, kFwdBatch>(r0, m, sm.list, lane, qbits); PHASE_ADD(1); }
             // quarters whose 8 pixels are all finished need no further evaluation
             const unsigned int dmask = __ballot_sync(kFull, done);
             const unsigned int my_n = ((dmask & qmask) == qmask) ? 0u : (qsel == 0 ? cnt.x : qsel == 1 ? cnt.y : qsel == 2 ? cnt.z : cnt.w);
@@ -392,7 +447,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
                     const float dx = q0[u].x - pxf, dy = q0[u].y - pyf;
                     const float power = gauss_power(q1[u].x, q1[u].y, q1[u].z, dx, dy);
                     const bool valid = !(power > 0.0f) && !(power < q0[u].w);
-                    const float alpha = fminf(kAlphaMax, q1[u].w * exp_core(valid ? power : 0.0f));
+                    const float alpha = fminf(kAlphaMax, q1[u].w * blend_exp<kExact>(valid ? power : 0.0f));
                     al[u] = valid ? alpha : 0.0f;
                 }
 #pragma unroll
@@ -422,7 +477,8 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
 #endif
                 for (; t0 < total; t0 += 4) trip_group(t0, std::integral_constant<int, 4>{});
             }
-            if (lastj != 0xffffffffu) last = cbase + lastj + 1u;
+            // n_contrib counts positions in the TILE's list (upstream's contributor index): bits 4.. of word 2
+            if (lastj != 0xffffffffu) last = (__float_as_uint(r0[lastj].z) >> 4) + 1u;
             __syncwarp();
 #ifdef SGR_PHASE_TIMING
             ph[2] += clock64() - pt_trips;
@@ -430,23 +486,39 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
 #endif
             // Mask refinement for the backward pass: clear the (block, quarter) bits of the records that no pixel of
             // the quarter blended (alpha test, finished pixels) — the backward walk culls on the same word.
-            if (refine && (cnt.x | cnt.y | cnt.z | cnt.w) != 0u) {
-                unsigned int hw[kFwdBatch / 32];
+            if (refine) {
+                if ((cnt.x | cnt.y | cnt.z | cnt.w) != 0u) {
+                    unsigned int hw[kFwdBatch / 32];
 #pragma unroll
-                for (int rr = 0; rr < kFwdBatch / 32; ++rr) hw[rr] = sm.hit[32 * rr + lane];
+                    for (int rr = 0; rr < kFwdBatch / 32; ++rr) hw[rr] = sm.hit[32 * rr + lane];
 #pragma unroll
-                for (int rr = 0; rr < kFwdBatch / 32; ++rr) {
-                    const unsigned int e = 32u * rr + lane;
-                    const unsigned int exact = ((hw[rr] & 0x01010101u) * 0x10204080u) >> 28;
-                    const unsigned int clear = qbits[rr] & ~exact;          // qbits = 0 beyond the batch
-                    if (clear) atomicAnd(a.rec0_words + 4 * (off + cbase + e) + 2, ~(clear << (4 * blk)));
-                    if (hw[rr]) sm.hit[e] = 0u;
+                    for (int rr = 0; rr < kFwdBatch / 32; ++rr) {
+                        const unsigned int e = 32u * rr + lane;
+                        const unsigned int exact = ((hw[rr] & 0x01010101u) * 0x10204080u) >> 28;
+                        const unsigned int clear = qbits[rr] & ~exact;      // qbits = 0 beyond the batch
+                        // the block owns its records: a plain store of the refined word
+                        if (clear) a.rec0_words[4 * (off + cbase + e) + 2] = __float_as_uint(r0[e].z) & ~clear;
+                        if (hw[rr]) sm.hit[e] = 0u;
+                        const unsigned int hb = __ballot_sync(kFull, exact != 0u);
+                        if (hb) { seg_hits += __popc(hb); eff = cbase + 32u * rr + (32u - __clz(hb)); }
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
+                // end of a backward segment (or of the list): one work item if anything blended in it
+                const unsigned int end = cbase + m;
+                if (end % kSegB == 0u || end == n) {
+                    if (seg_hits != 0u && lane == 0) {
+                        const int cls = bwd_class(seg_hits);
+                        const unsigned int slot = atomicAdd(&a.plan->n_items[cls], 1u);
+                        a.bwd_items[size_t(cls) * a.bwd_items_stride + a.plan->item_base + slot] =
+                            make_uint2(unsigned(tile_local) * kBlocksPerTile + blk, (end - 1u) / kSegB);
+                    }
+                    seg_hits = 0u;
+                }
             }
             // lists longer than one backward segment: checkpoint the running state at every segment boundary
-            if (n > unsigned(kSegment) && ((b + 1) * kFwdBatch) % kSegment == 0 && (b + 1) * kFwdBatch < n) {
-                const size_t ci = ((off / (kSegment / 2) + (b + 1) * kFwdBatch / kSegment - 1) * kBlocksPerTile + blk) * 32 + lane;
+            if (n > unsigned(kSegB) && ((b + 1) * kFwdBatch) % kSegB == 0 && (b + 1) * kFwdBatch < n) {
+                const size_t ci = (off / (kSegB / 2) + (b + 1) * kFwdBatch / kSegB - 1) * 32 + lane;
                 a.ck0[ci] = make_float4(T, C0, C1, C2);
                 a.ck1[ci] = D;
             }
@@ -468,10 +540,20 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
             }
         }
 #endif
-        if (n > unsigned(kSegment)) {                 // final state, read by the backward's non-final segments
-            const size_t ci = ((off / (kSegment / 2) + (n + kSegment - 1) / kSegment - 1) * kBlocksPerTile + blk) * 32 + lane;
+        if (n > unsigned(kSegB)) {                    // final state, read by the backward's non-final segments
+            const size_t ci = (off / (kSegB / 2) + (n + kSegB - 1) / kSegB - 1) * 32 + lane;
             a.ck0[ci] = make_float4(T, C0, C1, C2);
             a.ck1[ci] = D;
+        }
+        if (refine) {
+            // an early exit (all pixels finished) inside a segment leaves its item unpushed: push it now
+            if (seg_hits != 0u && lane == 0) {
+                const int cls = bwd_class(seg_hits);
+                const unsigned int slot = atomicAdd(&a.plan->n_items[cls], 1u);
+                a.bwd_items[size_t(cls) * a.bwd_items_stride + a.plan->item_base + slot] =
+                    make_uint2(unsigned(tile_local) * kBlocksPerTile + blk, (eff - 1u) / kSegB);
+            }
+            if (lane == 0) a.blk_eff[bi] = eff;
         }
         // drain: copies already in flight must land before their slots are reused by the next item
         while (consumed < issued) {
@@ -485,18 +567,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
             part = warp_sum(part);
             if (lane == 0) a.loss_part[size_t(tile_local) * kBlocksPerTile + blk] = part;
         }
-        if (inside) {
-            const size_t pix = size_t(py) * a.g.W + px;
-            float c0 = C0 + T * bg0, c1 = C1 + T * bg1, c2 = C2 + T * bg2;
-            if (a.clamp_color) {
-                c0 = fminf(fmaxf(c0, 0.0f), 1.0f); c1 = fminf(fmaxf(c1, 0.0f), 1.0f); c2 = fminf(fmaxf(c2, 0.0f), 1.0f);
-            }
-            float* oc = a.out_color + size_t(r) * 3 * P;
-            oc[pix] = c0; oc[P + pix] = c1; oc[2 * P + pix] = c2;
-            a.out_depth[size_t(r) * P + pix] = D;
-            a.out_alpha[size_t(r) * P + pix] = Wt;
-            a.n_contrib[size_t(r) * P + pix] = last;
-        }
+        write_pixel(a, r, P, px, py, inside, lane, C0 + T * bg0, C1 + T * bg1, C2 + T * bg2, D, Wt, last);
         if (a.tile_time && lane == 0) {          // diagnostics: start of block 0, duration of the slowest block
             const unsigned long long now = global_timer_ns();
             if (blk == 0) a.tile_time[tg].x = (unsigned int)t_begin;
@@ -505,8 +576,6 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
     }
 
     // ---------------- blocks of tiles without instances: background only
-    float e0 = bg0, e1 = bg1, e2 = bg2;
-    if (a.clamp_color) { e0 = fminf(fmaxf(e0, 0.0f), 1.0f); e1 = fminf(fmaxf(e1, 0.0f), 1.0f); e2 = fminf(fmaxf(e2, 0.0f), 1.0f); }
     // whole tiles are popped (8 uniform items per global atomic round trip)
     for (unsigned int item = 0xffffffffu;;) {
         if (item == 0xffffffffu || (item % kBlocksPerTile) == kBlocksPerTile - 1) {
@@ -530,14 +599,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
             part = warp_sum(part);
             if (lane == 0) a.loss_part[size_t(tile_local) * kBlocksPerTile + blk] = part;
         }
-        if (px < a.g.W && py < a.g.H) {
-            const size_t pix = size_t(py) * a.g.W + px;
-            float* oc = a.out_color + size_t(r) * 3 * P;
-            oc[pix] = e0; oc[P + pix] = e1; oc[2 * P + pix] = e2;
-            a.out_depth[size_t(r) * P + pix] = 0.0f;
-            a.out_alpha[size_t(r) * P + pix] = 0.0f;
-            a.n_contrib[size_t(r) * P + pix] = 0u;
-        }
+        write_pixel(a, r, P, px, py, px < a.g.W && py < a.g.H, lane, bg0, bg1, bg2, 0.0f, 0.0f, 0u);
     }
 }
 
@@ -545,38 +607,49 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
 struct BwdArgs {
     RenderGeom g;
     int render_base;
-    const unsigned int* tile_off;
-    const unsigned int* tile_cnt;
-    const unsigned int* sorted_ids;
-    const float4 *rec0, *rec1, *rec2;
+    const unsigned int* blk_off;
+    const unsigned int* blk_cnt;
+    const unsigned int* blk_eff;
+    const unsigned int* bids;
+    const float4 *rec0, *rec1, *rec2;     // block records (masks refined by the forward)
     const float* bg;
     const unsigned int* n_contrib;
+    const unsigned char* clamp_mask;      // NULL: the forward did not clamp
     const float *out_alpha, *dL_dcolor, *dL_ddepth, *dL_dalpha;
+    const float* loss_dL_dcolor;          // fused-loss gradient (already zero where the clamp saturated), or NULL
+    const float* dL_dfeed;                // gradient w.r.t. the LPIPS feed [R,3,H/2,W/2], or NULL
     float* accum;
     size_t plane;
-    const float4* ck0;            // forward checkpoints (sgr_common.cuh::kSegment)
+    const float4* ck0;            // forward checkpoints (sgr_common.cuh::kSegB)
     const float* ck1;
-    const uint2* work_seg;        // all chunks' (chunk-local tile, segment) items; this chunk's start at plan->seg_base
+    const uint2* bwd_items;       // [kBwdClasses][stride]; this chunk's items start at plan->item_base in every class
+    unsigned long long bwd_items_stride;
     ChunkPlan* plan;
-    const float* dL_scale;        // device scalar multiplying dL_dcolor, or NULL
+    const float* dL_scale;        // device scalar multiplying loss_dL_dcolor, or NULL
 };
 
-// Work item = (tile, segment, 8x4 pixel block): the block replays the list entries [lo, hi) of its segment back to
-// front, lo = segment * kSegment, hi = min(lo + kSegment, wmax), wmax = the largest n_contrib of its 32 pixels.
+// Work item = (block list, segment): the block replays the list entries [lo, hi) of its segment back to front,
+// lo = segment * kSegB, hi = min(lo + kSegB, blk_eff) (blk_eff = the last record any pixel blended, + 1).
 // A pixel whose contributors end inside the segment starts from its final state exactly like the sequential
 // algorithm; a pixel that continues behind the segment starts from the forward's checkpoint at the segment end:
 //   T = T_ck * (T_final / T_fin)   (T_final = 1 - alpha_out as in A.5; T_ck / T_fin = the forward's running values)
 //   accumulated colour / depth / alpha behind = (X_fin - X_ck) / T_ck
-// so that the long face / hand lists no longer serialise on one warp.
-template <bool kDepthAlphaGrads>
+// so that the long face / hand lists do not serialise on one warp.
+template <bool kDepthAlphaGrads, bool kExact>
 __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backward_kernel(BwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     BwdSmem& sm = reinterpret_cast<BwdSmem*>(smem_raw)[warp];
     const size_t P = size_t(a.g.H) * a.g.W;
     const float bg0 = a.bg[0], bg1 = a.bg[1], bg2 = a.bg[2];
-    const unsigned int n_items = a.plan->n_seg * kBlocksPerTile;
-    const uint2* work_seg = a.work_seg + a.plan->seg_base;
+    unsigned int cls_end[kBwdClasses];            // items are popped class by class, most blended records first
+    {
+        unsigned int run = 0;
+#pragma unroll
+        for (int c = 0; c < kBwdClasses; ++c) { run += a.plan->n_items[c]; cls_end[c] = run; }
+    }
+    const unsigned int n_items = cls_end[kBwdClasses - 1];
+    const unsigned int item_base = a.plan->item_base;
     const float ddelx_dx = 0.5f * float(a.g.W), ddely_dy = 0.5f * float(a.g.H);
     const float gscale = a.dL_scale ? *a.dL_scale : 1.0f;
     if (lane == 0) {
@@ -601,31 +674,56 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
     // and for lane = (trip, quarter) pairs reading one pixel of their quarter (phase C).
 
     for (;;) {
-        const unsigned int item = pop_item(&a.plan->seg_cursor, n_items, lane);
+        const unsigned int item = pop_item(&a.plan->cursor, n_items, lane);
         if (item == 0xffffffffu) break;
-        const uint2 ws = work_seg[item / kBlocksPerTile];
-        const unsigned int tile_local = ws.x;
-        const unsigned int lo = ws.y * unsigned(kSegment);
-        const int blk = item % kBlocksPerTile;
+        int cls = 0;
+#pragma unroll
+        for (int c = 0; c < kBwdClasses - 1; ++c) cls += item >= cls_end[c] ? 1 : 0;
+        const unsigned int in_cls = item - (cls ? cls_end[cls - 1] : 0u);
+        const uint2 ws = a.bwd_items[size_t(cls) * a.bwd_items_stride + item_base + in_cls];
+        const unsigned int tile_local = ws.x / kBlocksPerTile;
+        const int blk = ws.x % kBlocksPerTile;
+        const unsigned int lo = ws.y * unsigned(kSegB);
         const int rl = tile_local / a.g.num_tiles;
         const int tile = tile_local - rl * a.g.num_tiles;
         const int r = a.render_base + rl;
         const size_t tg = size_t(r) * a.g.num_tiles + tile;
+        const size_t bi = tg * kBlocksPerTile + blk;
         const int tx = tile % a.g.tiles_x, ty = tile / a.g.tiles_x;
         const int bx0 = tx * kTile + (blk & 1) * kBlockW, by0 = ty * kTile + (blk >> 1) * kBlockH;
         const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
         const bool inside = px < a.g.W && py < a.g.H;
         const size_t pix = size_t(py) * a.g.W + px;
-        const unsigned int last = inside ? a.n_contrib[size_t(r) * P + pix] : 0u;
-        const unsigned int wmax = __reduce_max_sync(kFull, last);   // entries at or beyond it are never replayed
-        if (wmax <= lo) continue;
-        const unsigned int hi = min(lo + unsigned(kSegment), wmax);
-        const size_t off = a.tile_off[tg];
+        const unsigned int last = inside ? a.n_contrib[size_t(r) * P + pix] : 0u;     // position in the TILE list + 1
+        const unsigned int eff = a.blk_eff[bi];
+        if (eff <= lo) continue;
+        const unsigned int hi = min(lo + unsigned(kSegB), eff);
+        const size_t off = a.blk_off[bi];
+        const unsigned int n = a.blk_cnt[bi];
         float T_final = 1.0f, dp0 = 0, dp1 = 0, dp2 = 0, ddep = 0, dalp = 0;
         if (inside) {
             T_final = 1.0f - a.out_alpha[size_t(r) * P + pix];
-            const float* dc = a.dL_dcolor + size_t(r) * 3 * P;
-            dp0 = dc[pix] * gscale; dp1 = dc[P + pix] * gscale; dp2 = dc[2 * P + pix] * gscale;
+            // d loss / d (unclamped colour): the caller's gradients w.r.t. the returned image / LPIPS feed, masked
+            // where the forward's clamp saturated, plus the fused loss's own gradient
+            if (a.dL_dcolor) {
+                const float* dc = a.dL_dcolor + size_t(r) * 3 * P;
+                dp0 = dc[pix]; dp1 = dc[P + pix]; dp2 = dc[2 * P + pix];
+            }
+            if (a.dL_dfeed) {
+                const size_t Pq = P >> 2;
+                const float* df = a.dL_dfeed + size_t(r) * 3 * Pq + size_t(py >> 1) * (a.g.W >> 1) + (px >> 1);
+                dp0 = fmaf(0.5f, df[0], dp0); dp1 = fmaf(0.5f, df[Pq], dp1); dp2 = fmaf(0.5f, df[2 * Pq], dp2);
+            }
+            if (a.clamp_mask) {
+                const unsigned int cm = a.clamp_mask[size_t(r) * P + pix];
+                if (cm & 1u) dp0 = 0.0f;
+                if (cm & 2u) dp1 = 0.0f;
+                if (cm & 4u) dp2 = 0.0f;
+            }
+            if (a.loss_dL_dcolor) {
+                const float* dc = a.loss_dL_dcolor + size_t(r) * 3 * P;
+                dp0 = fmaf(dc[pix], gscale, dp0); dp1 = fmaf(dc[P + pix], gscale, dp1); dp2 = fmaf(dc[2 * P + pix], gscale, dp2);
+            }
             if (kDepthAlphaGrads) {
                 if (a.dL_ddepth) ddep = a.dL_ddepth[size_t(r) * P + pix];
                 if (a.dL_dalpha) dalp = a.dL_dalpha[size_t(r) * P + pix];
@@ -639,11 +737,17 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
         const float4 *g0 = a.rec0 + off + lo, *g1 = a.rec1 + off + lo, *g2 = a.rec2 + off + lo;
         float T = T_final;
         float ar0 = 0, ar1 = 0, ar2 = 0, adr = 0, aar = 0, last_alpha = 0, lc0 = 0, lc1 = 0, lc2 = 0, last_depth = 0;
-        if (last > hi) {                         // contributors behind this segment: resume from the checkpoints
-            const unsigned int n = a.tile_cnt[tg];
-            const size_t slot0 = off / (kSegment / 2);
-            const size_t ci = ((slot0 + ws.y) * kBlocksPerTile + blk) * 32 + lane;
-            const size_t fi = ((slot0 + (n + kSegment - 1) / kSegment - 1) * kBlocksPerTile + blk) * 32 + lane;
+        // A pixel has contributors behind this segment iff its last contributor sits at or behind the first record
+        // after the segment (records are in tile-list order; word 2 >> 4 = position in the tile list).
+        bool resume = false;
+        if (lo + unsigned(kSegB) < n) {
+            const unsigned int next_pos = __float_as_uint(__ldg(&a.rec0[off + lo + kSegB].z)) >> 4;
+            resume = last > next_pos;
+        }
+        if (resume) {                            // resume from the checkpoints
+            const size_t slot0 = off / (kSegB / 2);
+            const size_t ci = (slot0 + ws.y) * 32 + lane;
+            const size_t fi = (slot0 + (n + kSegB - 1) / kSegB - 1) * 32 + lane;
             const float4 ck = a.ck0[ci], fin = a.ck0[fi];
             const float inv = 1.0f / ck.x;
             T = ck.x * (T_final / fin.x);
@@ -655,7 +759,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
         }
         const float bg_dot = (bg0 * dp0 + bg1 * dp1) + bg2 * dp2;
         float* acc = a.accum + size_t(rl) * a.g.N;
-        const unsigned int* ids = a.sorted_ids + off;
+        const unsigned int* ids = a.bids + off;
 
         // walk step k handles list batch (nb - 1 - k)
         unsigned int b_issued = 0;
@@ -690,7 +794,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
             const float4* r1 = sm.r1[s];
             const float4* r2 = sm.r2[s];
             unsigned int qbits[kBwdBatch / 32];
-            const uint4 cnt = cull_batch<true, kBwdBatch>(r0, m, blk, sm.list, lane, qbits);
+            const uint4 cnt = cull_batch<true, kBwdBatch>(r0, m, sm.list, lane, qbits);
             const int total = int(max(max(cnt.x, cnt.y), max(cnt.z, cnt.w)));
             BPH(1);
 #ifdef SGR_PHASE_TIMING
@@ -710,8 +814,8 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const unsigned int j = (packed >> (8 * u)) & 0xffu;
-                        has[u] = cbase + j < last;
                         q0[u] = r0[j];
+                        has[u] = (__float_as_uint(q0[u].z) >> 4) < last;
                         q1[u] = r1[j];
                         q2[u] = r2[j];
                     }
@@ -721,7 +825,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
                         const float dx = q0[u].x - pxf, dy = q0[u].y - pyf;
                         const float power = gauss_power(q1[u].x, q1[u].y, q1[u].z, dx, dy);
                         const bool valid = has[u] && !(power > 0.0f) && !(power < q0[u].w);
-                        gg[u] = exp_core(valid ? power : 0.0f);
+                        gg[u] = blend_exp<kExact>(valid ? power : 0.0f);
                         const float alpha = fminf(kAlphaMax, q1[u].w * gg[u]);
                         al[u] = (valid && !(alpha < kAlphaMin)) ? alpha : 0.0f;
                     }
@@ -872,24 +976,28 @@ cudaError_t prepare_kernel(K kernel, size_t smem, int* per_sm) {
 
 }  // namespace
 
-cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out_depth, float* out_alpha) {
+cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out_depth, float* out_alpha,
+                                 float* out_feed) {
     FwdArgs a;
-    a.g = c.g; a.render_base = c.render_base; a.tile_off = c.tile_off; a.tile_cnt = c.tile_cnt;
-    a.rec0 = c.rec0; a.rec1 = c.rec1; a.rec2 = c.rec2; a.bg = c.p->bg; a.n_contrib = c.n_contrib;
-    a.rec0_words = reinterpret_cast<unsigned int*>(c.rec0);
+    a.g = c.g; a.render_base = c.render_base; a.blk_off = c.blk_off; a.blk_cnt = c.blk_cnt; a.blk_eff = c.blk_eff;
+    a.rec0 = c.brec0; a.rec1 = c.brec1; a.rec2 = c.brec2; a.bg = c.p->bg; a.n_contrib = c.n_contrib;
+    a.rec0_words = reinterpret_cast<unsigned int*>(c.brec0);
     a.refine_masks = (c.p->flags & SGR_FLAG_FORWARD_ONLY) ? 0 : 1;
     a.tile_time = (c.p->flags & SGR_FLAG_TILE_TIMING) ? c.tile_time : nullptr;
-    a.out_color = out_color; a.out_depth = out_depth; a.out_alpha = out_alpha;
-    a.ck0 = c.ck0; a.ck1 = c.ck1;
+    a.out_color = out_color; a.out_depth = out_depth; a.out_alpha = out_alpha; a.out_feed = out_feed;
+    a.clamp_mask = c.clamp_mask;
+    a.ck0 = c.ck0; a.ck1 = c.ck1; a.plan = c.plan; a.bwd_items = c.bwd_items; a.bwd_items_stride = c.bwd_items_stride;
     a.work_blend = c.work_blend; a.work_empty = c.work_empty; a.wc = c.work_counts;
     a.clamp_color = ((c.p->flags & SGR_FLAG_CLAMP_COLOR) || c.loss_target) ? 1 : 0;
     a.loss_target = c.loss_target; a.loss_mask = c.loss_mask; a.loss_dL_dcolor = c.loss_dL_dcolor;
     a.loss_part = c.loss_part; a.loss_scale = c.loss_scale;
     constexpr size_t smem = sizeof(FwdSmem) * kWarpsPerCta;
-    static int per_sm_dev[kMaxDevices] = {};
-    int& per_sm = per_sm_dev[current_device_slot()];
+    const bool exact = (c.p->flags & SGR_FLAG_EXACT_EXP) != 0;
+    static int per_sm_dev[kMaxDevices][2] = {};
+    int& per_sm = per_sm_dev[current_device_slot()][exact ? 1 : 0];
     if (per_sm == 0) {
-        cudaError_t e = prepare_kernel(blend_forward_kernel, smem, &per_sm);
+        cudaError_t e = exact ? prepare_kernel(blend_forward_kernel<true>, smem, &per_sm)
+                              : prepare_kernel(blend_forward_kernel<false>, smem, &per_sm);
         if (e != cudaSuccess) return e;
     }
     const long long items = (long long)c.num_renders * c.g.num_tiles * kBlocksPerTile;
@@ -897,7 +1005,8 @@ cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out
     if (ctas_override < 0) { const char* v = getenv("SGR_FWD_CTAS_PER_SM"); ctas_override = v ? atoi(v) : 0; }
     const int use_per_sm = ctas_override > 0 ? min(ctas_override, per_sm) : per_sm;
     const int grid = int(min((long long)num_sms() * use_per_sm, (items + kWarpsPerCta - 1) / kWarpsPerCta));
-    blend_forward_kernel<<<grid, kBlendThreads, smem, c.stream>>>(a);
+    if (exact) blend_forward_kernel<true><<<grid, kBlendThreads, smem, c.stream>>>(a);
+    else blend_forward_kernel<false><<<grid, kBlendThreads, smem, c.stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -907,35 +1016,37 @@ cudaError_t launch_loss_reduce(const ChunkCtx& c, float* loss_out) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_blend_backward(const ChunkCtx& c, const float* out_alpha, const float* dL_dcolor,
-                                  const float* dL_ddepth, const float* dL_dalpha) {
-    BwdArgs a;
-    a.g = c.g; a.render_base = c.render_base; a.tile_off = c.tile_off; a.tile_cnt = c.tile_cnt;
-    a.sorted_ids = c.sorted_ids; a.rec0 = c.rec0; a.rec1 = c.rec1; a.rec2 = c.rec2; a.bg = c.p->bg;
-    a.n_contrib = c.n_contrib; a.out_alpha = out_alpha; a.dL_dcolor = dL_dcolor; a.dL_ddepth = dL_ddepth;
-    a.dL_dalpha = dL_dalpha; a.accum = c.accum; a.plane = size_t(c.num_renders) * c.g.N;
-    a.ck0 = c.ck0; a.ck1 = c.ck1; a.work_seg = c.work_seg; a.plan = c.plan; a.dL_scale = c.dL_scale;
+namespace {
+template <bool kDA, bool kExact>
+cudaError_t launch_bwd_variant(const BwdArgs& a, long long want, cudaStream_t stream) {
     constexpr size_t smem = sizeof(BwdSmem) * kWarpsPerCta;
+    static int per_sm_dev[kMaxDevices] = {};
+    int& per_sm = per_sm_dev[current_device_slot()];
+    if (per_sm == 0) {
+        cudaError_t e = prepare_kernel(blend_backward_kernel<kDA, kExact>, smem, &per_sm);
+        if (e != cudaSuccess) return e;
+    }
+    blend_backward_kernel<kDA, kExact><<<int(min((long long)num_sms() * per_sm, want)), kBlendThreads, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t launch_blend_backward(const ChunkCtx& c, const SgrBackwardArgs& b) {
+    BwdArgs a;
+    a.g = c.g; a.render_base = c.render_base; a.blk_off = c.blk_off; a.blk_cnt = c.blk_cnt; a.blk_eff = c.blk_eff;
+    a.bids = c.bids; a.rec0 = c.brec0; a.rec1 = c.brec1; a.rec2 = c.brec2; a.bg = c.p->bg;
+    a.n_contrib = c.n_contrib; a.out_alpha = b.out_alpha; a.dL_dcolor = b.dL_dcolor; a.dL_ddepth = b.dL_ddepth;
+    a.dL_dalpha = b.dL_dalpha; a.loss_dL_dcolor = b.loss_dL_dcolor; a.dL_dfeed = b.dL_dlpips_feed;
+    a.clamp_mask = ((c.p->flags & SGR_FLAG_CLAMP_COLOR) || b.fused_clamp) ? c.clamp_mask : nullptr;
+    a.accum = c.accum; a.plane = size_t(c.num_renders) * c.g.N;
+    a.ck0 = c.ck0; a.ck1 = c.ck1; a.bwd_items = c.bwd_items; a.bwd_items_stride = c.bwd_items_stride;
+    a.plan = c.plan; a.dL_scale = b.dL_dcolor_scale;
     const long long items = (long long)c.num_renders * c.g.num_tiles * kBlocksPerTile;
     const long long want = (items + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (dL_ddepth || dL_dalpha) {
-        static int per_sm_dev[kMaxDevices] = {};
-        int& per_sm = per_sm_dev[current_device_slot()];
-        if (per_sm == 0) {
-            cudaError_t e = prepare_kernel(blend_backward_kernel<true>, smem, &per_sm);
-            if (e != cudaSuccess) return e;
-        }
-        blend_backward_kernel<true><<<int(min((long long)num_sms() * per_sm, want)), kBlendThreads, smem, c.stream>>>(a);
-    } else {
-        static int per_sm_dev[kMaxDevices] = {};
-        int& per_sm = per_sm_dev[current_device_slot()];
-        if (per_sm == 0) {
-            cudaError_t e = prepare_kernel(blend_backward_kernel<false>, smem, &per_sm);
-            if (e != cudaSuccess) return e;
-        }
-        blend_backward_kernel<false><<<int(min((long long)num_sms() * per_sm, want)), kBlendThreads, smem, c.stream>>>(a);
-    }
-    return cudaGetLastError();
+    const bool exact = (c.p->flags & SGR_FLAG_EXACT_EXP) != 0;
+    if (b.dL_ddepth || b.dL_dalpha)
+        return exact ? launch_bwd_variant<true, true>(a, want, c.stream) : launch_bwd_variant<true, false>(a, want, c.stream);
+    return exact ? launch_bwd_variant<false, true>(a, want, c.stream) : launch_bwd_variant<false, false>(a, want, c.stream);
 }
 
 }  // namespace sgr

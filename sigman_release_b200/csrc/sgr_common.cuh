@@ -11,12 +11,17 @@ namespace sgr {
 constexpr int kTile = 16;                 // BLOCK_X = BLOCK_Y of the published algorithm
 constexpr int kTilePixels = kTile * kTile;
 constexpr int kDefaultRendersPerChunk = 16;
-// Backward work granularity: a tile's depth-ordered list is replayed in independent segments of kSegment records
-// (multiple of the blend kernels' 64-record batch).  The forward blend checkpoints every pixel's running state at the
-// segment boundaries of lists longer than one segment; slot (tile, s) = tile_off / (kSegment / 2) + s, s < #segments,
-// the last slot holding the final state (a list of n > kSegment records spans at least ceil(n / kSegment) slots).
-constexpr int kSegment = 1024;
-constexpr int kCkptPerSlot = kTilePixels;   // one entry per pixel of the tile: [8 blocks][32 lanes]
+constexpr int kBlocksPerTile = 8;            // a 16x16 tile = eight 8x4 pixel blocks (blk = (y block) * 2 + (x block))
+// Block lists: the per-tile sort emits, for every 8x4 pixel block of a tile, the depth-ordered sub-list of the tile's
+// instances whose conservative extent touches the block ("block records": the 48-byte record + the Gaussian id).  The
+// blend kernels stream block lists, so a warp never fetches or culls a record that cannot touch its pixels.
+// Backward work granularity: a block list is replayed in independent segments of kSegB block records (multiple of the
+// blend kernels' batch).  The forward blend checkpoints every pixel's running state at the segment boundaries of
+// lists longer than one segment; slot (block list, s) = blk_off / (kSegB / 2) + s, s < #segments, the last slot
+// holding the final state (a list of m > kSegB records spans at least ceil(m / kSegB) slots of that numbering).
+constexpr int kSegB = 256;
+constexpr int kCkptPerSlot = 32;             // one entry per pixel of the block
+constexpr int kBwdClasses = 4;               // backward items by number of records that really blended (most first)
 
 // ------------------------------------------------------------------------------------------------
 // Device-resident status / counters at the start of `state`.
@@ -25,37 +30,45 @@ constexpr int kCkptPerSlot = kTilePixels;   // one entry per pixel of the tile: 
 struct alignas(256) StateHeader {
     unsigned long long inst_required;      // total instances all renders need (even when overflowing)
     unsigned long long capacity;
-    unsigned int overflow;
+    unsigned int overflow;                 // bit 0: instances, bit 1: block records
     unsigned int max_tile_instances;
     unsigned int nonempty_tiles;
     unsigned int pad;
+    unsigned long long blk_required;       // block records all renders need (bump cursor of the tile sorts)
+    unsigned long long blk_capacity;
     unsigned long long inst_cursor;        // instances consumed so far (global offset of the next chunk)
 };
-static_assert(sizeof(SgrStatus) == 32, "SgrStatus layout is part of the ABI");
+static_assert(sizeof(SgrStatus) == 48, "SgrStatus layout is part of the ABI");
 
-// Backward work list of one chunk, planned by the forward (kept in `state`): items work_seg[seg_base .. + n_seg).
+// Backward work lists of one chunk (kept in `state`; filled by the forward blend, consumed by the backward blend):
+// class c holds n_items[c] items at bwd_items[c * items_stride + item_base ...].
 struct ChunkPlan {
-    unsigned int n_seg, seg_base, seg_cursor, pad;
+    unsigned int n_items[kBwdClasses];
+    unsigned int item_base, cursor, pad0, pad1;
 };
 
 // Layout of `state` (kept forward -> backward) for a problem shape.
 struct StateLayout {
-    uint64_t header, tile_off, tile_cnt, tile_time, n_contrib, sorted_ids, rec0, rec1, rec2, ck0, ck1, plan, work_seg, total;
+    uint64_t header, tile_off, tile_cnt, tile_time, n_contrib, clamp_mask, sorted_ids, rec0, rec1, rec2, blk_off, blk_cnt,
+        blk_eff, brec0, brec1, brec2, bids, ck0, ck1, plan, bwd_items, bwd_items_stride, total;
 };
 // Layout of `scratch` (valid only inside one call).
 struct ScratchLayout {
-    uint64_t keys, g0, g1, g2, rect, cursor, work_blend, work_empty, work_counts, loss_part, accum, total;
+    uint64_t keys, keys_tmp, g0, g1, g2, rect, cursor, work_blend, work_empty, work_counts, loss_part, accum, total;
 };
 
 __host__ __device__ inline uint64_t align_up(uint64_t x, uint64_t a = 256) { return (x + a - 1) / a * a; }
 
 inline int tiles_x(int W) { return (W + kTile - 1) / kTile; }
 inline int tiles_y(int H) { return (H + kTile - 1) / kTile; }
-inline uint64_t ckpt_slots(uint64_t cap) { return cap / (kSegment / 2) + 2; }
+inline uint64_t ckpt_slots(uint64_t capB) { return capB / (kSegB / 2) + 2; }
 
-inline StateLayout make_state_layout(int B, int V, int N, int H, int W, uint64_t cap) {
+// `simple`: SGR_FLAG_SIMPLE_BLEND keeps tile-level records (the upstream-shaped kernels walk whole tile lists) and no
+// block lists; the default path keeps block lists and no tile-level records.
+inline StateLayout make_state_layout(int B, int V, int N, int H, int W, uint64_t cap, uint64_t capB, bool simple) {
     (void)N;
     const uint64_t R = uint64_t(B) * V, T = uint64_t(tiles_x(W)) * tiles_y(H), P = uint64_t(H) * W;
+    const uint64_t rec_cap = simple ? cap : 0, blk_cap = simple ? 0 : capB;
     StateLayout L;
     uint64_t o = 0;
     L.header = o;      o = align_up(o + sizeof(StateHeader));
@@ -63,14 +76,24 @@ inline StateLayout make_state_layout(int B, int V, int N, int H, int W, uint64_t
     L.tile_cnt = o;    o = align_up(o + R * T * 4);
     L.tile_time = o;   o = align_up(o + R * T * 8);     // (start ns, duration ns) of the forward blend per tile
     L.n_contrib = o;   o = align_up(o + R * P * 4);
+    L.clamp_mask = o;  o = align_up(o + R * P);         // bit c: channel c of the pixel was clamped (SGR_FLAG_CLAMP_COLOR)
     L.sorted_ids = o;  o = align_up(o + cap * 4);
-    L.rec0 = o;        o = align_up(o + cap * 16);
-    L.rec1 = o;        o = align_up(o + cap * 16);
-    L.rec2 = o;        o = align_up(o + cap * 16);
-    L.ck0 = o;         o = align_up(o + ckpt_slots(cap) * kCkptPerSlot * 16);   // (T, C0, C1, C2) per pixel and slot
-    L.ck1 = o;         o = align_up(o + ckpt_slots(cap) * kCkptPerSlot * 4);    // D
-    L.plan = o;        o = align_up(o + R * sizeof(ChunkPlan));                 // one per chunk (at most R chunks)
-    L.work_seg = o;    o = align_up(o + (R * T + cap / kSegment + R + 1) * 8);  // backward (tile, segment) items
+    L.rec0 = o;        o = align_up(o + rec_cap * 16);
+    L.rec1 = o;        o = align_up(o + rec_cap * 16);
+    L.rec2 = o;        o = align_up(o + rec_cap * 16);
+    L.blk_off = o;     o = align_up(o + R * T * kBlocksPerTile * 4);
+    L.blk_cnt = o;     o = align_up(o + R * T * kBlocksPerTile * 4);
+    L.blk_eff = o;     o = align_up(o + R * T * kBlocksPerTile * 4);
+    L.brec0 = o;       o = align_up(o + blk_cap * 16);
+    L.brec1 = o;       o = align_up(o + blk_cap * 16);
+    L.brec2 = o;       o = align_up(o + blk_cap * 16);
+    L.bids = o;        o = align_up(o + blk_cap * 4);
+    L.ck0 = o;         o = align_up(o + ckpt_slots(blk_cap) * kCkptPerSlot * 16);   // (T, C0, C1, C2) per pixel and slot
+    L.ck1 = o;         o = align_up(o + ckpt_slots(blk_cap) * kCkptPerSlot * 4);    // D
+    L.plan = o;        o = align_up(o + R * sizeof(ChunkPlan));                     // one per chunk (at most R chunks)
+    // backward items: a chunk of n tiles and m block records emits at most 8 n + m / kSegB items per class
+    L.bwd_items_stride = R * T * kBlocksPerTile + blk_cap / kSegB + R + 1;
+    L.bwd_items = o;   o = align_up(o + L.bwd_items_stride * kBwdClasses * 8);
     L.total = o;
     return L;
 }
@@ -83,6 +106,7 @@ inline ScratchLayout make_scratch_layout(int B, int V, int N, int H, int W, uint
     ScratchLayout L;
     uint64_t o = 0;
     L.keys = o;        o = align_up(o + cap * 8);
+    L.keys_tmp = o;    o = align_up(o + cap * 8);
     L.g0 = o;          o = align_up(o + Rc * N * 16);
     L.g1 = o;          o = align_up(o + Rc * N * 16);
     L.g2 = o;          o = align_up(o + Rc * N * 16);
@@ -143,6 +167,16 @@ __device__ __forceinline__ float exp_core(float x) {
     p = __fmaf_rn(p, r, 1.0f);
     p = __fmaf_rn(p, r, 1.0f);
     return __int_as_float(__float_as_int(p) + (__float_as_int(tn) << 23));
+}
+
+// exp_fast: exp(x) = 2^(x * log2(e)) on the SFU (MUFU.EX2, ~2 ulp) — what upstream's own `exp(power)` compiles to.
+// One FMUL + one MUFU instead of exp_core's 12 fma-pipe instructions; not bit-reproducible on a CPU, so the blend
+// kernels built on it are compared with the oracle to a tolerance (kExactExp = false, the default) while the
+// exp_core instantiation (SGR_FLAG_EXACT_EXP) stays bit-exact.
+__device__ __forceinline__ float exp_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(__fmul_rn(x, 1.44269502162933349609375f)));
+    return y;
 }
 
 __device__ __forceinline__ float exp_spec(float x) {
@@ -210,14 +244,21 @@ struct ChunkCtx {
     uint2* tile_time;         // [R*T]
     unsigned int* n_contrib;  // [R*P]
     unsigned int* sorted_ids; // [cap]
-    float4 *rec0, *rec1, *rec2;   // [cap]
-    float4* ck0;              // [ckpt_slots][256] forward checkpoints (T, C0, C1, C2)
-    float* ck1;               // [ckpt_slots][256] forward checkpoints D
+    float4 *rec0, *rec1, *rec2;   // [cap] tile-level records (SGR_FLAG_SIMPLE_BLEND only)
+    unsigned char* clamp_mask; // [R*P]
+    unsigned int *blk_off, *blk_cnt, *blk_eff;   // [R*T*8] block lists: start, records, records the backward replays
+    float4 *brec0, *brec1, *brec2;               // [capB] block records
+    unsigned int* bids;                          // [capB] Gaussian id of every block record
+    unsigned long long blk_capacity;
+    float4* ck0;              // [ckpt_slots][32] forward checkpoints (T, C0, C1, C2)
+    float* ck1;               // [ckpt_slots][32] forward checkpoints D
     ChunkPlan* plan;          // this chunk's backward plan
-    uint2* work_seg;          // [R*T + cap/kSegment + R + 1] backward items of all chunks
+    uint2* bwd_items;         // [kBwdClasses][bwd_items_stride] backward (block, segment) items of all chunks
+    unsigned long long bwd_items_stride;
     int chunk_index;
     // scratch
     unsigned long long* keys; // [cap]
+    unsigned long long* keys_tmp; // [cap] bucket-ordered keys of tile lists that exceed the sort's shared memory
     float4 *g0, *g1, *g2;     // [Rc*N]
     uint2* rect;              // [Rc*N] packed tile rectangle
     unsigned int* cursor;     // [Rc*T]
@@ -225,11 +266,10 @@ struct ChunkCtx {
     WorkCounts* work_counts;
     float* loss_part;         // [Rc*T*8] fused-loss partial sums, one per (render, tile, pixel block)
     float* accum;             // [kAccumPlanes][Rc*N]
-    // optional fused loss (forward) / upstream gradient scalar (backward)
+    // optional fused loss (forward)
     const float *loss_target, *loss_mask;
     float* loss_dL_dcolor;
     float loss_scale;
-    const float* dL_scale;
     cudaStream_t stream;
 };
 
@@ -237,10 +277,10 @@ cudaError_t launch_preprocess(const ChunkCtx& c, int32_t* radii);
 cudaError_t launch_plan(const ChunkCtx& c);   // tile offsets, sort / blend / backward-segment work lists, status header
 cudaError_t launch_scatter(const ChunkCtx& c);
 cudaError_t launch_sort_tiles(const ChunkCtx& c);
-cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out_depth, float* out_alpha);
+cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out_depth, float* out_alpha,
+                                 float* out_feed);
 cudaError_t launch_loss_reduce(const ChunkCtx& c, float* loss_out);   // fused loss: sum of the chunk's partials
-cudaError_t launch_blend_backward(const ChunkCtx& c, const float* out_alpha, const float* dL_dcolor,
-                                  const float* dL_ddepth, const float* dL_dalpha);
+cudaError_t launch_blend_backward(const ChunkCtx& c, const SgrBackwardArgs& b);
 cudaError_t launch_preprocess_backward(const ChunkCtx& c, const SgrBackwardArgs& a);
 cudaError_t launch_mark_visible(const float* means3D, int N, const float* view, uint8_t* visible, cudaStream_t s);
 cudaError_t launch_cov3d_from_scale_rot(const float* scales, const float* rots, float mod, int N, float* cov6,

@@ -40,28 +40,58 @@ class GaussianRasterizationSettings(NamedTuple):
 
 
 # ------------------------------------------------------------------------------------------------ workspace policy
-# Number of (Gaussian, tile) instances is data dependent and counted on the device.  The shim sizes the instance
-# arrays from a per-shape estimate; the first call for a shape (and every call in "sync" mode) reads the device status
-# back and retries on overflow, later calls in "deferred" mode fetch the status with an asynchronous copy that is
-# verified when the backward pass (or the next call) runs.
+# The number of (Gaussian, tile) instances is data dependent and counted on the device.  The shim sizes the instance
+# arrays from a per-shape estimate (1.5x the largest requirement seen).  How an overflow of that estimate is caught:
+#   * the first call for a shape, every call of the per-view ``GaussianRasterizer`` module (the zero-change drop-in:
+#     upstream reads ``num_rendered`` back per view as well) and every call in ``SGR_OVERFLOW_CHECK=sync`` mode read
+#     the device status back and grow + retry INSIDE the call: their outputs are never wrong;
+#   * batched calls in the default ``deferred`` mode fetch the status with an asynchronous 64-byte copy.  A forward
+#     that a backward follows is verified at the END of that backward's launch sequence (the host waits for the
+#     forward's status copy while the GPU already works on the queued backward kernels: no idle time), so an
+#     overflowed step raises ``SgrError`` out of ``loss.backward()`` — before its gradients can be consumed;
+#   * a forward-only (no-grad) deferred call cannot be repaired after the fact: the overflow is reported with a
+#     ``RuntimeWarning`` by the next rasteriser call and raised by ``check_status()``; it never raises out of an
+#     unrelated later forward.
 _OVERFLOW_MODE = os.environ.get("SGR_OVERFLOW_CHECK", "deferred")      # "sync" | "deferred"
 _HEADROOM = 1.5
 _est_per_render: dict = {}
 _max_tile_hint: dict = {}      # (N, H, W) -> longest per-tile list observed (sizes the long-list sort's shared memory)
 _last_status: Optional[dict] = None
-_pending: list = []            # deferred status checks: (event, pinned tensor, key, renders)
+_pending: list = []            # deferred status checks, in launch order
+_unreported: list = []         # overflow messages of forward-only calls, raised by check_status()
+
+
+class _Pending:
+    """One deferred status copy: pinned 64-byte buffer + the event recorded behind the copy."""
+    __slots__ = ("ev", "pinned", "key", "R", "has_backward", "done", "status")
+
+    def __init__(self, ev, pinned, key, R, has_backward):
+        self.ev, self.pinned, self.key, self.R, self.has_backward = ev, pinned, key, R, has_backward
+        self.done, self.status = False, None
 
 
 def last_status() -> Optional[dict]:
-    """Status block of the most recent synchronously checked forward (instances, longest tile list, ...)."""
+    """Status block of the most recent checked forward (instances, longest tile list, ...)."""
     return _last_status
+
+
+_STATUS_FIELDS = ("instances_required", "instances_capacity", "overflow", "max_tile_instances", "nonempty_tiles",
+                  "block_records_required", "block_records_capacity")
 
 
 def _status_from_bytes(t: torch.Tensor) -> dict:
     st = _native.SgrStatus.from_buffer_copy(bytes(t.numpy().tobytes()[: ctypes.sizeof(_native.SgrStatus)]))
-    return dict(instances_required=int(st.instances_required), instances_capacity=int(st.instances_capacity),
-                overflow=int(st.overflow), max_tile_instances=int(st.max_tile_instances),
-                nonempty_tiles=int(st.nonempty_tiles))
+    return {f: int(getattr(st, f)) for f in _STATUS_FIELDS}
+
+
+def _note_status(key, R, st: dict) -> dict:
+    """Folds a status block into the per-shape capacity estimates (instances and block records per render)."""
+    _max_tile_hint[key[1:]] = max(_max_tile_hint.get(key[1:], 0), st["max_tile_instances"])
+    per = int(st["instances_required"] / max(R, 1) * _HEADROOM) + 1024
+    per_blk = int(st["block_records_required"] / max(R, 1) * _HEADROOM) + 2048
+    old = _est_per_render.get(key, (0, 0))
+    _est_per_render[key] = (max(old[0], per), max(old[1], per_blk))
+    return st
 
 
 _status_pool: list = []        # recycled (pinned 64-byte buffer, event) pairs of the deferred status copies
@@ -73,31 +103,52 @@ def _status_slot():
     return torch.empty((64,), dtype=torch.uint8, pin_memory=True), torch.cuda.Event()
 
 
-def _drain_pending(block: bool) -> None:
+def _overflow_message(st: dict) -> str:
+    return (f"the render overflowed its instance capacity ({st['instances_required']} (Gaussian, tile) instances "
+            f"needed, {st['instances_capacity']} available; {st['block_records_required']} block records needed, "
+            f"{st['block_records_capacity']} available): the dropped renders / tiles are background-only.  The "
+            "estimate has been raised; re-run the step (or set SGR_OVERFLOW_CHECK=sync).")
+
+
+def _complete(entry: "_Pending") -> dict:
+    """Waits for the entry's status copy, folds it into the per-shape estimates and recycles its buffers."""
     global _last_status
-    keep = []
-    todo = list(_pending)
-    for idx, (ev, pinned, key, R) in enumerate(todo):
-        if not block and not ev.query():
-            # status copies complete in launch order: everything behind the first unfinished one is left unpolled
-            keep.extend(todo[idx:])
-            break
-        ev.synchronize()
-        st = _status_from_bytes(pinned)
-        _status_pool.append((pinned, ev))
-        _last_status = st
-        _max_tile_hint[key[1:]] = max(_max_tile_hint.get(key[1:], 0), st["max_tile_instances"])
-        per = int(st["instances_required"] / max(R, 1) * _HEADROOM) + 1024
-        _est_per_render[key] = max(_est_per_render.get(key, 0), per)
-        if st["overflow"]:
-            _pending[:] = keep + todo[idx + 1:]
-            raise _native.SgrError(
-                _native.SGR_E_INSTANCE_OVERFLOW,
-                f"a previous deferred-check render overflowed its instance capacity "
-                f"({st['instances_required']} needed, {st['instances_capacity']} available); its outputs are "
-                "background-only for the dropped renders.  The estimate has been raised; re-run the step "
-                "(or set SGR_OVERFLOW_CHECK=sync).")
-    _pending[:] = keep
+    if entry.done:
+        return entry.status
+    entry.ev.synchronize()
+    st = _status_from_bytes(entry.pinned)
+    _status_pool.append((entry.pinned, entry.ev))
+    entry.done, entry.status, entry.pinned, entry.ev = True, st, None, None
+    _last_status = _note_status(entry.key, entry.R, st)
+    return st
+
+
+def _drain_pending(block: bool) -> None:
+    """Polls (or waits for) the deferred status copies in launch order.  Never raises: an overflowed forward with a
+    backward is reported by that backward (``_verify``), a forward-only one by a warning here and by check_status()."""
+    while _pending:
+        entry = _pending[0]
+        if not entry.done and not block and not entry.ev.query():
+            break                  # copies complete in launch order: everything behind stays unpolled
+        _pending.pop(0)
+        if entry.done:
+            continue
+        st = _complete(entry)
+        if st["overflow"] and not entry.has_backward:
+            msg = "a forward-only render: " + _overflow_message(st)
+            _unreported.append(msg)
+            import warnings
+            warnings.warn(msg, RuntimeWarning, stacklevel=3)
+
+
+def _verify(entry: Optional["_Pending"]) -> None:
+    """Same-step verification of a deferred forward (called at the end of its backward): raises on overflow."""
+    if entry is None:
+        return
+    st = _complete(entry)
+    if st["overflow"]:
+        raise _native.SgrError(_native.SGR_E_INSTANCE_OVERFLOW, "this step's forward: " + _overflow_message(st) +
+                               "  The gradients of this step must be discarded.")
 
 
 _graph_status: dict = {}       # device index -> persistent pinned status buffer of graph-captured forwards
@@ -122,30 +173,37 @@ def graph_status(device=None) -> Optional[dict]:
     st = _status_from_bytes(buf)
     if st["overflow"]:
         raise _native.SgrError(_native.SGR_E_INSTANCE_OVERFLOW,
-                               f"a graph replay overflowed its instance capacity ({st['instances_required']} needed, "
-                               f"{st['instances_capacity']} available); re-run eagerly and re-capture")
+                               f"a graph replay overflowed its instance capacity ({st['instances_required']} instances "
+                               f"needed, {st['instances_capacity']} available; {st['block_records_required']} block "
+                               f"records needed, {st['block_records_capacity']} available); re-run eagerly and re-capture")
     return st
 
 
 def check_status() -> Optional[dict]:
     """Waits for every deferred overflow check (``SGR_OVERFLOW_CHECK=deferred``) and raises ``SgrError`` if a
-    forward since the last check ran out of instance capacity; returns the latest status block.  Call it where the
-    training loop synchronises anyway (logging, optimizer step)."""
+    forward-only render since the last check ran out of instance capacity (forwards with a backward are verified by
+    their own backward); returns the latest status block.  Call it after a batch of no-grad renders (eval orbits)."""
     _drain_pending(block=True)
+    if _unreported:
+        msg = _unreported[0] + (f" (+{len(_unreported) - 1} more)" if len(_unreported) > 1 else "")
+        _unreported.clear()
+        raise _native.SgrError(_native.SGR_E_INSTANCE_OVERFLOW, msg)
     return _last_status
 
 
 _bytes_cache: dict = {}
 
 
-def _buffer_bytes(L, B, V, N, H, W, cap, rpc):
+def _buffer_bytes(L, B, V, N, H, W, cap, cap_b, flags, rpc):
     """(state bytes, scratch bytes) of a problem shape (cached: the launch path is host-latency sensitive)."""
-    key = (B, V, N, H, W, cap, rpc)
+    simple = flags & _native.FLAG_SIMPLE_BLEND
+    key = (B, V, N, H, W, cap, cap_b, simple, rpc)
     got = _bytes_cache.get(key)
     if got is None:
         if len(_bytes_cache) > 256:
             _bytes_cache.clear()
-        got = (int(L.sgr_state_bytes(B, V, N, H, W, cap)), int(L.sgr_scratch_bytes(B, V, N, H, W, cap, rpc)))
+        got = (int(L.sgr_state_bytes(B, V, N, H, W, cap, cap_b, simple)),
+               int(L.sgr_scratch_bytes(B, V, N, H, W, cap, rpc)))
         _bytes_cache[key] = got
     return got
 
@@ -167,24 +225,27 @@ def _check_input(name: str, t: torch.Tensor, shape) -> torch.Tensor:
 
 
 def _fill_problem(p: _native.SgrProblem, B, V, N, H, W, tanfovx, tanfovy, means3D, cov3D, colors, opacities, viewm,
-                  projm, bg, cap, flags, rpc):
+                  projm, bg, cap, cap_b, flags, rpc):
     p.num_subjects, p.views_per_subject, p.num_gaussians = B, V, N
     p.image_height, p.image_width = H, W
     p.tanfovx, p.tanfovy = float(tanfovx), float(tanfovy)
     p.means3D, p.cov3D, p.colors, p.opacities = _ptr(means3D), _ptr(cov3D), _ptr(colors), _ptr(opacities)
     p.viewmatrix, p.projmatrix, p.bg = _ptr(viewm), _ptr(projm), _ptr(bg)
     p.max_instances = cap
+    p.max_block_records = cap_b
     p.renders_per_chunk = rpc
     p.flags = flags
     p.max_tile_instances_hint = _max_tile_hint.get((N, H, W), 0)
 
 
 class _RasterizeBatch(torch.autograd.Function):
-    """means3D [B,N,3], cov3D [B,N,6], colors [B,N,3], opacities [B,N], means2D [B,V,N,3] (gradient slot only)."""
+    """means3D [B,N,3], cov3D [B,N,6], colors [B,N,3], opacities [B,N], means2D [B,V,N,3] (gradient slot only).
+    Returns (color, radii, depth, alpha, loss | None, lpips_feed | None)."""
 
     @staticmethod
     def forward(ctx, means3D, cov3D, colors, opacities, means2D, viewmatrix, projmatrix, bg, H, W, tanfovx, tanfovy,
-                flags, renders_per_chunk, loss_target=None, loss_mask=None):
+                flags, renders_per_chunk, loss_target=None, loss_mask=None, loss_scale=None, force_sync=False,
+                want_feed=False):
         global _last_status
         L = _native.lib()
         B, N = int(means3D.shape[0]), int(means3D.shape[1])
@@ -200,7 +261,9 @@ class _RasterizeBatch(torch.autograd.Function):
             fused = loss_target is not None
             loss = torch.empty((), dtype=torch.float32, device=dev) if fused else None
             g_fused = torch.empty((B, V, 3, H, W), dtype=torch.float32, device=dev) if fused else None
+            feed = torch.empty((B, V, 3, H // 2, W // 2), dtype=torch.float32, device=dev) if want_feed else None
             key = (dev.index, N, H, W)
+            pending = None
             capturing = torch.cuda.is_current_stream_capturing()
             if not capturing:
                 _drain_pending(block=False)
@@ -209,24 +272,26 @@ class _RasterizeBatch(torch.autograd.Function):
             if capturing and first:
                 raise RuntimeError("run the step at least once before capturing it in a CUDA graph: the first call for "
                                    "a problem shape sizes the instance buffers with a synchronous status read")
-            per = _est_per_render.get(key, max(3 * N, 4096))
-            sync_check = (first or _OVERFLOW_MODE == "sync") and not capturing
+            per, per_blk = _est_per_render.get(key, (max(3 * N, 4096), max(6 * N, 8192)))
+            sync_check = (first or force_sync or _OVERFLOW_MODE == "sync") and not capturing
             while True:
                 cap = min(int(per) * R, (1 << 32) - 2)
-                state_bytes, scratch_bytes = _buffer_bytes(L, B, V, N, H, W, cap, renders_per_chunk)
+                cap_b = min(int(per_blk) * R, (1 << 32) - 2)
+                state_bytes, scratch_bytes = _buffer_bytes(L, B, V, N, H, W, cap, cap_b, flags, renders_per_chunk)
                 state = torch.empty((state_bytes,), dtype=torch.uint8, device=dev)
                 scratch = torch.empty((scratch_bytes,), dtype=torch.uint8, device=dev)
                 a = _native.SgrForwardArgs()
                 _fill_problem(a.p, B, V, N, H, W, tanfovx, tanfovy, means3D, cov3D, colors, opacities, viewmatrix,
-                              projmatrix, bg, cap, flags, renders_per_chunk)
+                              projmatrix, bg, cap, cap_b, flags, renders_per_chunk)
                 a.out_color, a.out_depth, a.out_alpha, a.radii = _ptr(color), _ptr(depth), _ptr(alpha), _ptr(radii)
                 a.state, a.state_bytes = _ptr(state), state_bytes
                 a.scratch, a.scratch_bytes = _ptr(scratch), scratch_bytes
                 a.stream = ctypes.c_void_p(stream.cuda_stream)
+                a.out_lpips_feed = _ptr(feed)
                 if fused:
                     a.loss_target, a.loss_mask = _ptr(loss_target), _ptr(loss_mask)
                     a.loss_dL_dcolor, a.loss_out = _ptr(g_fused), _ptr(loss)
-                    a.loss_scale = 1.0 / float(B * V * 3 * H * W)
+                    a.loss_scale = float(loss_scale)
                 _native.check(L.sgr_forward(ctypes.byref(a)))
                 if capturing:
                     # inside a CUDA graph capture: no events, no host reads.  The status block of every replay lands
@@ -237,72 +302,62 @@ class _RasterizeBatch(torch.autograd.Function):
                     pinned, ev = _status_slot()
                     pinned.copy_(state[:64], non_blocking=True)
                     ev.record(stream)
-                    _pending.append((ev, pinned, key, R))
+                    pending = _Pending(ev, pinned, key, R, has_backward=not (flags & _native.FLAG_FORWARD_ONLY))
+                    _pending.append(pending)
                     break
                 st = _native.SgrStatus()
                 rc = L.sgr_read_status(_ptr(state), ctypes.c_void_p(stream.cuda_stream), ctypes.byref(st))
                 if rc not in (_native.SGR_OK, _native.SGR_E_INSTANCE_OVERFLOW):
                     _native.check(rc)
-                need_per = int(st.instances_required / max(R, 1) * _HEADROOM) + 1024
-                _est_per_render[key] = max(_est_per_render.get(key, 0), need_per)
-                _max_tile_hint[key[1:]] = max(_max_tile_hint.get(key[1:], 0), int(st.max_tile_instances))
-                _last_status = dict(instances_required=int(st.instances_required),
-                                    instances_capacity=int(st.instances_capacity), overflow=int(st.overflow),
-                                    max_tile_instances=int(st.max_tile_instances),
-                                    nonempty_tiles=int(st.nonempty_tiles))
+                _last_status = _note_status(key, R, {f: int(getattr(st, f)) for f in _STATUS_FIELDS})
                 if rc == _native.SGR_OK:
                     break
-                if int(st.instances_required) >= (1 << 32) - 2:
-                    raise _native.SgrError(rc, "more than 2^32 (Gaussian, tile) instances in one call; split the batch")
-                per = _est_per_render[key]
+                if max(int(st.instances_required), int(st.block_records_required)) >= (1 << 32) - 2:
+                    raise _native.SgrError(rc, "more than 2^32 (Gaussian, tile) instances / block records in one call; "
+                                               "split the batch")
+                per, per_blk = _est_per_render[key]
                 del state, scratch
         ctx.save_for_backward(means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg, alpha, radii, state)
-        ctx.dims = (B, V, N, H, W, float(tanfovx), float(tanfovy), cap, flags, renders_per_chunk, state_bytes)
+        ctx.dims = (B, V, N, H, W, float(tanfovx), float(tanfovy), (cap, cap_b, flags), flags, renders_per_chunk,
+                    state_bytes)
         ctx.want_means2D = means2D is not None and means2D.requires_grad
-        ctx.set_materialize_grads(False)     # unused depth / alpha outputs arrive as None, not as zero tensors
+        ctx.set_materialize_grads(False)     # unused outputs arrive as None, not as zero tensors
         ctx.g_fused = g_fused
-        if fused:                            # only the loss is differentiable; the images are by-products
-            ctx.mark_non_differentiable(color, radii, depth, alpha)
-            return loss, color, radii, depth, alpha
+        ctx.pending = pending                # deferred overflow check of this forward, verified by its backward
         ctx.mark_non_differentiable(radii)
-        return color, radii, depth, alpha
+        return color, radii, depth, alpha, loss, feed
 
     @staticmethod
-    def backward(ctx, *grads):
-        if ctx.g_fused is not None:          # fused loss: dL/dcolour was written by the forward's epilogue
-            g_loss, g_color, g_depth, g_alpha = grads[0], ctx.g_fused, None, None
-            if g_loss is None:
-                return (None,) * 16
-            g_loss = g_loss.detach().to(device=ctx.g_fused.device, dtype=torch.float32).contiguous()
-        else:
-            g_loss = None
-            g_color, _g_radii, g_depth, g_alpha = grads
+    def backward(ctx, g_color, _g_radii, g_depth, g_alpha, g_loss, g_feed):
+        if g_color is None and g_depth is None and g_alpha is None and g_feed is None and \
+                (g_loss is None or ctx.g_fused is None):
+            return (None,) * 19
         L = _native.lib()
         means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg, alpha, radii, state = ctx.saved_tensors
-        B, V, N, H, W, tanfovx, tanfovy, cap, flags, rpc, state_bytes = ctx.dims
+        B, V, N, H, W, tanfovx, tanfovy, caps, flags, rpc, state_bytes = ctx.dims
+        cap, cap_b = caps[0], caps[1]
         dev = means3D.device
-        # Deferred overflow checks never block the launch path (a blocking wait here would idle the GPU for the whole
-        # launch latency of the backward): an overflow surfaces at the first rasteriser call after its status copy
-        # has landed, or at check_status().
+        # A deferred overflow check never blocks BEFORE the backward kernels are queued (a wait here would idle the GPU
+        # for the whole launch latency of the backward); this forward's status is verified right after the launch.
         if not torch.cuda.is_current_stream_capturing():
             _drain_pending(block=False)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev)
-            if g_color is None:
+            f32c = lambda t: None if t is None else t.detach().to(device=dev, dtype=torch.float32).contiguous()
+            g_color, g_depth, g_alpha, g_feed = f32c(g_color), f32c(g_depth), f32c(g_alpha), f32c(g_feed)
+            g_loss = f32c(g_loss) if ctx.g_fused is not None else None
+            if flags & _native.FLAG_SIMPLE_BLEND and g_color is None:
                 g_color = torch.zeros((B, V, 3, H, W), dtype=torch.float32, device=dev)
-            g_color = g_color.contiguous().float()
-            g_depth = None if g_depth is None else g_depth.contiguous().float()
-            g_alpha = None if g_alpha is None else g_alpha.contiguous().float()
             d_means3D = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
             d_cov3D = torch.empty((B, N, 6), dtype=torch.float32, device=dev)
             d_colors = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
             d_opac = torch.empty((B, N), dtype=torch.float32, device=dev)
             d_means2D = torch.empty((B, V, N, 3), dtype=torch.float32, device=dev) if ctx.want_means2D else None
-            scratch_bytes = _buffer_bytes(L, B, V, N, H, W, cap, rpc)[1]
+            scratch_bytes = _buffer_bytes(L, B, V, N, H, W, cap, cap_b, flags, rpc)[1]
             scratch = torch.empty((scratch_bytes,), dtype=torch.uint8, device=dev)
             a = _native.SgrBackwardArgs()
             _fill_problem(a.p, B, V, N, H, W, tanfovx, tanfovy, means3D, cov3D, colors, opacities, viewmatrix,
-                          projmatrix, bg, cap, flags, rpc)
+                          projmatrix, bg, cap, cap_b, flags, rpc)
             a.out_alpha, a.radii = _ptr(alpha), _ptr(radii)
             a.dL_dcolor, a.dL_ddepth, a.dL_dalpha = _ptr(g_color), _ptr(g_depth), _ptr(g_alpha)
             a.dL_dmeans3D, a.dL_dcov3D, a.dL_dcolors, a.dL_dopacities = (_ptr(d_means3D), _ptr(d_cov3D),
@@ -311,81 +366,131 @@ class _RasterizeBatch(torch.autograd.Function):
             a.state, a.state_bytes = _ptr(state), state_bytes
             a.scratch, a.scratch_bytes = _ptr(scratch), scratch_bytes
             a.stream = ctypes.c_void_p(stream.cuda_stream)
-            a.dL_dcolor_scale = _ptr(g_loss)
+            a.dL_dlpips_feed = _ptr(g_feed)
+            if ctx.g_fused is not None:
+                a.fused_clamp = 1
+                if g_loss is not None:           # the fused loss's own gradient, scaled by the upstream scalar
+                    a.loss_dL_dcolor, a.dL_dcolor_scale = _ptr(ctx.g_fused), _ptr(g_loss)
             _native.check(L.sgr_backward(ctypes.byref(a)))
-        return (d_means3D, d_cov3D, d_colors, d_opac, d_means2D) + (None,) * 11
+        # the GPU now works on the queued backward while the host waits for the forward's 64-byte status copy: an
+        # overflowed step raises here, out of loss.backward(), before anything can consume its gradients
+        _verify(ctx.pending)
+        return (d_means3D, d_cov3D, d_colors, d_opac, d_means2D) + (None,) * 14
+
+
+def _checked(means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg):
+    if means3D.dim() != 3 or means3D.shape[-1] != 3:
+        raise ValueError("means3D must be [B,N,3]")
+    B, N = int(means3D.shape[0]), int(means3D.shape[1])
+    if viewmatrix.dim() != 4 or tuple(viewmatrix.shape[2:]) != (4, 4) or int(viewmatrix.shape[0]) != B:
+        raise ValueError("viewmatrix must be [B,V,4,4]")
+    V = int(viewmatrix.shape[1])
+    if opacities.dim() == 3:
+        opacities = opacities.reshape(B, N)
+    return (B, N, V, _check_input("means3D", means3D, (B, N, 3)), _check_input("cov3D", cov3D, (B, N, 6)),
+            _check_input("colors", colors, (B, N, 3)), _check_input("opacities", opacities, (B, N)),
+            _check_input("viewmatrix", viewmatrix, (B, V, 4, 4)), _check_input("projmatrix", projmatrix, (B, V, 4, 4)),
+            _check_input("bg", bg, (3,)))
+
+
+def _common_flags(grad_inputs, exact_exp) -> int:
+    flags = _native.FLAG_EXACT_EXP if (exact_exp or _EXACT_EXP_ENV) else 0
+    if not (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in grad_inputs)):
+        flags |= _native.FLAG_FORWARD_ONLY           # no backward can follow: skip the forward's bookkeeping for it
+    if os.environ.get("SGR_TILE_TIMING"):            # diagnostics (tools/tile_timing.py)
+        flags |= _native.FLAG_TILE_TIMING
+    return flags
+
+
+_EXACT_EXP_ENV = os.environ.get("SGR_EXACT_EXP", "0") not in ("", "0")
 
 
 def rasterize_batch(means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg, image_height, image_width,
-                    tanfovx, tanfovy, means2D=None, clamp_color=False, simple_blend=False, renders_per_chunk=0):
+                    tanfovx, tanfovy, means2D=None, clamp_color=False, simple_blend=False, renders_per_chunk=0,
+                    sync_if_no_grad=False, exact_exp=False, lpips_feed=False):
     """Render B subjects x V views in one launch set.
 
     means3D [B,N,3], cov3D [B,N,6] (xx,xy,xz,yy,yz,zz — gs.py:32-37), colors [B,N,3], opacities [B,N] or [B,N,1],
     viewmatrix / projmatrix [B,V,4,4] in the layout of gs.py:89-90 (``cam_view``, ``cam_view_proj``), bg [3].
     Returns ``(color [B,V,3,H,W], radii [B,V,N] int32, depth [B,V,1,H,W], alpha [B,V,1,H,W])``; differentiable
     w.r.t. means3D, cov3D, colors, opacities (gradients summed over a subject's views) and, if given, the per-render
-    gradient slot ``means2D [B,V,N,3]``.  ``clamp_color`` fuses gs.py:107's ``clamp(0, 1)``.
+    gradient slot ``means2D [B,V,N,3]``.
+
+    * ``clamp_color`` fuses gs.py:107's ``clamp(0, 1)`` into the blend epilogue; the clamp's gradient mask is kept in
+      the rasteriser state and applied inside the backward kernel (no clamp kernel, no saved image).
+    * ``lpips_feed=True`` (needs ``clamp_color``; even H, W) appends a fifth output
+      ``F.interpolate(color * 2 - 1, (H/2, W/2), mode='bilinear', align_corners=False)`` computed in the same epilogue
+      (whole_loss.py:132-136), differentiable as well.
+    * ``exact_exp=True`` evaluates ``exp(power)`` with the oracle's IEEE fp32 sequence (bit-exact against
+      ``oracle/``); the default uses the SFU like upstream's own ``exp`` (see include/sgr.h SGR_FLAG_EXACT_EXP).
+    * ``sync_if_no_grad``: a call that no backward can follow checks its instance capacity synchronously (grow and
+      retry inside the call) instead of deferring the check — see the workspace policy at the top of this module.
     """
-    if means3D.dim() != 3 or means3D.shape[-1] != 3:
-        raise ValueError("means3D must be [B,N,3]")
-    B, N = int(means3D.shape[0]), int(means3D.shape[1])
-    if viewmatrix.dim() != 4 or tuple(viewmatrix.shape[2:]) != (4, 4) or int(viewmatrix.shape[0]) != B:
-        raise ValueError("viewmatrix must be [B,V,4,4]")
-    V = int(viewmatrix.shape[1])
-    if opacities.dim() == 3:
-        opacities = opacities.reshape(B, N)
-    means3D = _check_input("means3D", means3D, (B, N, 3))
-    cov3D = _check_input("cov3D", cov3D, (B, N, 6))
-    colors = _check_input("colors", colors, (B, N, 3))
-    opacities = _check_input("opacities", opacities, (B, N))
-    viewmatrix = _check_input("viewmatrix", viewmatrix, (B, V, 4, 4))
-    projmatrix = _check_input("projmatrix", projmatrix, (B, V, 4, 4))
-    bg = _check_input("bg", bg, (3,))
+    B, N, V, means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg = _checked(
+        means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg)
     if means2D is not None and tuple(means2D.shape) != (B, V, N, 3):
         raise ValueError("means2D must be [B,V,N,3]")
+    if lpips_feed and not clamp_color:
+        raise ValueError("lpips_feed needs clamp_color=True (the reference resizes the clamped image)")
     flags = (_native.FLAG_CLAMP_COLOR if clamp_color else 0) | (_native.FLAG_SIMPLE_BLEND if simple_blend else 0)
-    if not (torch.is_grad_enabled() and any(t is not None and t.requires_grad
-                                            for t in (means3D, cov3D, colors, opacities, means2D))):
-        flags |= _native.FLAG_FORWARD_ONLY           # no backward can follow: skip the forward's bookkeeping for it
-    if os.environ.get("SGR_TILE_TIMING"):            # diagnostics (tools/tile_timing.py)
-        flags |= _native.FLAG_TILE_TIMING
-    return _RasterizeBatch.apply(means3D, cov3D, colors, opacities, means2D, viewmatrix, projmatrix, bg,
-                                 int(image_height), int(image_width), float(tanfovx), float(tanfovy), flags,
-                                 int(renders_per_chunk), None, None)
+    flags |= _common_flags((means3D, cov3D, colors, opacities, means2D), exact_exp)
+    force_sync = bool(sync_if_no_grad) and bool(flags & _native.FLAG_FORWARD_ONLY)
+    color, radii, depth, alpha, _loss, feed = _RasterizeBatch.apply(
+        means3D, cov3D, colors, opacities, means2D, viewmatrix, projmatrix, bg, int(image_height), int(image_width),
+        float(tanfovx), float(tanfovy), flags, int(renders_per_chunk), None, None, None, force_sync, bool(lpips_feed))
+    return (color, radii, depth, alpha, feed) if lpips_feed else (color, radii, depth, alpha)
+
+
+def _loss_scale(reduction, B, V, H, W) -> float:
+    if isinstance(reduction, (int, float)):
+        return float(reduction)
+    if reduction == "reference":         # torch.sum(l1(pred * m, gt * m)) / (B * V), whole_loss.py:130,139
+        return 1.0 / float(B * V)
+    if reduction == "mean":
+        return 1.0 / float(B * V * 3 * H * W)
+    if reduction == "sum":
+        return 1.0
+    raise ValueError("reduction must be 'reference', 'mean', 'sum' or a number (the factor applied to the sum)")
 
 
 def render_l1_loss(means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg, image_height, image_width,
-                   tanfovx, tanfovy, target, mask=None, renders_per_chunk=0):
+                   tanfovx, tanfovy, target, mask=None, renders_per_chunk=0, reduction="reference", exact_exp=False,
+                   lpips_feed=False):
     """Render B x V views and evaluate SIGMAN's reconstruction loss in the blend epilogue.
 
-    Equivalent to ``image = rasterize_batch(...)[0].clamp(0, 1)`` (gs.py:107) followed by
-    ``l1(image * mask, target * mask)`` with mean reduction (/root/reference/core/loss/whole_loss.py:126-130), but the
-    loss, the clamp mask and dL/dcolour never leave the blend kernel: no elementwise torch kernels, no autograd
-    graph over the images.  ``target`` [B,V,3,H,W], ``mask`` [B,V,1,H,W] or None.  Returns
-    ``(loss, image [B,V,3,H,W] clamped, radii, depth, alpha)``; only ``loss`` is differentiable (w.r.t. means3D,
-    cov3D, colors, opacities).
+    Equivalent to ``image = rasterize_batch(...)[0].clamp(0, 1)`` (gs.py:107) followed by the reference's L1 term:
+    ``loss_l1 = l1(image * mask, target * mask)`` is an UNREDUCED ``|x - y|``
+    (/root/reference/core/loss/whole_loss.py:49-50,130) that the reference reduces as
+    ``torch.sum(loss_l1) / loss_l1.shape[0]`` with ``shape[0] = B * V`` (whole_loss.py:139) — a per-image sum
+    averaged over the B*V images, NOT a mean over elements.  ``reduction``:
+
+    * ``"reference"`` (default): ``sum / (B * V)``, the reference's weighting against its LPIPS / KL / GAN terms;
+    * ``"mean"``: ``sum / (B * V * 3 * H * W)``;  ``"sum"``: the plain sum;  a number: that factor times the sum.
+
+    The reference then divides by ``exp(logvar)`` (whole_loss.py:142): multiply the returned scalar by your device
+    scalar — the product's gradient reaches the backward kernel as a device scalar (``dL_dcolor_scale``), no sync.
+
+    The loss, the clamp mask and dL/dcolour never leave the blend kernel: no elementwise torch kernels and no saved
+    image-sized tensors for the L1 term.  ``target`` [B,V,3,H,W], ``mask`` [B,V,1,H,W] or None.  Returns
+    ``(loss, image [B,V,3,H,W] clamped, radii, depth, alpha)``.  ``loss`` is differentiable w.r.t. means3D, cov3D,
+    colors, opacities; ``image`` (the clamped render), ``depth`` and ``alpha`` are differentiable as well, so further
+    image-space terms (LPIPS on the resized image, the generator's GAN term — whole_loss.py:132-170) can be added on
+    top: their gradient w.r.t. the clamped image is masked by the forward's clamp mask inside the backward kernel and
+    added to the fused L1 gradient.  ``lpips_feed=True`` (even H, W) appends the LPIPS input of whole_loss.py:132-136,
+    ``F.interpolate(image * 2 - 1, (H/2, W/2), mode='bilinear', align_corners=False)``, computed in the same epilogue
+    and differentiable.  ``exact_exp``: see ``rasterize_batch``.
     """
-    if means3D.dim() != 3 or means3D.shape[-1] != 3:
-        raise ValueError("means3D must be [B,N,3]")
-    B, N = int(means3D.shape[0]), int(means3D.shape[1])
-    if viewmatrix.dim() != 4 or tuple(viewmatrix.shape[2:]) != (4, 4) or int(viewmatrix.shape[0]) != B:
-        raise ValueError("viewmatrix must be [B,V,4,4]")
-    V = int(viewmatrix.shape[1])
+    B, N, V, means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg = _checked(
+        means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg)
     H, W = int(image_height), int(image_width)
-    if opacities.dim() == 3:
-        opacities = opacities.reshape(B, N)
-    means3D = _check_input("means3D", means3D, (B, N, 3))
-    cov3D = _check_input("cov3D", cov3D, (B, N, 6))
-    colors = _check_input("colors", colors, (B, N, 3))
-    opacities = _check_input("opacities", opacities, (B, N))
-    viewmatrix = _check_input("viewmatrix", viewmatrix, (B, V, 4, 4))
-    projmatrix = _check_input("projmatrix", projmatrix, (B, V, 4, 4))
-    bg = _check_input("bg", bg, (3,))
     target = _check_input("target", target.detach(), (B, V, 3, H, W))
     if mask is not None:
         mask = _check_input("mask", mask.detach(), (B, V, 1, H, W))
-    return _RasterizeBatch.apply(means3D, cov3D, colors, opacities, None, viewmatrix, projmatrix, bg, H, W,
-                                 float(tanfovx), float(tanfovy), 0, int(renders_per_chunk), target, mask)
+    flags = _common_flags((means3D, cov3D, colors, opacities), exact_exp)
+    color, radii, depth, alpha, loss, feed = _RasterizeBatch.apply(
+        means3D, cov3D, colors, opacities, None, viewmatrix, projmatrix, bg, H, W, float(tanfovx), float(tanfovy),
+        flags, int(renders_per_chunk), target, mask, _loss_scale(reduction, B, V, H, W), False, bool(lpips_feed))
+    return (loss, color, radii, depth, alpha, feed) if lpips_feed else (loss, color, radii, depth, alpha)
 
 
 # ------------------------------------------------------------------------------------------------ optional inputs
@@ -494,7 +599,8 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
     color, radii, depth, alpha = rasterize_batch(
         means3D.reshape(1, N, 3), cov3D.reshape(1, N, 6), colors_precomp.reshape(1, N, 3), opacities.reshape(1, N),
         s.viewmatrix.to(dev, torch.float32).reshape(1, 1, 4, 4), s.projmatrix.to(dev, torch.float32).reshape(1, 1, 4, 4),
-        s.bg.to(dev, torch.float32).reshape(3), H, W, float(s.tanfovx), float(s.tanfovy), means2D=m2)
+        s.bg.to(dev, torch.float32).reshape(3), H, W, float(s.tanfovx), float(s.tanfovy), means2D=m2,
+        sync_if_no_grad=True)
     return color[0, 0], radii[0, 0], depth[0, 0], alpha[0, 0]
 
 

@@ -140,11 +140,10 @@ class GaussianRenderer:
         means3D, cov3D, rgbs, opacity = self.prepare(gaussians)
         bg = self.bg_color if bg_color is None else bg_color
         bg = bg.to(device=device, dtype=torch.float32)
-        needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (means3D, cov3D, rgbs, opacity))
-        # scale_modifier and cam_pos do not enter the cov3D_precomp / colors_precomp path
+        # scale_modifier and cam_pos do not enter the cov3D_precomp / colors_precomp path.
+        # gs.py:107 `rendered_image.clamp(0, 1)` is fused into the blend epilogue; its gradient mask lives in the
+        # rasteriser state and is applied inside the backward kernel (no clamp kernel, no saved image).
         image, _radii, _depth, alpha = rasterize_batch(
             means3D, cov3D, rgbs, opacity, cam_view.float(), cam_view_proj.float(), bg, H, W,
-            self.tan_half_fov, self.tan_half_fov, clamp_color=not needs_grad)
-        if needs_grad:
-            image = image.clamp(0, 1)                           # gs.py:107 (keeps torch's clamp gradient mask)
+            self.tan_half_fov, self.tan_half_fov, clamp_color=True)
         return {"image": image, "alpha": alpha}

@@ -31,6 +31,9 @@ def view_tensors(view_ids):
 
 
 def gpu_forward(sc, view_ids, H, W, bg=(1.0, 1.0, 1.0), simple=False, requires_grad=False, tensors=None, **kw):
+    """One batched forward through the C ABI.  exact_exp defaults to True here: the parity tests compare bit for bit
+    with the oracle's exp_spec; the default (SFU) exponential is covered by tests/test_gpu_fast_exp.py."""
+    kw.setdefault("exact_exp", True)
     t = tensors if tensors is not None else scene_tensors(sc, requires_grad)
     vmt, pmt, vm, pm = view_tensors(view_ids)
     out = rasterizer.rasterize_batch(t["means3D"], t["cov3D"], t["colors"], t["opacities"], vmt, pmt,
@@ -45,16 +48,19 @@ def oracle_forward(sc, vm, pm, H, W, bg=(1.0, 1.0, 1.0), dtype=np.float32):
     return r, out
 
 
-def debug_state(fn_ctx_state, B, V, N, H, W, cap, render):
-    """(tile_ranges [T,2], n_contrib [H,W], point_list) of one render from the saved state tensor of a forward."""
+def debug_state(fn_ctx_state, B, V, N, H, W, caps, render):
+    """(tile_ranges [T,2], n_contrib [H,W], point_list) of one render from the saved state tensor of a forward;
+    caps = dims[7] of the autograd node = (max_instances, max_block_records, flags)."""
     L = _native.lib()
+    cap, cap_b, flags = caps
     T = ((W + 15) // 16) * ((H + 15) // 16)
     ranges = torch.zeros((T, 2), dtype=torch.int32, device="cuda")
     ncon = torch.zeros((H, W), dtype=torch.int32, device="cuda")
     cap_pl = max(int(cap), 1)
     pl = torch.full((cap_pl,), -1, dtype=torch.int32, device="cuda")
     st = torch.cuda.current_stream()
-    _native.check(L.sgr_debug_copy_state(ctypes.c_void_p(fn_ctx_state.data_ptr()), B, V, N, H, W, int(cap), render,
+    _native.check(L.sgr_debug_copy_state(ctypes.c_void_p(fn_ctx_state.data_ptr()), B, V, N, H, W, int(cap), int(cap_b),
+                                         int(flags), render,
                                          ctypes.c_void_p(ranges.data_ptr()), ctypes.c_void_p(ncon.data_ptr()),
                                          ctypes.c_void_p(pl.data_ptr()), cap_pl, None,
                                          ctypes.c_void_p(st.cuda_stream)))

@@ -27,25 +27,48 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_native.SYMBOLS), declared ^ set(_native.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.sgr_abi_version() == _native.ABI_VERSION == 2
+    assert lib.sgr_abi_version() == _native.ABI_VERSION == 3
 
 
-def test_struct_layout_matches_header(lib):
-    assert ctypes.sizeof(_native.SgrStatus) == 32
-    assert ctypes.sizeof(_native.SgrProblem) == 112
-    assert ctypes.sizeof(_native.SgrForwardArgs) == 112 + 9 * 8 + 5 * 8      # + the fused-loss block
-    assert ctypes.sizeof(_native.SgrBackwardArgs) == 112 + 16 * 8
+def test_struct_layout_matches_header(lib, tmp_path):
+    """sizeof / offsetof of every ABI struct as the C compiler sees include/sgr.h == the ctypes mirror."""
+    import subprocess
+
+    structs = {"SgrProblem": _native.SgrProblem, "SgrForwardArgs": _native.SgrForwardArgs,
+               "SgrBackwardArgs": _native.SgrBackwardArgs, "SgrStatus": _native.SgrStatus}
+    lines = []
+    for name, cls in structs.items():
+        lines.append(f'printf("{name} %zu\\n", sizeof({name}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{name}.{fname} %zu\\n", offsetof({name}, {fname}));')
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "sgr.h"\nint main(void) {\n' + "\n".join(lines) +
+                   "\nreturn 0; }\n")
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for name, cls in structs.items():
+        assert int(got[name]) == ctypes.sizeof(cls), name
+        for fname, _ in cls._fields_:
+            assert int(got[f"{name}.{fname}"]) == getattr(cls, fname).offset, f"{name}.{fname}"
+    assert ctypes.sizeof(_native.SgrStatus) == 48 <= 64      # the shim's asynchronous status copies are 64 bytes
 
 
 def test_buffer_size_queries(lib):
-    a = lib.sgr_state_bytes(1, 8, 100_000, 512, 512, 2_000_000)
-    b = lib.sgr_state_bytes(1, 8, 100_000, 512, 512, 4_000_000)
-    assert 0 < a < b and a % 256 == 0
-    # per instance: 4-byte id + three 16-byte record streams; per 512 instances one checkpoint slot of 256 pixels x 20 B;
-    # per 1024 instances one 8-byte backward work item (regions are 256-byte aligned)
-    growth = 2_000_000 * 52 + (4_000_000 // 512 - 2_000_000 // 512) * 256 * 20 + (4_000_000 // 1024 - 2_000_000 // 1024) * 8
-    assert abs((b - a) - growth) <= 256
-    assert lib.sgr_state_bytes(0, 8, 10, 64, 64, 10) == 0
+    a = lib.sgr_state_bytes(1, 8, 100_000, 512, 512, 2_000_000, 3_000_000, 0)
+    b = lib.sgr_state_bytes(1, 8, 100_000, 512, 512, 2_000_000, 6_000_000, 0)
+    c = lib.sgr_state_bytes(1, 8, 100_000, 512, 512, 4_000_000, 6_000_000, 0)
+    assert 0 < a < b < c and a % 256 == 0
+    # per block record: three 16-byte record streams + 4-byte id; per 128 block records one checkpoint slot of 32 pixels
+    # x 20 B; per 256 block records one 8-byte backward work item in each of the 4 classes (regions 256-byte aligned)
+    growth = 3_000_000 * 52 + (6_000_000 // 128 - 3_000_000 // 128) * 32 * 20 + (6_000_000 // 256 - 3_000_000 // 256) * 8 * 4
+    assert abs((b - a) - growth) <= 8 * 256
+    assert abs((c - b) - 2_000_000 * 4) <= 256                  # per instance: the 4-byte id of the tile-level point list
+    # SGR_FLAG_SIMPLE_BLEND keeps tile-level records (48 B per instance) and no block lists
+    d = lib.sgr_state_bytes(1, 8, 100_000, 512, 512, 2_000_000, 3_000_000, _native.FLAG_SIMPLE_BLEND)
+    e = lib.sgr_state_bytes(1, 8, 100_000, 512, 512, 4_000_000, 3_000_000, _native.FLAG_SIMPLE_BLEND)
+    assert abs((e - d) - 2_000_000 * 52) <= 4 * 256
+    assert lib.sgr_state_bytes(0, 8, 10, 64, 64, 10, 10, 0) == 0
     s16 = lib.sgr_scratch_bytes(8, 10, 100_000, 512, 512, 20_000_000, 16)
     s80 = lib.sgr_scratch_bytes(8, 10, 100_000, 512, 512, 20_000_000, 80)
     assert 0 < s16 < s80

@@ -11,9 +11,12 @@ from sigman_release_b200 import rasterizer, scenes
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("reduction", ["reference", "mean"])
 @pytest.mark.parametrize("with_mask", [False, True])
 @pytest.mark.parametrize("hw", [(64, 64), (100, 75)])
-def test_fused_l1_loss_matches_unfused_and_oracle(with_mask, hw):
+def test_fused_l1_loss_matches_unfused_and_oracle(with_mask, hw, reduction):
+    """reduction="reference" is the reference's own: loss_l1 = |pred*m - gt*m| unreduced (whole_loss.py:49-50,130),
+    then torch.sum(loss_l1) / loss_l1.shape[0] with shape[0] = B*V (whole_loss.py:139)."""
     H, W = hw
     views = [30, 65, 8]
     sc = scenes.body_gaussians(4000, seed=3)
@@ -27,15 +30,17 @@ def test_fused_l1_loss_matches_unfused_and_oracle(with_mask, hw):
 
     a = scene_tensors(sc, requires_grad=True)
     loss, image, radii, depth, alpha = rasterizer.render_l1_loss(a["means3D"], a["cov3D"], a["colors"], a["opacities"],
-                                                                 vmt, pmt, bg, H, W, TAN, TAN, tt, mt)
+                                                                 vmt, pmt, bg, H, W, TAN, TAN, tt, mt,
+                                                                 reduction=reduction, exact_exp=True)
     (loss * 2.5).backward()
 
     b = scene_tensors(sc, requires_grad=True)
     color, radii_b, depth_b, alpha_b = rasterizer.rasterize_batch(b["means3D"], b["cov3D"], b["colors"], b["opacities"],
-                                                                  vmt, pmt, bg, H, W, TAN, TAN)
+                                                                  vmt, pmt, bg, H, W, TAN, TAN, exact_exp=True)
     img_b = color.clamp(0, 1)
     m = mt if with_mask else 1.0
-    loss_b = (img_b * m - tt * m).abs().mean()
+    l1 = (img_b * m - tt * m).abs()                                   # whole_loss.py:130 (l1() does not reduce)
+    loss_b = torch.sum(l1) / (l1.shape[0] * l1.shape[1]) if reduction == "reference" else l1.mean()
     (loss_b * 2.5).backward()
 
     assert torch.equal(image, img_b) and torch.equal(depth, depth_b) and torch.equal(alpha, alpha_b)
@@ -51,7 +56,7 @@ def test_fused_l1_loss_matches_unfused_and_oracle(with_mask, hw):
         _, ora = oracle_forward(sc, vm[v], pm[v], H, W, bg=(1.0, 0.9, 1.2))
         mm = mask[0, v] if with_mask else 1.0
         ref += np.abs(np.clip(ora.color, 0, 1).astype(np.float64) * mm - target[0, v] * mm).sum()
-    ref /= target.size
+    ref /= len(views) if reduction == "reference" else target.size
     assert abs(float(loss) - ref) <= 2e-6 * ref
 
 
@@ -67,13 +72,13 @@ def test_fused_loss_chunked_batches_and_scale_pointer():
     target = torch.rand((B, len(views), 3, H, W), device="cuda")
     bg = torch.ones(3, device="cuda")
     out = rasterizer.render_l1_loss(t["means3D"], t["cov3D"], t["colors"], t["opacities"], vmt, pmt, bg, H, W, TAN, TAN,
-                                    target, None, renders_per_chunk=2)
+                                    target, None, renders_per_chunk=2, reduction="mean")
     out[0].backward()
     g1 = {k: v.grad.clone() for k, v in t.items()}
     for v in t.values():
         v.grad = None
     out2 = rasterizer.render_l1_loss(t["means3D"], t["cov3D"], t["colors"], t["opacities"], vmt, pmt, bg, H, W, TAN, TAN,
-                                     target, None)
+                                     target, None, reduction="mean")
     (out2[0] * 3.0).backward()
     assert abs(float(out[0]) - float(out2[0])) <= 1e-6 * float(out2[0])
     assert abs(float(out[0]) - float((out[1] - target).abs().mean())) <= 2e-6 * float(out[0])

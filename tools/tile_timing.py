@@ -14,7 +14,7 @@ for it in range(3):
     out, t, _ = gpu_forward(sc, VIEWS, 512, 512, requires_grad=True)
 torch.cuda.synchronize()
 state, dims = saved_state(out[0])
-B, V, N, H, W = dims[:5]; cap = dims[7]
+B, V, N, H, W = dims[:5]; cap, cap_b, flags = dims[7]
 L = _native.lib()
 T = 1024
 rows = []
@@ -22,7 +22,7 @@ for r in range(V):
     ranges = torch.zeros((T, 2), dtype=torch.int32, device="cuda")
     tt = torch.zeros((T, 2), dtype=torch.int32, device="cuda")
     st = torch.cuda.current_stream()
-    _native.check(L.sgr_debug_copy_state(ctypes.c_void_p(state.data_ptr()), B, V, N, H, W, int(cap), r,
+    _native.check(L.sgr_debug_copy_state(ctypes.c_void_p(state.data_ptr()), B, V, N, H, W, int(cap), int(cap_b), int(flags), r,
                                          ctypes.c_void_p(ranges.data_ptr()), None, None, 0,
                                          ctypes.c_void_p(tt.data_ptr()), ctypes.c_void_p(st.cuda_stream)))
     torch.cuda.synchronize()
