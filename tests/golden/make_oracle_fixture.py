@@ -37,10 +37,21 @@ def render(sc):
     return o, b, g, grads
 
 
+def render64(sc, g):
+    """fp64 instantiation of the same formulas: the reference the gradient-accuracy bound is measured against."""
+    vm, pm, _ = cameras.orbit_cameras([VIEW])
+    tan = cameras.tan_half_fov()
+    r = oracle.Rasterizer(np.float64)
+    r.forward(sc["means3D"], sc["cov3D"], sc["colors"], sc["opacities"], vm[0].reshape(-1), pm[0].reshape(-1), tan, tan,
+              (1.0, 0.5, 0.25), H, W)
+    return r.backward(g.astype(np.float64))
+
+
 if __name__ == "__main__":
     sc = scene()
     o, b, g, grads = render(sc)
+    grads64 = render64(sc, g)
     np.savez_compressed(os.path.join(HERE, "oracle_scene_v1.npz"), color=o.color, depth=o.depth, alpha=o.alpha, radii=o.radii,
                         point_list=b["point_list"], ranges=b["ranges"], n_contrib=b["n_contrib"],
-                        **{"grad_" + k: v for k, v in grads.items()})
+                        **{"grad_" + k: v for k, v in grads.items()}, **{"grad64_" + k: v for k, v in grads64.items()})
     print("wrote oracle_scene_v1.npz:", o.num_instances, "instances,", o.blends, "blends")

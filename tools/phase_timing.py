@@ -17,6 +17,7 @@ L.sgr_debug_phase_counters(out, 1)
 v = list(out)
 names = ["tma wait", "cull", "trips", "refine+ckpt"]
 tot = sum(v[:4])
+print("quarter survivors (sum over quarters)", v[6], "trips (max over quarters)", v[4], "mean/max", v[6] / 4 / max(v[4], 1))
 print("all items: cycles", {n: f"{x/1e6:.1f}M ({100*x/tot:.0f}%)" for n, x in zip(names, v[:4])}, "trips", v[4], "batches", v[5],
       f"cycles/trip {v[2]/max(v[4],1):.0f} cull cycles/batch {v[1]/max(v[5],1):.0f} refine/batch {v[3]/max(v[5],1):.0f} wait/batch {v[0]/max(v[5],1):.0f}")
 tot = sum(v[8:12])
