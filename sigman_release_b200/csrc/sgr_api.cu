@@ -114,7 +114,7 @@ void fill_ctx(ChunkCtx& c, const SgrProblem& p, void* state, void* scratch, cuda
     c.clamp_mask = reinterpret_cast<unsigned char*>(s + S.clamp_mask);
     c.blk_off = reinterpret_cast<unsigned int*>(s + S.blk_off);
     c.blk_cnt = reinterpret_cast<unsigned int*>(s + S.blk_cnt);
-    c.q_eff = reinterpret_cast<unsigned int*>(s + S.q_eff);
+    c.blk_eff = reinterpret_cast<unsigned int*>(s + S.blk_eff);
     c.brec0 = reinterpret_cast<float4*>(s + S.brec0);
     c.brec1 = reinterpret_cast<float4*>(s + S.brec1);
     c.brec2 = reinterpret_cast<float4*>(s + S.brec2);

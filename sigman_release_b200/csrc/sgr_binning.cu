@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
 #pragma unroll
         for (int c = 0; c < kBwdClasses; ++c) a.plan->n_items[c] = 0;
         const unsigned long long used = min(a.header->blk_required, a.header->blk_capacity);   // records really stored
-        a.plan->item_base = a.item_region + kQuartersPerBlock * static_cast<unsigned int>(used / kSegB);
+        a.plan->item_base = a.item_region + static_cast<unsigned int>(used / kSegB);
         a.plan->cursor = 0;
     }
     __syncthreads();
@@ -499,9 +499,9 @@ cudaError_t launch_plan(const ChunkCtx& c) {
     a.n = c.num_renders * c.g.num_tiles;
     a.first_chunk = c.render_base == 0 ? 1 : 0;
     a.capacity = c.p->max_instances;
-    // every chunk owns the item slots [32 * render_base * T + chunk_index + 4 * (block records before it / kSegB), ...)
-    // of every class: a chunk with n tiles and m block records emits at most 32 n + 4 (m / kSegB) items
-    a.item_region = static_cast<unsigned int>(base * kItemsPerTile + size_t(c.chunk_index));
+    // every chunk owns the item slots [8 * render_base * T + chunk_index + block records before it / kSegB, ...) of
+    // every class: a chunk with n tiles and m block records emits at most 8 n + m / kSegB items
+    a.item_region = static_cast<unsigned int>(base * kBlocksPerTile + size_t(c.chunk_index));
     a.blk_capacity = c.blk_capacity;
     a.tile_cnt = c.tile_cnt + base;
     a.tile_off = c.tile_off + base;

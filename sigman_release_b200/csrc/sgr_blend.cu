@@ -2,41 +2,34 @@
 //
 // Replaces upstream renderCUDA forward/backward (third-party diff_gaussian_rasterization; call site
 // /root/reference/core/gaussians/gs.py:99-106).  Design (DESIGN.md "blend"):
-//   * the unit of work is one 4x2 pixel QUARTER of one 8x4 pixel block of one tile of one render.  Every WARP is
-//     autonomous: it pops work items from a device-side queue ordered longest-list-first
-//     (sgr_binning.cu::plan_kernel), streams the BLOCK's depth-ordered 48-byte records (three float4 streams; the
-//     per-tile sort emits one contiguous list per block that holds only the instances whose extent touches the
-//     block) through its own shared-memory ring with 1-D TMA bulk copies (cp.async.bulk) completing on its own
-//     mbarriers, and never waits for another warp — no block-wide barrier, no producer/consumer hand-off, early exit
-//     as soon as its 8 pixels are finished;
-//   * lane = (pixel, slot): 8 pixels x 4 slots.  A batch of 128 records is culled against the quarter (lane =
-//     record: the per-record quarter bit built by the tile sort, one ballot per round, compaction of the survivors'
-//     batch-local indices into a sentinel-padded list); a "super-trip" then evaluates FOUR consecutive survivors for
-//     the 8 pixels at once.  The sequential part of compositing — the transmittance T — crosses the slots with a
-//     two-step shuffle prefix over (1 - alpha) that does not depend on T, so the T-dependent chain is one multiply
-//     per four Gaussians and dense lists are no longer a single warp's dependent-issue chain; colour / depth /
-//     weight are accumulated per (pixel, slot) lane and combined once per item.  Culled records would have been
-//     skipped by the alpha test, so every survivor is evaluated with the straightforward kernel's arithmetic;
-//   * exp(power) is a template switch: kExact = the oracle's exp_spec sequence and the oracle's sequential
-//     test_T = fma(-alpha, T, T) chain evaluated redundantly by the four slot lanes of a pixel (SGR_FLAG_EXACT_EXP:
-//     T, the alpha / T thresholds and therefore n_contrib are bit-identical to oracle/sgr_oracle.cpp; colour, depth
-//     and alpha differ from it only by the order of the four partial sums, ~1e-7); default = the SFU's ex2 like
-//     upstream's own exp() and the prefix product (~1e-6 from the oracle);
-//   * per batch the forward clears the quarter bits of the records that did not blend in the quarter (the backward
-//     culls on the exact set), checkpoints the running state every kSegB records and pushes one backward work item
-//     per (quarter, segment) that blended anything, classed by the number of records that blended;
-//   * backward: work items are (block, quarter, kSegB-record segment), resumed from the forward's checkpoints; the
-//     same lanes walk the survivors back to front, four per super-trip.  With u_j = w_j (c_j . dL/dC + z_j dL/dD) the
-//     per-pixel recurrences are scalar: T_k = T_(k+1) / (1 - alpha_k) (prefix product across the slots) and
-//     U_k = sum_(j behind k) u_j (prefix sum), dL/dalpha_k = T_k (c_k . g) - (U_k + T_final (bg . g - dL/dA)) / (1 -
-//     alpha_k); the nine gradient terms of a (Gaussian, quarter) pair are reduced over its 8 pixel lanes with a
-//     reduce-scatter butterfly and leave as ONE atomic per component (no shared-memory stash, no role flip).
-//     Gradient arithmetic is free to use FMA (tolerance, not bit-exact);
-//   * optional epilogues: clamp (+ mask for the backward), masked L1 loss + dL/dcolour (SgrForwardArgs::loss_*), the
-//     factor-2 bilinear LPIPS feed.
+//   * the unit of work is one 8x4 pixel block of one tile of one render.  Every WARP is autonomous: it pops work items
+//     from a device-side queue ordered longest-list-first (sgr_binning.cu::plan_kernel), streams the BLOCK's
+//     depth-ordered 48-byte records (three float4 streams; the per-tile sort emits one contiguous list per block that
+//     holds only the instances whose extent touches the block) through its own shared-memory ring with 1-D TMA bulk
+//     copies (cp.async.bulk) completing on its own mbarriers, and never waits for another warp — no block-wide
+//     barrier, no producer/consumer hand-off, early exit as soon as its 32 pixels are finished;
+//   * a block is four 4x2 quarters.  A batch of 128 records is culled in straight-line code (lane = record): the
+//     per-record 4-bit quarter masks built by the tile sort are read, one ballot per (round, quarter), and the
+//     survivors' batch-local indices are compacted into one sentinel-padded list per quarter; every quarter then
+//     walks only its own survivors (lane = pixel), so up to four different Gaussians are evaluated per trip.  Culled
+//     records would have been skipped by the alpha test, so the per-pixel arithmetic, the contributor index and every
+//     output bit equal the straightforward kernel's;
+//   * forward trips run in groups of eight (four at the end of a list): eight independent alpha chains written
+//     load-first, then the sequential compositing recurrence; per batch the forward clears the mask bits of the
+//     (quarter, record) pairs that did not blend (a plain store: the block owns its records) so that the backward
+//     culls on the exact set, checkpoints the running state every kSegB records and pushes one backward work item
+//     per segment that blended anything, classed by the number of records that blended;
+//   * backward: work items are (block, kSegB-record segment), resumed from the forward's checkpoints; the same
+//     walk in reverse over descending lists with phases A+B (alpha, G, then the per-pixel transmittance / colour
+//     recurrences producing dL/dalpha and the blend weight, stashed) and C: the roles flip to lane = (Gaussian,
+//     quarter) pair, each lane summing the gradient terms of its quarter's 8 pixels in registers (XOR-swizzled stash,
+//     no shuffles) before one atomic per component.  Gradient arithmetic is free to use FMA (tolerance, not bit-exact);
+//   * optional epilogue: clamp + masked L1 loss + dL/dcolour (SgrForwardArgs::loss_*).
 //
 // Compiled with --fmad=false: the per-pixel expressions are the oracle's (oracle/sgr_oracle.cpp::blend_forward /
-// blend_backward) evaluated in the same order.
+// blend_backward) evaluated in the same order.  exp(power) is a template switch: kExact = the oracle's exp_spec
+// sequence (SGR_FLAG_EXACT_EXP: colour, depth, alpha and n_contrib bit-exact), default = the SFU's ex2 like upstream's
+// own exp() (sgr_common.cuh::exp_fast; ~1e-6 from the oracle).
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
@@ -52,29 +45,35 @@ namespace {
 #ifndef SGR_FWD_STAGES
 #define SGR_FWD_STAGES 2
 #endif
+constexpr int kFwdBatch = SGR_FWD_BATCH;       // records per ring stage (culled 32 at a time: lane = record), forward
 #ifndef SGR_BWD_BATCH
 #define SGR_BWD_BATCH 128
 #endif
 #ifndef SGR_BWD_STAGES
-#define SGR_BWD_STAGES 2
+#define SGR_BWD_STAGES 1
 #endif
-constexpr int kFwdBatch = SGR_FWD_BATCH;       // records per ring stage (culled 32 at a time: lane = record)
-constexpr int kBwdBatch = SGR_BWD_BATCH;
-constexpr int kFwdStages = SGR_FWD_STAGES;     // per-warp TMA ring depth
-constexpr int kBwdStages = SGR_BWD_STAGES;
-static_assert(kSegB % kFwdBatch == 0 && kSegB % kBwdBatch == 0, "segments are whole batches");
-constexpr int kWarpsPerCta = 8;
+constexpr int kBwdBatch = SGR_BWD_BATCH;       // ... backward
+constexpr int kFwdStages = SGR_FWD_STAGES;     // per-warp TMA ring depth, forward
+constexpr int kBwdStages = SGR_BWD_STAGES;     // backward: one 128-record stage (the stash takes the rest of the budget)
+constexpr int kWarpsPerCta = 8;                // backward: two CTAs of 8 warps per SM
 constexpr int kBlendThreads = kWarpsPerCta * 32;
-constexpr int kBlockW = 8, kBlockH = 4;
-constexpr int kSlots = 4;                      // consecutive survivors evaluated per super-trip (lane = pixel + 8 * slot)
-#ifndef SGR_FWD_GROUPS
-#define SGR_FWD_GROUPS 2
+// forward: ONE CTA of 16 warps per SM, so that the warps that share an SM sub-partition (warp % 4) can see each
+// other in shared memory: a warp that walks a dense block list gets its scheduler to itself (see "parking" below)
+constexpr int kFwdWarps = 16;
+constexpr int kFwdThreads = kFwdWarps * 32;
+#ifndef SGR_FWD_DENSE
+#define SGR_FWD_DENSE 640
 #endif
-#ifndef SGR_BWD_GROUPS
-#define SGR_BWD_GROUPS 1
+#ifndef SGR_FWD_PARK
+#define SGR_FWD_PARK 0
 #endif
-constexpr int kFwdGroups = SGR_FWD_GROUPS;     // super-trips written load-first per loop iteration (ILP)
-constexpr int kBwdGroups = SGR_BWD_GROUPS;
+constexpr unsigned int kDenseRecords = SGR_FWD_DENSE;   // block lists at least this long are "dense"
+constexpr int kParkLimit = SGR_FWD_PARK;                // scheduler mates that may park beside a dense warp (0 = off)
+constexpr int kBlockW = 8, kBlockH = 4;        // pixel block of one warp (four 4x2 quarters walk separate lists)
+#ifndef SGR_BWD_SLOTS
+#define SGR_BWD_SLOTS 16
+#endif
+constexpr int kBwdSlots = SGR_BWD_SLOTS;       // backward: trips per phase pass (8 or 16: the stash swizzle)
 constexpr unsigned int kFull = 0xffffffffu;
 template <bool kExact>
 __device__ __forceinline__ float blend_exp(float x) { return kExact ? exp_core(x) : exp_fast(x); }
@@ -124,56 +123,70 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
-constexpr int kListPad = 16;                   // the group loops read up to 4 * groups - 1 entries past the count
+constexpr int kListPad = 16;                   // keeps the rows 16-byte aligned
 
-template <int kNumStages, int kBatch>
+template <int kStashes, int kDepth, int kNumStages, int kBatch>
 struct WarpSmem {
     static constexpr int stages = kNumStages;
     float4 r0[kNumStages][kBatch + 1];          // slot kBatch of every stage = the sentinel record (never blends)
     float4 r1[kNumStages][kBatch + 1];
     float4 r2[kNumStages][kBatch + 1];
-    // batch-local indices of the quarter's survivors, sentinel-filled
-    unsigned char list[kBatch + kListPad];
-    unsigned char hit[kBatch + kListPad];       // forward: hit[j] != 0 <=> some pixel of the quarter blended record j
+    float stash[kStashes][kDepth][32];
+    float dpix[4][32];                          // backward: dL/dcolor (3) and dL/ddepth of the block's pixels
+    // per quarter: batch-local indices of the survivors, sentinel-filled; the trip loops read whole groups of 4 / 8
+    // entries starting at multiples of their size, which stays inside kBatch — the pad is a safety margin
+    unsigned char list[4][kBatch + kListPad];
+    unsigned int hit[kBatch + 1];               // forward: byte q of word j != 0 <=> quarter q blended record j
     uint64_t full[kNumStages];
 };
 
-// Cull a batch of m <= kBatch block records against the warp's 4x2 quarter `q` of the block: 32 records per round
-// (lane = record) read bit q of their quarter mask (low bits of rec0.z, built by the tile sort from
-// sgr_common.cuh::quarter_mask and refined by the forward), one ballot per round, warp-parallel compaction of the
-// survivors' batch-local indices into list[...] (ascending; descending with kReverse — the backward walks back to
-// front); unused list entries point at the sentinel record.  bits[r] != 0: record 32 r + lane is a candidate.
+// Cull a batch of m <= kBatch block records against the four 4x2 quarters of the warp's 8x4 pixel block:
+// 32 records per round (lane = record) read their 4-bit quarter mask (low bits of rec0.z, built by the tile sort
+// from sgr_common.cuh::quarter_mask), one ballot per quarter, warp-parallel compaction of the survivors'
+// batch-local indices into list[quarter][...] (ascending; descending with kReverse — the backward walks back to front);
+// unused list entries point at the sentinel record.  Returns the four survivor counts.
 template <bool kReverse, int kBatch>
-__device__ __forceinline__ unsigned int cull_batch(const float4* r0, unsigned int m, int q, unsigned char* list, int lane,
-                                                   unsigned int (&bits)[kBatch / 32]) {
+__device__ __forceinline__ uint4 cull_batch(const float4* r0, unsigned int m,
+                                            unsigned char (*list)[kBatch + kListPad],
+                                            int lane, unsigned int (&bits)[kBatch / 32]) {
+    // Straight-line code (the per-batch overhead is latency, not work): all mask words are loaded first, then all
+    // ballots, then the compaction stores.  bits[r] = this lane's 4-bit quarter mask of record 32 * r + lane.
     constexpr int R = kBatch / 32;
     const unsigned int lt = kReverse ? ~((2u << lane) - 1u) : (1u << lane) - 1u;   // lanes before / after this one
     const unsigned int* words = reinterpret_cast<const unsigned int*>(r0);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const unsigned int e = 32u * r + lane;
-        bits[r] = (e < m) ? ((words[4 * e + 2] >> q) & 1u) : 0u;
+        bits[r] = (e < m) ? (words[4 * e + 2] & 0xfu) : 0u;
     }
     {                             // every list entry the compaction does not overwrite points at the sentinel record
         constexpr unsigned int fill = kBatch * 0x01010101u;
-        uint4* lw = reinterpret_cast<uint4*>(list);
-        constexpr int kVecs = (kBatch + kListPad) / 16;
-        if (lane < kVecs) lw[lane] = make_uint4(fill, fill, fill, fill);
-        static_assert(kVecs <= 32, "one store per lane fills the list");
-    }
-    unsigned int mq[R];
+        uint4* lw = reinterpret_cast<uint4*>(&list[0][0]);
+        constexpr int kVecs = 4 * (kBatch + kListPad) / 16;       // the four rows including their pads
 #pragma unroll
-    for (int r = 0; r < R; ++r) mq[r] = __ballot_sync(kFull, bits[r]);
+        for (int v = 0; v < kVecs; v += 32)
+            if (v + lane < kVecs) lw[v + lane] = make_uint4(fill, fill, fill, fill);
+    }
+    unsigned int mq[4][R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mq[q][r] = __ballot_sync(kFull, bits[r] & (1u << q));
+    }
     __syncwarp();                 // the sentinel fill is ordered before the compaction stores
-    unsigned int n = 0;
+    unsigned int n[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int k = 0; k < R; ++k) {
         const int r = kReverse ? R - 1 - k : k;                 // descending lists walk the rounds from the back
-        if (bits[r]) list[n + __popc(mq[r] & lt)] = static_cast<unsigned char>(32u * r + lane);
-        n += __popc(mq[r]);
+        const unsigned int e = 32u * r + lane;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (bits[r] & (1u << q)) list[q][n[q] + __popc(mq[q][r] & lt)] = static_cast<unsigned char>(e);
+            n[q] += __popc(mq[q][r]);
+        }
     }
     __syncwarp();
-    return n;
+    return make_uint4(n[0], n[1], n[2], n[3]);
 }
 
 // Per-warp TMA ring: `issued` / `consumed` count batches over the whole kernel (stage = k % stages,
@@ -192,7 +205,7 @@ __device__ __forceinline__ void ring_issue(Smem& sm, unsigned int issued, const 
     }
 }
 
-// Pops one work item for the calling warp, or 0xffffffff when the queue is empty.
+// Pops one work item for the calling warp: (chunk-local tile index, pixel block) or 0xffffffff when the queue is empty.
 __device__ __forceinline__ unsigned int pop_item(unsigned int* cursor, unsigned int n_items, int lane) {
     unsigned int w = 0;
     if (lane == 0) w = atomicAdd(cursor, 1u);
@@ -200,19 +213,15 @@ __device__ __forceinline__ unsigned int pop_item(unsigned int* cursor, unsigned 
     return w < n_items ? w : 0xffffffffu;
 }
 
-// Sum / product / max of a per-(pixel, slot) value over the four slot lanes of a pixel (lane = pixel + 8 * slot).
-__device__ __forceinline__ float slots_sum(float v) {
-    v += __shfl_xor_sync(kFull, v, 8);
-    return v + __shfl_xor_sync(kFull, v, 16);
-}
-__device__ __forceinline__ float slots_prod(float v) {
-    v *= __shfl_xor_sync(kFull, v, 8);
-    return v * __shfl_xor_sync(kFull, v, 16);
-}
-__device__ __forceinline__ unsigned int slots_max(unsigned int v) {
-    v = max(v, __shfl_xor_sync(kFull, v, 8));
-    return max(v, __shfl_xor_sync(kFull, v, 16));
-}
+#ifdef SGR_PHASE_TIMING
+// Experiment build only: cycles spent per phase by lane 0 of (a) all items, (b) block 7 of the first (longest) tile.
+__device__ unsigned long long g_phase[16];
+#define PHASE_T0() const long long pt0__ = clock64()
+#define PHASE_ADD(k) do { const long long d__ = clock64() - pt0__; ph[k] += d__; } while (0)
+#else
+#define PHASE_T0()
+#define PHASE_ADD(k)
+#endif
 
 // ------------------------------------------------------------------------------------------------ forward
 struct FwdArgs {
@@ -220,7 +229,7 @@ struct FwdArgs {
     int render_base;
     const unsigned int* blk_off;  // [R*T*8] block lists (sgr_binning.cu step 5)
     const unsigned int* blk_cnt;
-    unsigned int* q_eff;          // [R*T*32] out: records of the block list the backward replays for the quarter
+    unsigned int* blk_eff;        // out: records of the block list the backward has to replay
     const float4 *rec0, *rec1, *rec2;   // block records
     unsigned int* rec0_words;     // rec0 as words: the forward refines the quarter masks (word 2 of every record)
     int refine_masks;
@@ -245,7 +254,7 @@ struct FwdArgs {
     float loss_scale;
 };
 
-// Backward item classes by the number of records of the (quarter, segment) that blended.
+// Backward item classes by the number of records of the segment that blended in at least one quarter.
 __device__ __forceinline__ int bwd_class(unsigned int hits) {
     return hits >= 3u * kSegB / 4 ? 0 : hits >= 3u * kSegB / 8 ? 1 : hits >= kSegB / 8 ? 2 : 3;
 }
@@ -278,34 +287,32 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// Output epilogue of one pixel; all 32 lanes call it.  `writer`: this lane stores the pixel (one lane per pixel).
-// kRowXor = lane distance of the pixel one row below (8: lane = 8x4 block pixel; 4: lane & 7 = 4x2 quarter pixel).
+// Output epilogue of one pixel (all 32 lanes of the block call it; lane = pixel (x = lane & 7, y = lane >> 3)).
 // clamp_color: gs.py:107 `clamp(0, 1)` fused, with the clamp mask kept for the backward (bit c = channel c saturated,
 // torch's rule: the gradient passes where 0 <= c <= 1).  out_feed: the LPIPS input of whole_loss.py:132-136 — a
-// factor-2 bilinear resize (align_corners=False) is the mean over 2x2 pixels, here two shuffles.
-template <int kRowXor>
-__device__ __forceinline__ void write_pixel(const FwdArgs& a, int r, size_t P, int px, int py, bool writer, float c0,
-                                            float c1, float c2, float D, float Wt, unsigned int last) {
+// factor-2 bilinear resize (align_corners=False) is the mean over 2x2 pixels, here two shuffles inside the block.
+__device__ __forceinline__ void write_pixel(const FwdArgs& a, int r, size_t P, int px, int py, bool inside, int lane,
+                                            float c0, float c1, float c2, float D, float Wt, unsigned int last) {
+    (void)lane;
     const size_t pix = size_t(py) * a.g.W + px;
     if (a.clamp_color) {
         const unsigned int m = (c0 >= 0.0f && c0 <= 1.0f ? 0u : 1u) | (c1 >= 0.0f && c1 <= 1.0f ? 0u : 2u) |
                                (c2 >= 0.0f && c2 <= 1.0f ? 0u : 4u);
         c0 = fminf(fmaxf(c0, 0.0f), 1.0f); c1 = fminf(fmaxf(c1, 0.0f), 1.0f); c2 = fminf(fmaxf(c2, 0.0f), 1.0f);
-        if (writer) a.clamp_mask[size_t(r) * P + pix] = static_cast<unsigned char>(m);
+        if (inside) a.clamp_mask[size_t(r) * P + pix] = static_cast<unsigned char>(m);
     }
     if (a.out_feed) {                           // even H, W: a 2x2 cell is entirely inside or outside the image
         float s0 = c0 + __shfl_xor_sync(kFull, c0, 1), s1 = c1 + __shfl_xor_sync(kFull, c1, 1),
               s2 = c2 + __shfl_xor_sync(kFull, c2, 1);
-        s0 += __shfl_xor_sync(kFull, s0, kRowXor); s1 += __shfl_xor_sync(kFull, s1, kRowXor);
-        s2 += __shfl_xor_sync(kFull, s2, kRowXor);
-        if (writer && (px & 1) == 0 && (py & 1) == 0) {
+        s0 += __shfl_xor_sync(kFull, s0, 8); s1 += __shfl_xor_sync(kFull, s1, 8); s2 += __shfl_xor_sync(kFull, s2, 8);
+        if (inside && (px & 1) == 0 && (py & 1) == 0) {
             const size_t Pq = P >> 2;
             const size_t q = size_t(py >> 1) * (a.g.W >> 1) + (px >> 1);
             float* of = a.out_feed + size_t(r) * 3 * Pq;
             of[q] = 0.5f * s0 - 1.0f; of[Pq + q] = 0.5f * s1 - 1.0f; of[2 * Pq + q] = 0.5f * s2 - 1.0f;
         }
     }
-    if (writer) {
+    if (inside) {
         float* oc = a.out_color + size_t(r) * 3 * P;
         oc[pix] = c0; oc[P + pix] = c1; oc[2 * P + pix] = c2;
         a.out_depth[size_t(r) * P + pix] = D;
@@ -314,79 +321,106 @@ __device__ __forceinline__ void write_pixel(const FwdArgs& a, int r, size_t P, i
     }
 }
 
-using FwdSmem = WarpSmem<kFwdStages, kFwdBatch>;
-using BwdSmem = WarpSmem<kBwdStages, kBwdBatch>;
+using FwdSmem = WarpSmem<1, 1, kFwdStages, kFwdBatch>;      // the forward needs no stash
+using BwdSmem = WarpSmem<3, kBwdSlots, kBwdStages, kBwdBatch>;
 
+#ifndef SGR_FWD_GROUP8
+#define SGR_FWD_GROUP8 1
+#endif
 #ifndef SGR_FWD_MIN_CTAS
-#define SGR_FWD_MIN_CTAS 2
+#define SGR_FWD_MIN_CTAS 1
 #endif
 #ifndef SGR_BWD_MIN_CTAS
 #define SGR_BWD_MIN_CTAS 2
 #endif
-
 template <bool kExact>
-__global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward_kernel(FwdArgs a) {
+__global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_kernel(FwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    // Parking: the launch is bounded by the walk of the densest block lists, and a warp that shares its scheduler
+    // with three others issues at a quarter of its possible rate.  Warps of one SM sub-partition (warp % 4) therefore
+    // keep a count of the dense lists being walked on it; a mate that finishes its item while the count is non-zero
+    // does not pop new work but sleeps (at most kParkLimit of them) until the dense walk is over.  Nothing depends on
+    // which warps share a scheduler: a wrong guess only parks the wrong warps.
+    __shared__ int s_dense[4], s_parked[4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 4) { s_dense[threadIdx.x] = 0; s_parked[threadIdx.x] = 0; }
+    __syncthreads();
+    const int part = warp & 3;
     FwdSmem& sm = reinterpret_cast<FwdSmem*>(smem_raw)[warp];
     const size_t P = size_t(a.g.H) * a.g.W;
     const float bg0 = a.bg[0], bg1 = a.bg[1], bg2 = a.bg[2];
-    const unsigned int n_items = a.wc->n_blend * kItemsPerTile, n_empty_items = a.wc->n_empty * kBlocksPerTile;
+    const unsigned int n_items = a.wc->n_blend * kBlocksPerTile, n_empty_items = a.wc->n_empty * kBlocksPerTile;
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < kFwdStages; ++s) mbar_init(&sm.full[s], 1);
         fence_barrier_init();
     }
     __syncwarp();
-    const int pl = lane & 7, slot = lane >> 3;   // pixel of the quarter (x = pl & 3, y = pl >> 2), survivor slot
+    const int qsel = ((lane >> 2) & 1) | ((lane >> 3) & 2);        // 4x2 pixel quarter of this lane: x half | 2 * y half
+    const unsigned int qmask = 0x00000f0fu << ((lane & 4) | (lane & 16));   // the quarter's 8 lanes
+    const unsigned char* mylist = sm.list[qsel];
     unsigned int issued = 0, consumed = 0;       // ring counters (warp-uniform)
     const bool refine = a.refine_masks != 0;
-    for (int w = lane; w < kFwdBatch + kListPad; w += 32) sm.hit[w] = 0;
-    if (lane < kFwdStages) {      // the sentinel record: opacity 0 at power 0 -> alpha 0; never valid in exact mode
+    unsigned char* hit_bytes = reinterpret_cast<unsigned char*>(sm.hit) + qsel;       // indexed with 4 * j
+#pragma unroll
+    for (int w = 0; w < kFwdBatch; w += 32) sm.hit[w + lane] = 0u;
+    if (lane < kFwdStages) {      // the sentinel record: threshold +inf -> never valid, alpha 0, colour 0
         sm.r0[lane][kFwdBatch] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0x7f800000));
         sm.r1[lane][kFwdBatch] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         sm.r2[lane][kFwdBatch] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     __syncwarp();
 
-    // ---------------- quarters of tiles with instances
+    // ---------------- blocks of tiles with instances
     for (;;) {
+        if (kParkLimit > 0) {                     // a dense walk is in progress on this sub-partition: stay out of its way
+            int go = 1;
+            if (lane == 0 && *reinterpret_cast<volatile int*>(&s_dense[part]) > 0) {
+                if (atomicAdd(&s_parked[part], 1) < kParkLimit)
+                    while (*reinterpret_cast<volatile int*>(&s_dense[part]) > 0) __nanosleep(200);
+                atomicSub(&s_parked[part], 1);
+            }
+            go = __shfl_sync(kFull, go, 0);
+            (void)go;
+        }
         const unsigned int item = pop_item(&a.wc->blend_cursor, n_items, lane);
         if (item == 0xffffffffu) break;
-        const unsigned int tile_local = a.work_blend[item / kItemsPerTile];
-        const int blk = (item % kItemsPerTile) / kQuartersPerBlock;
-        const int q = item % kQuartersPerBlock;
+        const unsigned int tile_local = a.work_blend[item / kBlocksPerTile];
+        const int blk = item % kBlocksPerTile;
         const int rl = tile_local / a.g.num_tiles;
         const int tile = tile_local - rl * a.g.num_tiles;
         const int r = a.render_base + rl;
         const size_t tg = size_t(r) * a.g.num_tiles + tile;
         const size_t bi = tg * kBlocksPerTile + blk;
-        const size_t item_slot = (size_t(tile_local) * kBlocksPerTile + blk) * kQuartersPerBlock + q;
         const unsigned int n = a.blk_cnt[bi];                       // records of this block's list
         const size_t off = a.blk_off[bi];
         const unsigned int nb = (n + kFwdBatch - 1) / kFwdBatch;
         const int tx = tile % a.g.tiles_x, ty = tile / a.g.tiles_x;
-        const int qx0 = tx * kTile + (blk & 1) * kBlockW + (q & 1) * 4, qy0 = ty * kTile + (blk >> 1) * kBlockH + (q >> 1) * 2;
-        if (qx0 >= a.g.W || qy0 >= a.g.H) {                        // quarter entirely outside the image
+        const int bx0 = tx * kTile + (blk & 1) * kBlockW, by0 = ty * kTile + (blk >> 1) * kBlockH;
+        if (bx0 >= a.g.W || by0 >= a.g.H) {                        // block entirely outside the image
             if (lane == 0) {
-                if (a.loss_target) a.loss_part[item_slot] = 0.0f;
-                if (refine) a.q_eff[bi * kQuartersPerBlock + q] = 0u;
+                if (a.loss_target) a.loss_part[size_t(tile_local) * kBlocksPerTile + blk] = 0.0f;
+                if (refine) a.blk_eff[bi] = 0u;
             }
             continue;
         }
+        const bool dense = kParkLimit > 0 && n >= kDenseRecords;
+        if (dense && lane == 0) atomicAdd(&s_dense[part], 1);
         const unsigned long long t_begin = global_timer_ns();
-        const int px = qx0 + (pl & 3), py = qy0 + (pl >> 2);
+        const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
         const bool inside = px < a.g.W && py < a.g.H;
         const float pxf = float(px), pyf = float(py);
         const float4 *g0 = a.rec0 + off, *g1 = a.rec1 + off, *g2 = a.rec2 + off;
 
-        // T and done are per pixel (identical in the pixel's four slot lanes); the sums are per (pixel, slot)
         float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, D = 0.0f, Wt = 0.0f;
-        float fix = 1.0f;                        // default mode: (1 - alpha) of the slots that blended in the pixel's last super-trip
-        unsigned int last = 0;                   // position in the tile list + 1 of the last record this lane blended
+        unsigned int last = 0;
         bool done = !inside;
         unsigned int b_issued = 0;
         unsigned int seg_hits = 0, eff = 0;      // records of the current segment that blended; last such record + 1
+#ifdef SGR_PHASE_TIMING
+        long long ph[5] = {0, 0, 0, 0, 0};
+        unsigned long long ntrips = 0;
+#endif
         while (b_issued < nb && b_issued < unsigned(kFwdStages - 1)) {
             ring_issue(sm, issued, g0 + b_issued * kFwdBatch, g1 + b_issued * kFwdBatch, g2 + b_issued * kFwdBatch,
                        min(unsigned(kFwdBatch), n - b_issued * kFwdBatch), lane);
@@ -399,104 +433,108 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
                 ++issued; ++b_issued;
             }
             const int s = consumed % kFwdStages;
-            mbar_wait(&sm.full[s], (consumed / kFwdStages) & 1);
+            { PHASE_T0(); mbar_wait(&sm.full[s], (consumed / kFwdStages) & 1); PHASE_ADD(0); }
             ++consumed;
             const unsigned int m = min(unsigned(kFwdBatch), n - b * kFwdBatch);
             const unsigned int cbase = b * kFwdBatch;
             const float4* r0 = sm.r0[s];
             const float4* r1 = sm.r1[s];
             const float4* r2 = sm.r2[s];
+            uint4 cnt;
             unsigned int qbits[kFwdBatch / 32];
-            const unsigned int cnt = cull_batch<false, kFwdBatch>(r0, m, q, sm.list, lane, qbits);
-            // One super-trip = the quarter's next four survivors (slot = which of the four) for its 8 pixels.  List
-            // entries past the count point at the sentinel record (alpha = 0): no bounds checks in the loop.
-            for (unsigned int t0 = 0; t0 < cnt; t0 += kSlots * kFwdGroups) {
-                float4 q0[kFwdGroups], q1[kFwdGroups];
-                unsigned int jj[kFwdGroups];
-                float al[kFwdGroups];
+            { PHASE_T0(); cnt = cull_batch<false, kFwdBatch>(r0, m, sm.list, lane, qbits); PHASE_ADD(1); }
+            // quarters whose 8 pixels are all finished need no further evaluation
+            const unsigned int dmask = __ballot_sync(kFull, done);
+            const unsigned int my_n = ((dmask & qmask) == qmask) ? 0u : (qsel == 0 ? cnt.x : qsel == 1 ? cnt.y : qsel == 2 ? cnt.z : cnt.w);
+            const int total = int(__reduce_max_sync(kFull, my_n));
+            // One trip = every quarter evaluates its next survivor (lane = pixel).  Four trips per iteration, written
+            // load-first so that the four independent alpha chains interleave ahead of the sequential compositing
+            // recurrence.  List entries past a quarter's count point at the sentinel record (alpha = 0): no bounds
+            // checks in the loop.  Quarters that are finished still walk (ok = false for all their lanes).
+            unsigned int lastj = 0xffffffffu;
+#ifdef SGR_PHASE_TIMING
+            const long long pt_trips = clock64();
+            ntrips += total;
+#endif
+            // A group of G trips: G independent alpha chains (loads first), then the compositing recurrence with the
+            // colour records fetched as they are needed.  Groups of 8 while at least 5 trips remain (a single warp's
+            // issue rate is bounded by the dependent-issue latency, so the long lists that run alone at the end of the
+            // launch need the extra instruction-level parallelism), a group of 4 for the rest.
+            auto trip_group = [&](int t0, auto G_tag) {
+                constexpr int G = decltype(G_tag)::value;
+                float4 q0[G], q1[G];
+                unsigned int jj[G];
 #pragma unroll
-                for (int g = 0; g < kFwdGroups; ++g) {
-                    jj[g] = sm.list[t0 + kSlots * g + slot];
-                    q0[g] = r0[jj[g]];
-                    q1[g] = r1[jj[g]];
-                }
+                for (int w4 = 0; w4 < G / 4; ++w4) {
+                    const unsigned int packed = *reinterpret_cast<const unsigned int*>(mylist + t0 + 4 * w4);
 #pragma unroll
-                for (int g = 0; g < kFwdGroups; ++g) {
-                    const float dx = q0[g].x - pxf, dy = q0[g].y - pyf;
-                    const float power = gauss_power(q1[g].x, q1[g].y, q1[g].z, dx, dy);
-                    // exact mode: exp_core needs power >= the record's threshold (>= -87); below it alpha < 1/255 anyway
-                    const bool valid = kExact ? (!(power > 0.0f) && !(power < q0[g].w)) : !(power > 0.0f);
-                    const float alpha = fminf(kAlphaMax, q1[g].w * blend_exp<kExact>(valid ? power : 0.0f));
-                    al[g] = (valid && !(alpha < kAlphaMin)) ? alpha : 0.0f;
-                }
-#pragma unroll
-                for (int g = 0; g < kFwdGroups; ++g) {
-                    float Tb;                    // transmittance in front of this lane's record
-                    bool blend;
-                    if (kExact) {
-                        // the oracle's sequential chain over the four slots, evaluated by every slot lane of the pixel
-                        float Tk = T;
-                        bool dn = done;
-                        Tb = T; blend = false;
-#pragma unroll
-                        for (int k = 0; k < kSlots; ++k) {
-                            const float ak = __shfl_sync(kFull, al[g], pl + 8 * k);
-                            const bool ok = !dn && ak != 0.0f;
-                            const float test_T = __fmaf_rn(-ak, Tk, Tk);
-                            const bool stop = ok && (test_T < kTMin);
-                            const bool bl = ok && !stop;
-                            if (k == slot) { Tb = Tk; blend = bl; }
-                            Tk = bl ? test_T : Tk;
-                            dn = dn || stop;
-                        }
-                        T = Tk; done = dn;
-                    } else {
-                        // prefix product of (1 - alpha) across the slots (independent of T), then one multiply by T
-                        const float om = 1.0f - al[g];
-                        float inc = om;
-                        float v = __shfl_up_sync(kFull, inc, 8);
-                        inc = slot >= 1 ? inc * v : inc;
-                        v = __shfl_up_sync(kFull, inc, 16);
-                        inc = slot >= 2 ? inc * v : inc;
-                        float exc = __shfl_up_sync(kFull, inc, 8);
-                        exc = slot >= 1 ? exc : 1.0f;
-                        const float tot = __shfl_sync(kFull, inc, pl + 24);
-                        Tb = T * exc;
-                        const bool pass = !(T * inc < kTMin);       // monotone over the slots: a stop holds for all behind
-                        blend = !done && al[g] != 0.0f && pass;
-                        const float T3 = T * tot;
-                        const bool stop_now = !done && (T3 < kTMin);
-                        // a pixel that stops inside this super-trip keeps T and remembers which slots still blended
-                        fix = stop_now ? (blend ? om : 1.0f) : fix;
-                        T = (done || stop_now) ? T : T3;
-                        done = done || stop_now;
+                    for (int u = 0; u < 4; ++u) {
+                        jj[4 * w4 + u] = (packed >> (8 * u)) & 0xffu;
+                        q0[4 * w4 + u] = r0[jj[4 * w4 + u]];
+                        q1[4 * w4 + u] = r1[jj[4 * w4 + u]];
                     }
-                    const float4 q2 = r2[jj[g]];
-                    const float w = blend ? al[g] * Tb : 0.0f;      // adding c * 0 leaves the sums bit-unchanged
+                }
+                float al[G];
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                    const float dx = q0[u].x - pxf, dy = q0[u].y - pyf;
+                    const float power = gauss_power(q1[u].x, q1[u].y, q1[u].z, dx, dy);
+                    // exact mode: exp_core needs power >= the record's threshold (>= -87; below it alpha < 1/255
+                    // anyway); the SFU exponential takes any argument
+                    const bool valid = kExact ? (!(power > 0.0f) && !(power < q0[u].w)) : !(power > 0.0f);
+                    const float alpha = fminf(kAlphaMax, q1[u].w * blend_exp<kExact>(kExact ? (valid ? power : 0.0f) : power));
+                    al[u] = valid ? alpha : 0.0f;
+                }
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                    const float4 q2 = r2[jj[u]];
+                    const bool ok = !done && !(al[u] < kAlphaMin);
+                    const float test_T = __fmaf_rn(-al[u], T, T);
+                    const bool stop = ok && (test_T < kTMin);
+                    const bool blend = ok && !stop;
+                    const float w = blend ? al[u] * T : 0.0f;      // adding c * 0 leaves the sums bit-unchanged
                     C0 = __fmaf_rn(q2.x, w, C0);
                     C1 = __fmaf_rn(q2.y, w, C1);
                     C2 = __fmaf_rn(q2.z, w, C2);
-                    Wt += w;
+                    if (kExact) Wt += w;                           // default mode: alpha = 1 - T at the end
                     D = __fmaf_rn(q2.w, w, D);
-                    // n_contrib counts positions in the TILE's list (upstream's contributor index): bits 4.. of word 2
-                    last = blend ? (__float_as_uint(q0[g].z) >> 4) + 1u : last;
-                    // same-value stores of the record's lanes to one byte: benign
-                    if (refine && blend) sm.hit[jj[g]] = 1;
+                    T = blend ? test_T : T;
+                    lastj = blend ? jj[u] : lastj;
+                    done = done || stop;
+                    // same-value stores of the quarter's lanes to one byte: benign
+                    if (refine && blend) hit_bytes[4u * jj[u]] = 1;
                 }
+            };
+            {
+                int t0 = 0;
+#if SGR_FWD_GROUP8
+                for (; total - t0 > 4; t0 += 8) trip_group(t0, std::integral_constant<int, 8>{});
+#endif
+                for (; t0 < total; t0 += 4) trip_group(t0, std::integral_constant<int, 4>{});
             }
+            // n_contrib counts positions in the TILE's list (upstream's contributor index): bits 4.. of word 2
+            if (lastj != 0xffffffffu) last = (__float_as_uint(r0[lastj].z) >> 4) + 1u;
             __syncwarp();
+#ifdef SGR_PHASE_TIMING
+            ph[2] += clock64() - pt_trips;
+            const long long pt_ref = clock64();
+#endif
+            // Mask refinement for the backward pass: clear the (block, quarter) bits of the records that no pixel of
+            // the quarter blended (alpha test, finished pixels) — the backward walk culls on the same word.
             if (refine) {
-                // Mask refinement for the backward pass: clear the quarter's bit of the candidates that no pixel of
-                // the quarter blended (alpha test, finished pixels) — the backward walk culls on the same word.  The
-                // four quarters of a block share its records: atomic AND.
-                if (cnt != 0u) {
+                if ((cnt.x | cnt.y | cnt.z | cnt.w) != 0u) {
+                    unsigned int hw[kFwdBatch / 32];
+#pragma unroll
+                    for (int rr = 0; rr < kFwdBatch / 32; ++rr) hw[rr] = sm.hit[32 * rr + lane];
 #pragma unroll
                     for (int rr = 0; rr < kFwdBatch / 32; ++rr) {
                         const unsigned int e = 32u * rr + lane;
-                        const unsigned int h = sm.hit[e];
-                        if (qbits[rr] && !h) atomicAnd(a.rec0_words + 4 * (off + cbase + e) + 2, ~(1u << q));
-                        if (h) sm.hit[e] = 0;
-                        const unsigned int hb = __ballot_sync(kFull, h != 0u);
+                        const unsigned int exact = ((hw[rr] & 0x01010101u) * 0x10204080u) >> 28;
+                        const unsigned int clear = qbits[rr] & ~exact;      // qbits = 0 beyond the batch
+                        // the block owns its records: a plain store of the refined word
+                        if (clear) a.rec0_words[4 * (off + cbase + e) + 2] = __float_as_uint(r0[e].z) & ~clear;
+                        if (hw[rr]) sm.hit[e] = 0u;
+                        const unsigned int hb = __ballot_sync(kFull, exact != 0u);
                         if (hb) { seg_hits += __popc(hb); eff = cbase + 32u * rr + (32u - __clz(hb)); }
                     }
                     __syncwarp();
@@ -506,31 +544,39 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
                 if (end % kSegB == 0u || end == n) {
                     if (seg_hits != 0u && lane == 0) {
                         const int cls = bwd_class(seg_hits);
-                        const unsigned int sl = atomicAdd(&a.plan->n_items[cls], 1u);
-                        a.bwd_items[size_t(cls) * a.bwd_items_stride + a.plan->item_base + sl] =
-                            make_uint2(unsigned(item_slot), (end - 1u) / kSegB);
+                        const unsigned int slot = atomicAdd(&a.plan->n_items[cls], 1u);
+                        a.bwd_items[size_t(cls) * a.bwd_items_stride + a.plan->item_base + slot] =
+                            make_uint2(unsigned(tile_local) * kBlocksPerTile + blk, (end - 1u) / kSegB);
                     }
                     seg_hits = 0u;
                 }
             }
             // lists longer than one backward segment: checkpoint the running state at every segment boundary
             if (n > unsigned(kSegB) && ((b + 1) * kFwdBatch) % kSegB == 0 && (b + 1) * kFwdBatch < n) {
-                const float c0 = slots_sum(C0), c1 = slots_sum(C1), c2 = slots_sum(C2), dd = slots_sum(D);
-                const float Tc = kExact ? T : T * slots_prod(fix);
-                if (slot == 0) {
-                    const size_t ci = (off / (kSegB / 2) + (b + 1) * kFwdBatch / kSegB - 1) * 32 + q * 8 + pl;
-                    a.ck0[ci] = make_float4(Tc, c0, c1, c2);
-                    a.ck1[ci] = dd;
-                }
+                const size_t ci = (off / (kSegB / 2) + (b + 1) * kFwdBatch / kSegB - 1) * 32 + lane;
+                a.ck0[ci] = make_float4(T, C0, C1, C2);
+                a.ck1[ci] = D;
             }
+#ifdef SGR_PHASE_TIMING
+            ph[3] += clock64() - pt_ref;
+#endif
             if (__all_sync(kFull, done)) break;
         }
-        // combine the four slot lanes of every pixel
-        C0 = slots_sum(C0); C1 = slots_sum(C1); C2 = slots_sum(C2); D = slots_sum(D); Wt = slots_sum(Wt);
-        last = slots_max(last);
-        if (!kExact) T *= slots_prod(fix);
-        if (n > unsigned(kSegB) && slot == 0) {       // final state, read by the backward's non-final segments
-            const size_t ci = (off / (kSegB / 2) + (n + kSegB - 1) / kSegB - 1) * 32 + q * 8 + pl;
+#ifdef SGR_PHASE_TIMING
+        if (lane == 0) {
+            const long long tot = clock64() - (long long)0;
+            (void)tot;
+            for (int k = 0; k < 4; ++k) atomicAdd(&g_phase[k], (unsigned long long)ph[k]);
+            atomicAdd(&g_phase[4], ntrips);
+            atomicAdd(&g_phase[5], (unsigned long long)nb);
+            if (item / kBlocksPerTile == 0 && blk == 7) {
+                for (int k = 0; k < 4; ++k) g_phase[8 + k] = (unsigned long long)ph[k];
+                g_phase[12] = ntrips; g_phase[13] = nb; g_phase[14] = n;
+            }
+        }
+#endif
+        if (n > unsigned(kSegB)) {                    // final state, read by the backward's non-final segments
+            const size_t ci = (off / (kSegB / 2) + (n + kSegB - 1) / kSegB - 1) * 32 + lane;
             a.ck0[ci] = make_float4(T, C0, C1, C2);
             a.ck1[ci] = D;
         }
@@ -538,11 +584,11 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
             // an early exit (all pixels finished) inside a segment leaves its item unpushed: push it now
             if (seg_hits != 0u && lane == 0) {
                 const int cls = bwd_class(seg_hits);
-                const unsigned int sl = atomicAdd(&a.plan->n_items[cls], 1u);
-                a.bwd_items[size_t(cls) * a.bwd_items_stride + a.plan->item_base + sl] =
-                    make_uint2(unsigned(item_slot), (eff - 1u) / kSegB);
+                const unsigned int slot = atomicAdd(&a.plan->n_items[cls], 1u);
+                a.bwd_items[size_t(cls) * a.bwd_items_stride + a.plan->item_base + slot] =
+                    make_uint2(unsigned(tile_local) * kBlocksPerTile + blk, (eff - 1u) / kSegB);
             }
-            if (lane == 0) a.q_eff[bi * kQuartersPerBlock + q] = eff;
+            if (lane == 0) a.blk_eff[bi] = eff;
         }
         // drain: copies already in flight must land before their slots are reused by the next item
         while (consumed < issued) {
@@ -550,22 +596,23 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
             ++consumed;
         }
         __syncwarp();
-        const bool writer = inside && slot == 0;
         if (a.loss_target) {
             float part = 0.0f;
-            if (writer) part = loss_pixel(a, size_t(r) * P, P, size_t(py) * a.g.W + px, C0 + T * bg0, C1 + T * bg1, C2 + T * bg2);
+            if (inside) part = loss_pixel(a, size_t(r) * P, P, size_t(py) * a.g.W + px, C0 + T * bg0, C1 + T * bg1, C2 + T * bg2);
             part = warp_sum(part);
-            if (lane == 0) a.loss_part[item_slot] = part;
+            if (lane == 0) a.loss_part[size_t(tile_local) * kBlocksPerTile + blk] = part;
         }
-        write_pixel<4>(a, r, P, px, py, writer, C0 + T * bg0, C1 + T * bg1, C2 + T * bg2, D, Wt, last);
-        if (a.tile_time && lane == 0) {          // diagnostics: earliest start, duration of the slowest quarter
+        if (!kExact) Wt = 1.0f - T;                  // sum of the blend weights up to rounding (the oracle sums them)
+        write_pixel(a, r, P, px, py, inside, lane, C0 + T * bg0, C1 + T * bg1, C2 + T * bg2, D, Wt, last);
+        if (dense && lane == 0) atomicSub(&s_dense[part], 1);
+        if (a.tile_time && lane == 0) {          // diagnostics: start of block 0, duration of the slowest block
             const unsigned long long now = global_timer_ns();
-            if (blk == 0 && q == 0) a.tile_time[tg].x = (unsigned int)t_begin;
+            if (blk == 0) a.tile_time[tg].x = (unsigned int)t_begin;
             atomicMax(&a.tile_time[tg].y, (unsigned int)(now - t_begin));
         }
     }
 
-    // ---------------- blocks of tiles without instances: background only (lane = pixel of the 8x4 block)
+    // ---------------- blocks of tiles without instances: background only
     // whole tiles are popped (8 uniform items per global atomic round trip)
     for (unsigned int item = 0xffffffffu;;) {
         if (item == 0xffffffffu || (item % kBlocksPerTile) == kBlocksPerTile - 1) {
@@ -583,16 +630,13 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_FWD_MIN_CTAS) blend_forward
         const int r = a.render_base + rl;
         const int tx = tile % a.g.tiles_x, ty = tile / a.g.tiles_x;
         const int px = tx * kTile + (blk & 1) * kBlockW + (lane & 7), py = ty * kTile + (blk >> 1) * kBlockH + (lane >> 3);
-        const bool inside = px < a.g.W && py < a.g.H;
         if (a.loss_target) {
             float part = 0.0f;
-            if (inside) part = loss_pixel(a, size_t(r) * P, P, size_t(py) * a.g.W + px, bg0, bg1, bg2);
+            if (px < a.g.W && py < a.g.H) part = loss_pixel(a, size_t(r) * P, P, size_t(py) * a.g.W + px, bg0, bg1, bg2);
             part = warp_sum(part);
-            // one partial per (block, quarter) slot: the block's sum goes to quarter 0
-            if (lane < kQuartersPerBlock)
-                a.loss_part[(size_t(tile_local) * kBlocksPerTile + blk) * kQuartersPerBlock + lane] = lane == 0 ? part : 0.0f;
+            if (lane == 0) a.loss_part[size_t(tile_local) * kBlocksPerTile + blk] = part;
         }
-        write_pixel<8>(a, r, P, px, py, inside, bg0, bg1, bg2, 0.0f, 0.0f, 0u);
+        write_pixel(a, r, P, px, py, px < a.g.W && py < a.g.H, lane, bg0, bg1, bg2, 0.0f, 0.0f, 0u);
     }
 }
 
@@ -602,7 +646,7 @@ struct BwdArgs {
     int render_base;
     const unsigned int* blk_off;
     const unsigned int* blk_cnt;
-    const unsigned int* q_eff;
+    const unsigned int* blk_eff;
     const unsigned int* bids;
     const float4 *rec0, *rec1, *rec2;     // block records (masks refined by the forward)
     const float* bg;
@@ -621,33 +665,10 @@ struct BwdArgs {
     const float* dL_scale;        // device scalar multiplying loss_dL_dcolor, or NULL
 };
 
-// Reduce-scatter of 8 per-lane values over the 8 pixel lanes of a slot group (lanes pl = 0..7): after the three
-// exchange levels lane pl holds the full sum of value `pl`.  7 shuffles instead of 24.
-__device__ __forceinline__ float reduce_scatter8(const float (&v)[8], int pl) {
-    const bool h4 = (pl & 4) != 0, h2 = (pl & 2) != 0, h1 = (pl & 1) != 0;
-    float w4[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {                // lanes with pl & 4 keep values 4..7
-        const float send = h4 ? v[i] : v[i + 4];
-        const float keep = h4 ? v[i + 4] : v[i];
-        w4[i] = keep + __shfl_xor_sync(kFull, send, 4);
-    }
-    float w2[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {                // ... pl & 2 keep the upper pair
-        const float send = h2 ? w4[i] : w4[i + 2];
-        const float keep = h2 ? w4[i + 2] : w4[i];
-        w2[i] = keep + __shfl_xor_sync(kFull, send, 2);
-    }
-    const float send = h1 ? w2[0] : w2[1];
-    const float keep = h1 ? w2[1] : w2[0];
-    return keep + __shfl_xor_sync(kFull, send, 1);
-}
-
-// Work item = (block list, quarter, segment): the quarter replays the list entries [lo, hi) of its segment back to
-// front, lo = segment * kSegB, hi = min(lo + kSegB, q_eff) (q_eff = the last record any of its pixels blended, + 1).
-// A pixel whose contributors end inside the segment starts from its final state (T = 1 - alpha_out, nothing behind);
-// a pixel that continues behind the segment starts from the forward's checkpoints: T = T_ck and
+// Work item = (block list, segment): the block replays the list entries [lo, hi) of its segment back to front,
+// lo = segment * kSegB, hi = min(lo + kSegB, blk_eff) (blk_eff = the last record any pixel blended, + 1).
+// A pixel whose contributors end inside the segment starts from its final state (T = 1 - alpha_out as in A.5, nothing
+// behind); a pixel that continues behind the segment starts from the forward's checkpoints: T = T_ck and
 // U = (C_fin - C_ck) . dL/dC + (D_fin - D_ck) dL/dD — so the long face / hand lists do not serialise on one warp.
 template <bool kDepthAlphaGrads, bool kExact>
 __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backward_kernel(BwdArgs a) {
@@ -672,17 +693,20 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
         fence_barrier_init();
     }
     __syncwarp();
-    const int pl = lane & 7, slot = lane >> 3;
-    if (lane < kBwdStages) {      // the sentinel record: opacity 0 -> alpha 0; threshold +inf -> never valid (exact mode)
+    const int qsel = ((lane >> 2) & 1) | ((lane >> 3) & 2);        // 4x2 pixel quarter of this lane: x half | 2 * y half
+    if (lane < kBwdStages) {      // the sentinel record: threshold +inf -> never valid
         sm.r0[lane][kBwdBatch] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0x7f800000));
         sm.r1[lane][kBwdBatch] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         sm.r2[lane][kBwdBatch] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     __syncwarp();
+    float (*stA)[32] = sm.stash[0];             // phase A: alpha; phase B overwrites it with dL/dalpha
+    float (*stW)[32] = sm.stash[1];             // blend weight alpha * T (0 = the pixel did not blend this Gaussian)
+    float (*stG)[32] = sm.stash[2];             // G = exp(power)
+    const unsigned char* mylist = sm.list[qsel];
     unsigned int issued = 0, consumed = 0;
-    // reduce_scatter8 leaves component pl in lane pl: 0 mean2D.x, 1 mean2D.y, 2..4 conic, 5 opacity, 6..7 colour r, g
-    // (colour b and the depth term take a plain butterfly); this is the lane's accumulator plane and its scale
-    const float out_scale = pl == 0 ? ddelx_dx : pl == 1 ? ddely_dy : (pl >= 2 && pl <= 4) ? -0.5f : 1.0f;
+    // Stash rows are XOR-swizzled by trip, column = lane ^ swz(t): conflict-free both for lane = pixel (phases A, B)
+    // and for lane = (trip, quarter) pairs reading one pixel of their quarter (phase C).
 
     for (;;) {
         const unsigned int item = pop_item(&a.plan->cursor, n_items, lane);
@@ -692,9 +716,8 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
         for (int c = 0; c < kBwdClasses - 1; ++c) cls += item >= cls_end[c] ? 1 : 0;
         const unsigned int in_cls = item - (cls ? cls_end[cls - 1] : 0u);
         const uint2 ws = a.bwd_items[size_t(cls) * a.bwd_items_stride + item_base + in_cls];
-        const unsigned int tile_local = ws.x / kItemsPerTile;
-        const int blk = (ws.x % kItemsPerTile) / kQuartersPerBlock;
-        const int q = ws.x % kQuartersPerBlock;
+        const unsigned int tile_local = ws.x / kBlocksPerTile;
+        const int blk = ws.x % kBlocksPerTile;
         const unsigned int lo = ws.y * unsigned(kSegB);
         const int rl = tile_local / a.g.num_tiles;
         const int tile = tile_local - rl * a.g.num_tiles;
@@ -702,12 +725,12 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
         const size_t tg = size_t(r) * a.g.num_tiles + tile;
         const size_t bi = tg * kBlocksPerTile + blk;
         const int tx = tile % a.g.tiles_x, ty = tile / a.g.tiles_x;
-        const int qx0 = tx * kTile + (blk & 1) * kBlockW + (q & 1) * 4, qy0 = ty * kTile + (blk >> 1) * kBlockH + (q >> 1) * 2;
-        const int px = qx0 + (pl & 3), py = qy0 + (pl >> 2);
+        const int bx0 = tx * kTile + (blk & 1) * kBlockW, by0 = ty * kTile + (blk >> 1) * kBlockH;
+        const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
         const bool inside = px < a.g.W && py < a.g.H;
         const size_t pix = size_t(py) * a.g.W + px;
         const unsigned int last = inside ? a.n_contrib[size_t(r) * P + pix] : 0u;     // position in the TILE list + 1
-        const unsigned int eff = a.q_eff[bi * kQuartersPerBlock + q];
+        const unsigned int eff = a.blk_eff[bi];
         if (eff <= lo) continue;
         const unsigned int hi = min(lo + unsigned(kSegB), eff);
         const size_t off = a.blk_off[bi];
@@ -741,12 +764,14 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
                 if (a.dL_dalpha) dalp = a.dL_dalpha[size_t(r) * P + pix];
             }
         }
+        sm.dpix[0][lane] = dp0; sm.dpix[1][lane] = dp1; sm.dpix[2][lane] = dp2; sm.dpix[3][lane] = ddep;
+        __syncwarp();
         const unsigned int nb = (hi - lo + kBwdBatch - 1) / kBwdBatch;
         const float pxf = float(px), pyf = float(py);
+        const float wx0 = float(bx0), wy0 = float(by0);
         const float4 *g0 = a.rec0 + off + lo, *g1 = a.rec1 + off + lo, *g2 = a.rec2 + off + lo;
-        // per-pixel state (identical in the pixel's four slot lanes): transmittance in front of the records handled
-        // so far (walking back to front) and U = sum over the records behind of w_j (c_j . dL/dC + z_j dL/dD)
-        float T = T_final, U = 0.0f;
+        float T = T_final;
+        float U = 0.0f;
         // A pixel has contributors behind this segment iff its last contributor sits at or behind the first record
         // after the segment (records are in tile-list order; word 2 >> 4 = position in the tile list).
         bool resume = false;
@@ -756,9 +781,10 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
         }
         if (resume) {                            // resume from the checkpoints
             const size_t slot0 = off / (kSegB / 2);
-            const size_t ci = (slot0 + ws.y) * 32 + q * 8 + pl;
-            const size_t fi = (slot0 + (n + kSegB - 1) / kSegB - 1) * 32 + q * 8 + pl;
+            const size_t ci = (slot0 + ws.y) * 32 + lane;
+            const size_t fi = (slot0 + (n + kSegB - 1) / kSegB - 1) * 32 + lane;
             const float4 ck = a.ck0[ci], fin = a.ck0[fi];
+            // T = the forward's running transmittance at the segment end, U = what the records behind contribute
             T = ck.x;
             U = (fin.y - ck.y) * dp0;
             U = fmaf(fin.z - ck.z, dp1, U);
@@ -766,17 +792,19 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
             if (kDepthAlphaGrads) U = fmaf(a.ck1[fi] - a.ck1[ci], ddep, U);
         }
         const float bg_dot = (bg0 * dp0 + bg1 * dp1) + bg2 * dp2;
-        const float K = T_final * (bg_dot - dalp);     // dL/dalpha_k = T_k (c_k . g) - (U_k + K) / (1 - alpha_k)
+        const float K = T_final * (bg_dot - dalp);
         float* acc = a.accum + size_t(rl) * a.g.N;
-        const unsigned int* ids = a.bids + off + lo;
+        const unsigned int* ids = a.bids + off;
 
         // walk step k handles list batch (nb - 1 - k)
         unsigned int b_issued = 0;
-        while (b_issued < nb && b_issued < unsigned(kBwdStages - 1)) {     // prefetch depth of the ring
-            const unsigned int lb = nb - 1 - b_issued;
-            ring_issue(sm, issued, g0 + lb * kBwdBatch, g1 + lb * kBwdBatch, g2 + lb * kBwdBatch,
-                       min(unsigned(kBwdBatch), hi - lo - lb * kBwdBatch), lane);
-            ++issued; ++b_issued;
+        if constexpr (kBwdStages > 1) {              // prefetch depth of the ring (none with a single stage)
+            while (b_issued < nb && b_issued < unsigned(kBwdStages - 1)) {
+                const unsigned int lb = nb - 1 - b_issued;
+                ring_issue(sm, issued, g0 + lb * kBwdBatch, g1 + lb * kBwdBatch, g2 + lb * kBwdBatch,
+                           min(unsigned(kBwdBatch), hi - lo - lb * kBwdBatch), lane);
+                ++issued; ++b_issued;
+            }
         }
         for (unsigned int b = 0; b < nb; ++b) {
             if (b_issued < nb) {
@@ -786,84 +814,147 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
                 ++issued; ++b_issued;
             }
             const int s = consumed % kBwdStages;
+#ifdef SGR_PHASE_TIMING
+            long long bt = clock64();
+#define BPH(k) do { const long long n__ = clock64(); if (lane == 0) atomicAdd(&g_phase[k], (unsigned long long)(n__ - bt)); bt = n__; } while (0)
+#else
+#define BPH(k)
+#endif
             mbar_wait(&sm.full[s], (consumed / kBwdStages) & 1);
             ++consumed;
-            const unsigned int bbase = (nb - 1 - b) * kBwdBatch;          // segment-local index of the batch's first record
-            const unsigned int m = min(unsigned(kBwdBatch), hi - lo - bbase);
+            BPH(0);
+            const unsigned int cbase = lo + (nb - 1 - b) * kBwdBatch;     // list index of the batch's first record
+            const unsigned int m = min(unsigned(kBwdBatch), hi - cbase);
             const float4* r0 = sm.r0[s];
             const float4* r1 = sm.r1[s];
             const float4* r2 = sm.r2[s];
             unsigned int qbits[kBwdBatch / 32];
-            const unsigned int cnt = cull_batch<true, kBwdBatch>(r0, m, q, sm.list, lane, qbits);
-            // super-trip: slot s handles the quarter's (t0 + s)-th survivor from the back
-            for (unsigned int t0 = 0; t0 < cnt; t0 += kSlots * kBwdGroups) {
+            const uint4 cnt = cull_batch<true, kBwdBatch>(r0, m, sm.list, lane, qbits);
+            const int total = int(max(max(cnt.x, cnt.y), max(cnt.z, cnt.w)));
+            BPH(1);
+#ifdef SGR_PHASE_TIMING
+            if (lane == 0) { atomicAdd(&g_phase[4], (unsigned long long)total); atomicAdd(&g_phase[5], 1ull); }
+#endif
+            // trip t of the batch handles the quarter's survivor number (my_n - 1 - t): back to front
+            for (int base = 0; base < total; base += kBwdSlots) {
+                const int trips = min(kBwdSlots, total - base);
+                // ---- phases A + B: alpha / G of four trips (independent, load-first), then the sequential per-pixel
+                // recurrences -> dL/dalpha and blend weight per trip, stashed for phase C.  The lists are descending
+                // (trip t = the quarter's t-th survivor from the back) and sentinel-padded.
+                for (int t0 = 0; t0 < trips; t0 += 4) {
+                    const unsigned int packed = *reinterpret_cast<const unsigned int*>(mylist + base + t0);
+                    float4 q0[4], q1[4], q2[4];
+                    bool has[4];
 #pragma unroll
-                for (int g = 0; g < kBwdGroups; ++g) {
-                    const unsigned int j = sm.list[t0 + kSlots * g + slot];
-                    const float4 q0 = r0[j], q1 = r1[j], q2 = r2[j];
-                    const float dx = q0.x - pxf, dy = q0.y - pyf;
-                    const float power = gauss_power(q1.x, q1.y, q1.z, dx, dy);
-                    const bool has = (__float_as_uint(q0.z) >> 4) < last;
-                    const bool valid = has && (kExact ? (!(power > 0.0f) && !(power < q0.w)) : !(power > 0.0f));
-                    const float G = blend_exp<kExact>(valid ? power : 0.0f);
-                    const float alpha = fminf(kAlphaMax, q1.w * G);
-                    const float al = (valid && !(alpha < kAlphaMin)) ? alpha : 0.0f;   // 0: the pixel did not blend it
-                    // c . g of this lane's record
-                    float cg = q2.x * dp0;
-                    cg = fmaf(q2.y, dp1, cg);
-                    cg = fmaf(q2.z, dp2, cg);
-                    if (kDepthAlphaGrads) cg = fmaf(q2.w, ddep, cg);
-                    // T_k = T / prod over the slots up to mine of (1 - alpha): inclusive prefix product of 1 / (1 - alpha)
-                    const float rinv = rcp_approx(1.0f - al);
-                    float pinc = rinv;
-                    float v = __shfl_up_sync(kFull, pinc, 8);
-                    pinc = slot >= 1 ? pinc * v : pinc;
-                    v = __shfl_up_sync(kFull, pinc, 16);
-                    pinc = slot >= 2 ? pinc * v : pinc;
-                    const float Tk = T * pinc;
-                    const float w = al * Tk;                 // blend weight of this record in this pixel
-                    const float u = w * cg;
-                    // U_k = U + sum of u over the slots before mine (they are behind my record)
-                    float uinc = u;
-                    v = __shfl_up_sync(kFull, uinc, 8);
-                    uinc = slot >= 1 ? uinc + v : uinc;
-                    v = __shfl_up_sync(kFull, uinc, 16);
-                    uinc = slot >= 2 ? uinc + v : uinc;
-                    const float Uk = U + (uinc - u);
-                    const float dal = al != 0.0f ? fmaf(Tk, cg, -(Uk + K) * rinv) : 0.0f;    // dL/dalpha
-                    T *= __shfl_sync(kFull, pinc, pl + 24);
-                    U += __shfl_sync(kFull, uinc, pl + 24);
-                    // gradient terms of (this pixel, this record)
-                    const float dL_dG = q1.w * dal;
-                    const float gdx = G * dx, gdy = G * dy;
-                    float t[8];
-                    // -gdx*A - gdy*B = 2*gdx*hA + gdy*nB   (rec1 = (-A/2, -B, -C/2, o))
-                    t[0] = dL_dG * fmaf(2.0f * q1.x, gdx, q1.y * gdy);
-                    t[1] = dL_dG * fmaf(2.0f * q1.z, gdy, q1.y * gdx);
-                    t[2] = gdx * dx * dL_dG;
-                    t[3] = gdx * dy * dL_dG;
-                    t[4] = gdy * dy * dL_dG;
-                    t[5] = G * dal;
-                    t[6] = w * dp0;
-                    t[7] = w * dp1;
-                    float t8 = w * dp2, t9 = kDepthAlphaGrads ? w * ddep : 0.0f;
-                    // reduce over the 8 pixels of the quarter: lane pl ends up with component pl of its slot's record;
-                    // components 8 (and 9) take a plain butterfly
-                    const float red = reduce_scatter8(t, pl);
-                    t8 += __shfl_xor_sync(kFull, t8, 4); t8 += __shfl_xor_sync(kFull, t8, 2); t8 += __shfl_xor_sync(kFull, t8, 1);
-                    if (kDepthAlphaGrads) {
-                        t9 += __shfl_xor_sync(kFull, t9, 4); t9 += __shfl_xor_sync(kFull, t9, 2); t9 += __shfl_xor_sync(kFull, t9, 1);
+                    for (int u = 0; u < 4; ++u) {
+                        const unsigned int j = (packed >> (8 * u)) & 0xffu;
+                        q0[u] = r0[j];
+                        has[u] = (__float_as_uint(q0[u].z) >> 4) < last;
+                        q1[u] = r1[j];
+                        q2[u] = r2[j];
                     }
-                    if (j < unsigned(kBwdBatch)) {           // not the sentinel
-                        const unsigned int id = __ldg(ids + bbase + j);
-                        float* gacc = acc + id;
-                        if (red != 0.0f) atomicAdd(gacc + size_t(pl) * a.plane, red * out_scale);
-                        if (pl == 0 && t8 != 0.0f) atomicAdd(gacc + 8 * a.plane, t8);
-                        if (kDepthAlphaGrads && pl == 1 && t9 != 0.0f) atomicAdd(gacc + 9 * a.plane, t9);
+                    float al[4], gg[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float dx = q0[u].x - pxf, dy = q0[u].y - pyf;
+                        const float power = gauss_power(q1[u].x, q1[u].y, q1[u].z, dx, dy);
+                        const bool valid = has[u] && !(power > 0.0f) && !(power < q0[u].w);
+                        gg[u] = blend_exp<kExact>(valid ? power : 0.0f);
+                        const float alpha = fminf(kAlphaMax, q1[u].w * gg[u]);
+                        al[u] = (valid && !(alpha < kAlphaMin)) ? alpha : 0.0f;
+                    }
+                    // The per-pixel recurrences are two scalars: with cg_k = c_k . dL/dC (+ z_k dL/dD),
+                    //   T_k = T_(k+1) / (1 - alpha_k),   U_k = sum over the records behind k of w_j cg_j,
+                    //   dL/dalpha_k = T_k cg_k - (U_k + K) / (1 - alpha_k),   K = T_final (bg . dL/dC - dL/dA).
+                    float dl[4], wg[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float alpha = al[u];
+                        const bool on = alpha != 0.0f;
+                        const float inv_om = rcp_approx(1.0f - alpha);
+                        const float Tn = T * inv_om;
+                        float cg = q2[u].x * dp0;
+                        cg = fmaf(q2[u].y, dp1, cg);
+                        cg = fmaf(q2[u].z, dp2, cg);
+                        if (kDepthAlphaGrads) cg = fmaf(q2[u].w, ddep, cg);
+                        const float w = alpha * Tn;
+                        dl[u] = on ? fmaf(Tn, cg, -(U + K) * inv_om) : 0.0f;
+                        wg[u] = on ? w : 0.0f;
+                        U = on ? fmaf(w, cg, U) : U;
+                        T = on ? Tn : T;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int t = t0 + u;
+                        const int col = lane ^ ((t & 3) | ((t & 4) << 1));
+                        stA[t][col] = dl[u];
+                        stW[t][col] = wg[u];
+                        stG[t][col] = gg[u];
                     }
                 }
+                __syncwarp();
+                BPH(2);
+                // ---- phase C: the roles flip to lane = (trip, quarter) pair, i.e. one Gaussian of one quarter; the
+                // lane sums the gradient terms of the quarter's 8 pixels in registers (no shuffles) and issues the
+                // atomics.  The pass's pairs are enumerated quarter by quarter and taken 32 at a time.
+                {
+                    const int c0n = min(max(int(cnt.x) - base, 0), kBwdSlots), c1n = min(max(int(cnt.y) - base, 0), kBwdSlots);
+                    const int c2n = min(max(int(cnt.z) - base, 0), kBwdSlots), c3n = min(max(int(cnt.w) - base, 0), kBwdSlots);
+                    const int e1 = c0n + c1n, e2 = e1 + c2n, npairs = e2 + c3n;
+                    for (int pbase = 0; pbase < npairs; pbase += 32) {
+                        const int pi = pbase + lane;
+                        const bool cvalid = pi < npairs;
+                        const int cq = pi < c0n ? 0 : pi < e1 ? 1 : pi < e2 ? 2 : 3;
+                        const int ct = cvalid ? pi - (cq == 0 ? 0 : cq == 1 ? c0n : cq == 2 ? e1 : e2) : 0;
+                        const unsigned int j = cvalid ? sm.list[cq][base + ct] : 0u;
+                        const float4 q0 = r0[j];
+                        const float4 q1 = r1[j];
+                        const int cswz = (ct & 3) | ((ct & 4) << 1);
+                        const int cpl0 = ((cq & 1) << 2) | ((cq & 2) << 3);           // first pixel lane of quarter cq
+                        const float bxq = wx0 + float((cq & 1) * 4), byq = wy0 + float((cq >> 1) * 2);
+                        const float hA2 = 2.0f * q1.x, hC2 = 2.0f * q1.z;
+                        float s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0, s8 = 0, s9 = 0;
+#pragma unroll
+                        for (int p = 0; p < 8; ++p) {
+                            const int pl = cpl0 + (p & 3) + ((p >> 2) << 3);       // pixel lane inside the quarter
+                            const int col = pl ^ cswz;
+                            const float w = cvalid ? stW[ct][col] : 0.0f;
+                            const float dal = cvalid ? stA[ct][col] : 0.0f;
+                            const float G = stG[ct][col];
+                            const float dx = q0.x - (bxq + float(p & 3)), dy = q0.y - (byq + float(p >> 2));
+                            const float dL_dG = q1.w * dal;
+                            const float gdx = G * dx, gdy = G * dy;
+                            // -gdx*A - gdy*B = 2*gdx*hA + gdy*nB   (rec1 = (-A/2, -B, -C/2, o))
+                            s0 = fmaf(dL_dG, fmaf(hA2, gdx, q1.y * gdy), s0);
+                            s1 = fmaf(dL_dG, fmaf(hC2, gdy, q1.y * gdx), s1);
+                            s2 = fmaf(gdx * dx, dL_dG, s2);
+                            s3 = fmaf(gdx * dy, dL_dG, s3);
+                            s4 = fmaf(gdy * dy, dL_dG, s4);
+                            s5 = fmaf(G, dal, s5);
+                            s6 = fmaf(w, sm.dpix[0][pl], s6);
+                            s7 = fmaf(w, sm.dpix[1][pl], s7);
+                            s8 = fmaf(w, sm.dpix[2][pl], s8);
+                            if (kDepthAlphaGrads) s9 = fmaf(w, sm.dpix[3][pl], s9);
+                        }
+                        if (cvalid) {
+                            const unsigned int id = __ldg(ids + cbase + j);
+                            float* g = acc + id;
+                            if (s0 != 0.0f) atomicAdd(g + 0 * a.plane, s0 * ddelx_dx);
+                            if (s1 != 0.0f) atomicAdd(g + 1 * a.plane, s1 * ddely_dy);
+                            if (s2 != 0.0f) atomicAdd(g + 2 * a.plane, -0.5f * s2);
+                            if (s3 != 0.0f) atomicAdd(g + 3 * a.plane, -0.5f * s3);
+                            if (s4 != 0.0f) atomicAdd(g + 4 * a.plane, -0.5f * s4);
+                            if (s5 != 0.0f) atomicAdd(g + 5 * a.plane, s5);
+                            if (s6 != 0.0f) atomicAdd(g + 6 * a.plane, s6);
+                            if (s7 != 0.0f) atomicAdd(g + 7 * a.plane, s7);
+                            if (s8 != 0.0f) atomicAdd(g + 8 * a.plane, s8);
+                            if (kDepthAlphaGrads && s9 != 0.0f) atomicAdd(g + 9 * a.plane, s9);
+                        }
+                    }
+                }
+                __syncwarp();
+                BPH(3);
             }
-            __syncwarp();
         }
         __syncwarp();
     }
@@ -896,16 +987,59 @@ int num_sms() {
 
 // Opts the kernel into its dynamic shared memory size and returns the resident CTAs per SM (cached per kernel).
 template <typename K>
-cudaError_t prepare_kernel(K kernel, size_t smem, int* per_sm) {
+cudaError_t prepare_kernel(K kernel, size_t smem, int* per_sm, int threads = kBlendThreads) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kBlendThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem);
     if (e != cudaSuccess) return e;
     *per_sm = n > 0 ? n : 1;
     return cudaSuccess;
 }
 
+}  // namespace
+
+cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out_depth, float* out_alpha,
+                                 float* out_feed) {
+    FwdArgs a;
+    a.g = c.g; a.render_base = c.render_base; a.blk_off = c.blk_off; a.blk_cnt = c.blk_cnt; a.blk_eff = c.blk_eff;
+    a.rec0 = c.brec0; a.rec1 = c.brec1; a.rec2 = c.brec2; a.bg = c.p->bg; a.n_contrib = c.n_contrib;
+    a.rec0_words = reinterpret_cast<unsigned int*>(c.brec0);
+    a.refine_masks = (c.p->flags & SGR_FLAG_FORWARD_ONLY) ? 0 : 1;
+    a.tile_time = (c.p->flags & SGR_FLAG_TILE_TIMING) ? c.tile_time : nullptr;
+    a.out_color = out_color; a.out_depth = out_depth; a.out_alpha = out_alpha; a.out_feed = out_feed;
+    a.clamp_mask = c.clamp_mask;
+    a.ck0 = c.ck0; a.ck1 = c.ck1; a.plan = c.plan; a.bwd_items = c.bwd_items; a.bwd_items_stride = c.bwd_items_stride;
+    a.work_blend = c.work_blend; a.work_empty = c.work_empty; a.wc = c.work_counts;
+    a.clamp_color = ((c.p->flags & SGR_FLAG_CLAMP_COLOR) || c.loss_target) ? 1 : 0;
+    a.loss_target = c.loss_target; a.loss_mask = c.loss_mask; a.loss_dL_dcolor = c.loss_dL_dcolor;
+    a.loss_part = c.loss_part; a.loss_scale = c.loss_scale;
+    constexpr size_t smem = sizeof(FwdSmem) * kFwdWarps;
+    const bool exact = (c.p->flags & SGR_FLAG_EXACT_EXP) != 0;
+    static int per_sm_dev[kMaxDevices][2] = {};
+    int& per_sm = per_sm_dev[current_device_slot()][exact ? 1 : 0];
+    if (per_sm == 0) {
+        cudaError_t e = exact ? prepare_kernel(blend_forward_kernel<true>, smem, &per_sm, kFwdThreads)
+                              : prepare_kernel(blend_forward_kernel<false>, smem, &per_sm, kFwdThreads);
+        if (e != cudaSuccess) return e;
+    }
+    const long long items = (long long)c.num_renders * c.g.num_tiles * kBlocksPerTile;
+    static int ctas_override = -1;               // experiment hook: SGR_FWD_CTAS_PER_SM
+    if (ctas_override < 0) { const char* v = getenv("SGR_FWD_CTAS_PER_SM"); ctas_override = v ? atoi(v) : 0; }
+    const int use_per_sm = ctas_override > 0 ? min(ctas_override, per_sm) : per_sm;
+    const int grid = int(min((long long)num_sms() * use_per_sm, (items + kFwdWarps - 1) / kFwdWarps));
+    if (exact) blend_forward_kernel<true><<<grid, kFwdThreads, smem, c.stream>>>(a);
+    else blend_forward_kernel<false><<<grid, kFwdThreads, smem, c.stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_loss_reduce(const ChunkCtx& c, float* loss_out) {
+    const unsigned int n = unsigned(c.num_renders) * c.g.num_tiles * kBlocksPerTile;
+    loss_reduce_kernel<<<1, 1024, 0, c.stream>>>(c.loss_part, n, loss_out, c.render_base == 0 ? 1 : 0, c.loss_scale);
+    return cudaGetLastError();
+}
+
+namespace {
 template <bool kDA, bool kExact>
 cudaError_t launch_bwd_variant(const BwdArgs& a, long long want, cudaStream_t stream) {
     constexpr size_t smem = sizeof(BwdSmem) * kWarpsPerCta;
@@ -918,52 +1052,11 @@ cudaError_t launch_bwd_variant(const BwdArgs& a, long long want, cudaStream_t st
     blend_backward_kernel<kDA, kExact><<<int(min((long long)num_sms() * per_sm, want)), kBlendThreads, smem, stream>>>(a);
     return cudaGetLastError();
 }
-
 }  // namespace
-
-cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out_depth, float* out_alpha,
-                                 float* out_feed) {
-    FwdArgs a;
-    a.g = c.g; a.render_base = c.render_base; a.blk_off = c.blk_off; a.blk_cnt = c.blk_cnt; a.q_eff = c.q_eff;
-    a.rec0 = c.brec0; a.rec1 = c.brec1; a.rec2 = c.brec2; a.bg = c.p->bg; a.n_contrib = c.n_contrib;
-    a.rec0_words = reinterpret_cast<unsigned int*>(c.brec0);
-    a.refine_masks = (c.p->flags & SGR_FLAG_FORWARD_ONLY) ? 0 : 1;
-    a.tile_time = (c.p->flags & SGR_FLAG_TILE_TIMING) ? c.tile_time : nullptr;
-    a.out_color = out_color; a.out_depth = out_depth; a.out_alpha = out_alpha; a.out_feed = out_feed;
-    a.clamp_mask = c.clamp_mask;
-    a.ck0 = c.ck0; a.ck1 = c.ck1; a.plan = c.plan; a.bwd_items = c.bwd_items; a.bwd_items_stride = c.bwd_items_stride;
-    a.work_blend = c.work_blend; a.work_empty = c.work_empty; a.wc = c.work_counts;
-    a.clamp_color = ((c.p->flags & SGR_FLAG_CLAMP_COLOR) || c.loss_target) ? 1 : 0;
-    a.loss_target = c.loss_target; a.loss_mask = c.loss_mask; a.loss_dL_dcolor = c.loss_dL_dcolor;
-    a.loss_part = c.loss_part; a.loss_scale = c.loss_scale;
-    constexpr size_t smem = sizeof(FwdSmem) * kWarpsPerCta;
-    const bool exact = (c.p->flags & SGR_FLAG_EXACT_EXP) != 0;
-    static int per_sm_dev[kMaxDevices][2] = {};
-    int& per_sm = per_sm_dev[current_device_slot()][exact ? 1 : 0];
-    if (per_sm == 0) {
-        cudaError_t e = exact ? prepare_kernel(blend_forward_kernel<true>, smem, &per_sm)
-                              : prepare_kernel(blend_forward_kernel<false>, smem, &per_sm);
-        if (e != cudaSuccess) return e;
-    }
-    const long long items = (long long)c.num_renders * c.g.num_tiles * kItemsPerTile;
-    static int ctas_override = -1;               // experiment hook: SGR_FWD_CTAS_PER_SM
-    if (ctas_override < 0) { const char* v = getenv("SGR_FWD_CTAS_PER_SM"); ctas_override = v ? atoi(v) : 0; }
-    const int use_per_sm = ctas_override > 0 ? min(ctas_override, per_sm) : per_sm;
-    const int grid = int(min((long long)num_sms() * use_per_sm, (items + kWarpsPerCta - 1) / kWarpsPerCta));
-    if (exact) blend_forward_kernel<true><<<grid, kBlendThreads, smem, c.stream>>>(a);
-    else blend_forward_kernel<false><<<grid, kBlendThreads, smem, c.stream>>>(a);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_loss_reduce(const ChunkCtx& c, float* loss_out) {
-    const unsigned int n = unsigned(c.num_renders) * c.g.num_tiles * kItemsPerTile;
-    loss_reduce_kernel<<<1, 1024, 0, c.stream>>>(c.loss_part, n, loss_out, c.render_base == 0 ? 1 : 0, c.loss_scale);
-    return cudaGetLastError();
-}
 
 cudaError_t launch_blend_backward(const ChunkCtx& c, const SgrBackwardArgs& b) {
     BwdArgs a;
-    a.g = c.g; a.render_base = c.render_base; a.blk_off = c.blk_off; a.blk_cnt = c.blk_cnt; a.q_eff = c.q_eff;
+    a.g = c.g; a.render_base = c.render_base; a.blk_off = c.blk_off; a.blk_cnt = c.blk_cnt; a.blk_eff = c.blk_eff;
     a.bids = c.bids; a.rec0 = c.brec0; a.rec1 = c.brec1; a.rec2 = c.brec2; a.bg = c.p->bg;
     a.n_contrib = c.n_contrib; a.out_alpha = b.out_alpha; a.dL_dcolor = b.dL_dcolor; a.dL_ddepth = b.dL_ddepth;
     a.dL_dalpha = b.dL_dalpha; a.loss_dL_dcolor = b.loss_dL_dcolor; a.dL_dfeed = b.dL_dlpips_feed;
@@ -971,7 +1064,7 @@ cudaError_t launch_blend_backward(const ChunkCtx& c, const SgrBackwardArgs& b) {
     a.accum = c.accum; a.plane = size_t(c.num_renders) * c.g.N;
     a.ck0 = c.ck0; a.ck1 = c.ck1; a.bwd_items = c.bwd_items; a.bwd_items_stride = c.bwd_items_stride;
     a.plan = c.plan; a.dL_scale = b.dL_dcolor_scale;
-    const long long items = (long long)c.num_renders * c.g.num_tiles * kItemsPerTile;
+    const long long items = (long long)c.num_renders * c.g.num_tiles * kBlocksPerTile;
     const long long want = (items + kWarpsPerCta - 1) / kWarpsPerCta;
     const bool exact = (c.p->flags & SGR_FLAG_EXACT_EXP) != 0;
     if (b.dL_ddepth || b.dL_dalpha)
@@ -980,3 +1073,12 @@ cudaError_t launch_blend_backward(const ChunkCtx& c, const SgrBackwardArgs& b) {
 }
 
 }  // namespace sgr
+
+#ifdef SGR_PHASE_TIMING
+extern "C" int sgr_debug_phase_counters(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, sgr::g_phase, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(sgr::g_phase, z, sizeof(z)); }
+    return 0;
+}
+#endif

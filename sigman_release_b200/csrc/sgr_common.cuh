@@ -12,12 +12,10 @@ constexpr int kTile = 16;                 // BLOCK_X = BLOCK_Y of the published 
 constexpr int kTilePixels = kTile * kTile;
 constexpr int kDefaultRendersPerChunk = 16;
 constexpr int kBlocksPerTile = 8;            // a 16x16 tile = eight 8x4 pixel blocks (blk = (y block) * 2 + (x block))
-constexpr int kQuartersPerBlock = 4;         // an 8x4 block = four 4x2 quarters (q = x half | y half << 1): one blend work item each
-constexpr int kItemsPerTile = kBlocksPerTile * kQuartersPerBlock;
 // Block lists: the per-tile sort emits, for every 8x4 pixel block of a tile, the depth-ordered sub-list of the tile's
 // instances whose conservative extent touches the block ("block records": the 48-byte record + the Gaussian id).  The
-// blend kernels stream block lists, so a warp never fetches a record that cannot touch its block.
-// Backward work granularity: a block list is replayed per quarter in independent segments of kSegB block records (multiple of the
+// blend kernels stream block lists, so a warp never fetches or culls a record that cannot touch its pixels.
+// Backward work granularity: a block list is replayed in independent segments of kSegB block records (multiple of the
 // blend kernels' batch).  The forward blend checkpoints every pixel's running state at the segment boundaries of
 // lists longer than one segment; slot (block list, s) = blk_off / (kSegB / 2) + s, s < #segments, the last slot
 // holding the final state (a list of m > kSegB records spans at least ceil(m / kSegB) slots of that numbering).
@@ -52,7 +50,7 @@ struct ChunkPlan {
 // Layout of `state` (kept forward -> backward) for a problem shape.
 struct StateLayout {
     uint64_t header, tile_off, tile_cnt, tile_time, n_contrib, clamp_mask, sorted_ids, rec0, rec1, rec2, blk_off, blk_cnt,
-        q_eff, brec0, brec1, brec2, bids, ck0, ck1, plan, bwd_items, bwd_items_stride, total;
+        blk_eff, brec0, brec1, brec2, bids, ck0, ck1, plan, bwd_items, bwd_items_stride, total;
 };
 // Layout of `scratch` (valid only inside one call).
 struct ScratchLayout {
@@ -85,7 +83,7 @@ inline StateLayout make_state_layout(int B, int V, int N, int H, int W, uint64_t
     L.rec2 = o;        o = align_up(o + rec_cap * 16);
     L.blk_off = o;     o = align_up(o + R * T * kBlocksPerTile * 4);
     L.blk_cnt = o;     o = align_up(o + R * T * kBlocksPerTile * 4);
-    L.q_eff = o;       o = align_up(o + R * T * kItemsPerTile * 4);
+    L.blk_eff = o;     o = align_up(o + R * T * kBlocksPerTile * 4);
     L.brec0 = o;       o = align_up(o + blk_cap * 16);
     L.brec1 = o;       o = align_up(o + blk_cap * 16);
     L.brec2 = o;       o = align_up(o + blk_cap * 16);
@@ -93,8 +91,8 @@ inline StateLayout make_state_layout(int B, int V, int N, int H, int W, uint64_t
     L.ck0 = o;         o = align_up(o + ckpt_slots(blk_cap) * kCkptPerSlot * 16);   // (T, C0, C1, C2) per pixel and slot
     L.ck1 = o;         o = align_up(o + ckpt_slots(blk_cap) * kCkptPerSlot * 4);    // D
     L.plan = o;        o = align_up(o + R * sizeof(ChunkPlan));                     // one per chunk (at most R chunks)
-    // backward items: a chunk of n tiles and m block records emits at most 32 n + 4 (m / kSegB) items per class
-    L.bwd_items_stride = R * T * kItemsPerTile + kQuartersPerBlock * (blk_cap / kSegB) + R + 1;
+    // backward items: a chunk of n tiles and m block records emits at most 8 n + m / kSegB items per class
+    L.bwd_items_stride = R * T * kBlocksPerTile + blk_cap / kSegB + R + 1;
     L.bwd_items = o;   o = align_up(o + L.bwd_items_stride * kBwdClasses * 8);
     L.total = o;
     return L;
@@ -117,7 +115,7 @@ inline ScratchLayout make_scratch_layout(int B, int V, int N, int H, int W, uint
     L.work_blend = o;  o = align_up(o + Rc * T * 4);
     L.work_empty = o;  o = align_up(o + Rc * T * 4);
     L.work_counts = o; o = align_up(o + 256);
-    L.loss_part = o;   o = align_up(o + Rc * T * kItemsPerTile * 4);               // fused loss: one partial per work item
+    L.loss_part = o;   o = align_up(o + Rc * T * 8 * 4);                           // fused loss: one partial per work item
     L.accum = o;       o = align_up(o + Rc * N * 4 * kAccumPlanes);
     L.total = o;
     return L;
@@ -248,8 +246,7 @@ struct ChunkCtx {
     unsigned int* sorted_ids; // [cap]
     float4 *rec0, *rec1, *rec2;   // [cap] tile-level records (SGR_FLAG_SIMPLE_BLEND only)
     unsigned char* clamp_mask; // [R*P]
-    unsigned int *blk_off, *blk_cnt;             // [R*T*8] block lists: start, records
-    unsigned int* q_eff;                         // [R*T*32] per quarter: records of its block list the backward replays
+    unsigned int *blk_off, *blk_cnt, *blk_eff;   // [R*T*8] block lists: start, records, records the backward replays
     float4 *brec0, *brec1, *brec2;               // [capB] block records
     unsigned int* bids;                          // [capB] Gaussian id of every block record
     unsigned long long blk_capacity;
@@ -267,7 +264,7 @@ struct ChunkCtx {
     unsigned int* cursor;     // [Rc*T]
     unsigned int *work_blend, *work_empty;
     WorkCounts* work_counts;
-    float* loss_part;         // [Rc*T*32] fused-loss partial sums, one per (render, tile, block, quarter)
+    float* loss_part;         // [Rc*T*8] fused-loss partial sums, one per (render, tile, pixel block)
     float* accum;             // [kAccumPlanes][Rc*N]
     // optional fused loss (forward)
     const float *loss_target, *loss_mask;
