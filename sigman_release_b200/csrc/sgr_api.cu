@@ -115,10 +115,7 @@ void fill_ctx(ChunkCtx& c, const SgrProblem& p, void* state, void* scratch, cuda
     c.blk_off = reinterpret_cast<unsigned int*>(s + S.blk_off);
     c.blk_cnt = reinterpret_cast<unsigned int*>(s + S.blk_cnt);
     c.blk_eff = reinterpret_cast<unsigned int*>(s + S.blk_eff);
-    c.brec0 = reinterpret_cast<float4*>(s + S.brec0);
-    c.brec1 = reinterpret_cast<float4*>(s + S.brec1);
-    c.brec2 = reinterpret_cast<float4*>(s + S.brec2);
-    c.bids = reinterpret_cast<unsigned int*>(s + S.bids);
+    c.bidx = reinterpret_cast<unsigned int*>(s + S.bidx);
     c.blk_capacity = (p.flags & SGR_FLAG_SIMPLE_BLEND) ? 0ull : p.max_block_records;
     c.ck0 = reinterpret_cast<float4*>(s + S.ck0);
     c.ck1 = reinterpret_cast<float*>(s + S.ck1);

@@ -164,19 +164,19 @@ struct SortArgs {
     const unsigned int* tile_off;    // global arrays
     const unsigned int* tile_cnt;
     const unsigned long long* keys;
+    unsigned long long* keys_w;      // the same buffer, writable: (mask, id) pairs of spilled tiles after their keys are dead
     unsigned long long* keys_tmp;    // second key buffer [cap]: bucket-ordered keys of lists beyond the shared memory
     unsigned int* sorted_ids;
-    float4 *rec0, *rec1, *rec2;      // tile-level records (simple != 0 only)
+    float4 *rec0, *rec1, *rec2;      // tile-level records in depth order
     const float4 *g0, *g1, *g2;
     const unsigned int* work;        // chunk-local indices of the non-empty tiles, longest list first
     WorkCounts* wc;                  // n_big: the first n_big tiles go to the big kernel; sort_cursor: small queue
     unsigned int big_smem_keys;      // key capacity of the big kernel's shared-memory buffer
-    int simple;                      // SGR_FLAG_SIMPLE_BLEND: emit tile-level records instead of block lists
+    int simple;                      // SGR_FLAG_SIMPLE_BLEND: no block lists
     // block lists (simple == 0)
     StateHeader* header;
     unsigned int *blk_off, *blk_cnt;
-    float4 *brec0, *brec1, *brec2;
-    unsigned int* bids;
+    unsigned int* bidx;              // block-list entries (position in the tile list << 4 | quarter mask)
     unsigned long long blk_capacity;
 };
 
@@ -250,7 +250,7 @@ __device__ __forceinline__ void block_exclusive_scan(unsigned int* hist, unsigne
 // over the unsorted keys (range, histogram, scatter) cost ONE exposed global-memory latency instead of three (the
 // per-tile sort is a latency chain, not a bandwidth problem); KPT == 0 re-reads the keys from global memory.
 template <int THREADS, int NB, int KPT>
-__device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local, unsigned long long* kb,
+__device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local, unsigned long long* kb, unsigned int* aux,
                                               unsigned int* hist, unsigned int* s_warp, unsigned long long* s_red) {
     const int t = threadIdx.x;
     const int rl = tile_local / a.num_tiles;
@@ -316,7 +316,6 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
     // 4. exact rank inside the bucket -> final position of the id (upstream's point_list).  Unrolled so that several
     //    independent chains are in flight per thread (the step is L2-latency bound).  With `simple` the owner of an
     //    element also gathers its 48-byte record into depth order (tile-level stream of the upstream-shaped kernels).
-    unsigned int* ids = a.sorted_ids + off;
     const size_t gb = size_t(rl) * a.N;
     const int tile = tile_local - rl * a.num_tiles;
     const float X0 = float((tile % a.tiles_x) * kTile), Y0 = float((tile / a.tiles_x) * kTile);
@@ -331,43 +330,50 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
         const unsigned int id = static_cast<unsigned int>(key & 0xffffffffull);
         const size_t pos = off + s + cnt;
         a.sorted_ids[pos] = id;
-        if (a.simple) {
-            float4 v0 = __ldg(a.g0 + gb + id);
-            v0.z = __uint_as_float(quarter_mask(v0.x, v0.y, v0.z, X0, Y0));
-            a.rec0[pos] = v0;
-            a.rec1[pos] = __ldg(a.g1 + gb + id);
-            a.rec2[pos] = __ldg(a.g2 + gb + id);
-        }
+        // the owner of an element gathers its 48-byte record into depth order (the tile-level stream); word 2 of rec0
+        // becomes the instance's position in the tile list (upstream's contributor index)
+        float4 v0 = __ldg(a.g0 + gb + id);
+        const unsigned int mask = quarter_mask(v0.x, v0.y, v0.z, X0, Y0);   // the instance's cull mask for this tile
+        v0.z = __uint_as_float(s + cnt);
+        a.rec0[pos] = v0;
+        a.rec1[pos] = __ldg(a.g1 + gb + id);
+        a.rec2[pos] = __ldg(a.g2 + gb + id);
+        if (!a.simple) aux[s + cnt] = mask;              // masks in sorted order for the block-list emission
     }
     __syncthreads();
     if (a.simple) return;
 
     // 5. block lists.  Every instance is appended to the list of each 8x4 pixel block of the tile that its
-    //    conservative alpha >= 1/255 extent touches (quarter_mask), keeping the depth order: two sweeps over the sorted
-    //    ids in chunks of 32 (lane = record) around a scan of the per-chunk, per-block counts.  The key buffer is dead
-    //    after the ranking and is reused for the masks and the counts.  Block record = the instance's record with
-    //    word 2 of rec0 = (position in the tile list << 4 | the block's 4-bit quarter mask) + the Gaussian id.
+    //    conservative alpha >= 1/255 extent touches (quarter_mask), keeping the depth order: per chunk of 32 sorted
+    //    instances (lane = record) one ballot per block, a scan of the per-chunk counts, then the copies.  The key
+    //    buffer is dead after the ranking and holds the counts.  A block-list entry is 4 bytes: (position in the tile
+    //    list << 4 | the block's 4-bit quarter mask); the blend kernels gather the records themselves from the
+    //    tile-level stream (cp.async), so the 48-byte records are written once per instance, not once per block.
+    //    Every list starts at a multiple of 4 entries (16-byte aligned: the index batches travel by 1-D TMA).
     const size_t tgb = tg * kBlocksPerTile;
     const unsigned int nchunks = (n + 31u) >> 5;
-    unsigned int* mbuf = reinterpret_cast<unsigned int*>(kb);              // [32 * nchunks] quarter masks, sorted order
-    unsigned int* cpre = mbuf + 32u * nchunks;                             // [nchunks][8] counts -> exclusive prefixes
+    unsigned int* cpre = reinterpret_cast<unsigned int*>(kb);              // [nchunks][8] counts -> exclusive prefixes
     const int warp = t >> 5, lane = t & 31;
     constexpr int kWarps = THREADS / 32;
-    for (unsigned int c = warp; c < nchunks; c += kWarps) {
-        const unsigned int p = 32u * c + lane;
-        unsigned int mask = 0;
-        if (p < n) {
-            const float4 v0 = __ldg(a.g0 + gb + ids[p]);
-            mask = quarter_mask(v0.x, v0.y, v0.z, X0, Y0);
-        }
-        mbuf[p] = mask;
-        unsigned int mine = 0;
+    for (unsigned int c0 = warp; c0 < nchunks; c0 += 4 * kWarps) {      // four chunks in flight per warp
+        unsigned int mk[4];
 #pragma unroll
-        for (int b = 0; b < kBlocksPerTile; ++b) {
-            const unsigned int bal = __ballot_sync(0xffffffffu, (mask >> (4 * b)) & 0xfu);
-            if (lane == b) mine = __popc(bal);
+        for (int k = 0; k < 4; ++k) {
+            const unsigned int p = 32u * (c0 + k * kWarps) + lane;
+            mk[k] = p < n ? aux[p] : 0u;
         }
-        if (lane < kBlocksPerTile) cpre[c * kBlocksPerTile + lane] = mine;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned int c = c0 + k * kWarps;
+            if (c >= nchunks) break;
+            unsigned int mine = 0;
+#pragma unroll
+            for (int b = 0; b < kBlocksPerTile; ++b) {
+                const unsigned int bal = __ballot_sync(0xffffffffu, (mk[k] >> (4 * b)) & 0xfu);
+                if (lane == b) mine = __popc(bal);
+            }
+            if (lane < kBlocksPerTile) cpre[c * kBlocksPerTile + lane] = mine;
+        }
     }
     __syncthreads();
     if (warp < kBlocksPerTile) {                 // warp w: exclusive scan of block w's chunk counts
@@ -387,10 +393,10 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
         if (lane == 0) s_warp[warp] = running;
     }
     __syncthreads();
-    if (t == 0) {                                // reserve the tile's block records (bump allocation)
+    if (t == 0) {                                // reserve the tile's block-list entries (bump allocation)
         unsigned int total = 0;
 #pragma unroll
-        for (int b = 0; b < kBlocksPerTile; ++b) total += s_warp[b];
+        for (int b = 0; b < kBlocksPerTile; ++b) total += (s_warp[b] + 3u) & ~3u;
         const unsigned long long base = atomicAdd(&a.header->blk_required, static_cast<unsigned long long>(total));
         const bool fits = base + total <= a.blk_capacity;
         if (!fits) atomicOr(&a.header->overflow, 2u);     // the tile's blocks stay empty; reported via the status
@@ -400,39 +406,41 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
             a.blk_off[tgb + b] = fits ? run : 0u;
             a.blk_cnt[tgb + b] = fits ? s_warp[b] : 0u;
             s_warp[8 + b] = run;
-            run += s_warp[b];
+            run += (s_warp[b] + 3u) & ~3u;
         }
         s_warp[16] = fits ? 1u : 0u;
     }
     __syncthreads();
     if (s_warp[16]) {
         const unsigned int lt = (1u << lane) - 1u;
-        for (unsigned int c = warp; c < nchunks; c += kWarps) {
-            const unsigned int p = 32u * c + lane;
-            const unsigned int mask = mbuf[p];
-            unsigned int id = 0;
-            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;
-            if (mask) {
-                id = ids[p];
-                v0 = __ldg(a.g0 + gb + id);
-                v1 = __ldg(a.g1 + gb + id);
-                v2 = __ldg(a.g2 + gb + id);
+        for (unsigned int c0 = warp; c0 < nchunks; c0 += 4 * kWarps) {      // four chunks in flight per warp
+            unsigned int mk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned int p = 32u * (c0 + k * kWarps) + lane;
+                mk[k] = p < n ? aux[p] : 0u;
             }
 #pragma unroll
-            for (int b = 0; b < kBlocksPerTile; ++b) {
-                const unsigned int nib = (mask >> (4 * b)) & 0xfu;
-                const unsigned int bal = __ballot_sync(0xffffffffu, nib);
-                if (nib) {
-                    const size_t dst = size_t(s_warp[8 + b]) + cpre[c * kBlocksPerTile + b] + __popc(bal & lt);
-                    a.brec0[dst] = make_float4(v0.x, v0.y, __uint_as_float((p << 4) | nib), v0.w);
-                    a.brec1[dst] = v1;
-                    a.brec2[dst] = v2;
-                    a.bids[dst] = id;
+            for (int k = 0; k < 4; ++k) {
+                const unsigned int c = c0 + k * kWarps;
+                if (c >= nchunks) break;
+                const unsigned int p = 32u * c + lane;
+#pragma unroll
+                for (int b = 0; b < kBlocksPerTile; ++b) {
+                    const unsigned int nib = (mk[k] >> (4 * b)) & 0xfu;
+                    const unsigned int bal = __ballot_sync(0xffffffffu, nib);
+                    if (nib)
+                        a.bidx[size_t(s_warp[8 + b]) + cpre[c * kBlocksPerTile + b] + __popc(bal & lt)] = (p << 4) | nib;
                 }
             }
         }
+        // the pad entries (up to 3 per list) are read by the 16-byte granular index copies: quarter mask 0
+        if (t < kBlocksPerTile) {
+            const unsigned int cnt_b = s_warp[t];
+            for (unsigned int k = cnt_b; k < ((cnt_b + 3u) & ~3u); ++k) a.bidx[size_t(s_warp[8 + t]) + k] = 0u;
+        }
     }
-    __syncthreads();                             // the key buffer is reused by the CTA's next tile
+    __syncthreads();                             // the buffers are reused by the CTA's next tile
 }
 
 #ifndef SGR_SORT_SMALL_MIN_CTAS
@@ -452,12 +460,15 @@ __global__ void __launch_bounds__(kSmallSortThreads, SGR_SORT_SMALL_MIN_CTAS) so
         const unsigned int w = s_item;
         if (w >= nw) break;
         const int tile_local = a.work[w];
-        const unsigned int n = a.tile_cnt[size_t(a.render_base) * a.num_tiles + tile_local];
+        const size_t tg = size_t(a.render_base) * a.num_tiles + tile_local;
+        const unsigned int n = a.tile_cnt[tg];
+        // (quarter mask, Gaussian id) pairs in sorted order: the tile's own key segment, dead once the keys sit in kb
+        unsigned int* aux = reinterpret_cast<unsigned int*>(a.keys_w + a.tile_off[tg]);
         if (n <= 4u * kSmallSortThreads)
-            sort_one_tile<kSmallSortThreads, kSmallSortBuckets, 4>(a, tile_local, kb, hist, s_warp, s_red);
+            sort_one_tile<kSmallSortThreads, kSmallSortBuckets, 4>(a, tile_local, kb, aux, hist, s_warp, s_red);
         else
             sort_one_tile<kSmallSortThreads, kSmallSortBuckets, kSmallSortCap / kSmallSortThreads>(
-                a, tile_local, kb, hist, s_warp, s_red);
+                a, tile_local, kb, aux, hist, s_warp, s_red);
     }
     // Programmatic dependent launch (launch_sort_tiles): this grid started before sort_big_kernel finished.  The
     // blend behind it in the stream is ordered after THIS grid only, so every CTA waits here for the long-list
@@ -469,7 +480,7 @@ __global__ void __launch_bounds__(kSmallSortThreads, SGR_SORT_SMALL_MIN_CTAS) so
 
 __global__ void __launch_bounds__(kBigSortThreads) sort_big_kernel(SortArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* kb_s = reinterpret_cast<unsigned long long*>(smem_raw);                 // kBigSortSmemCap
+    unsigned long long* kb_s = reinterpret_cast<unsigned long long*>(smem_raw);                 // big_smem_keys
     unsigned int* hist = reinterpret_cast<unsigned int*>(kb_s + a.big_smem_keys);               // kBigSortBuckets
     // Programmatic dependent launch: the short-list kernel behind this one in the stream may start as soon as every
     // CTA of this grid is resident (it does not consume this kernel's output) — see launch_sort_tiles.
@@ -481,13 +492,15 @@ __global__ void __launch_bounds__(kBigSortThreads) sort_big_kernel(SortArgs a) {
         const int tile_local = a.work[w];
         const size_t tg = size_t(a.render_base) * a.num_tiles + tile_local;
         const unsigned int n = a.tile_cnt[tg];
-        // lists that do not fit in shared memory use their segment of the second global key buffer
+        // lists that do not fit in shared memory use their segment of the second global key buffer; the (mask, id)
+        // pairs in sorted order go to the tile's own segment of the first one, dead once the keys sit in kb
         const bool spill = n > a.big_smem_keys;
         unsigned long long* kb = spill ? a.keys_tmp + a.tile_off[tg] : kb_s;
+        unsigned int* aux = reinterpret_cast<unsigned int*>(a.keys_w + a.tile_off[tg]);
         if (n <= 8u * kBigSortThreads && !spill)
-            sort_one_tile<kBigSortThreads, kBigSortBuckets, 8>(a, tile_local, kb, hist, s_warp, s_red);
+            sort_one_tile<kBigSortThreads, kBigSortBuckets, 8>(a, tile_local, kb, aux, hist, s_warp, s_red);
         else
-            sort_one_tile<kBigSortThreads, kBigSortBuckets, 0>(a, tile_local, kb, hist, s_warp, s_red);
+            sort_one_tile<kBigSortThreads, kBigSortBuckets, 0>(a, tile_local, kb, aux, hist, s_warp, s_red);
     }
 }
 
@@ -521,10 +534,10 @@ cudaError_t launch_sort_tiles(const ChunkCtx& c) {
     a.tile_off = c.tile_off; a.tile_cnt = c.tile_cnt; a.keys = c.keys; a.sorted_ids = c.sorted_ids;
     a.rec0 = c.rec0; a.rec1 = c.rec1; a.rec2 = c.rec2; a.g0 = c.g0; a.g1 = c.g1; a.g2 = c.g2;
     a.work = c.work_blend; a.wc = c.work_counts;
-    a.keys_tmp = c.keys_tmp;
+    a.keys_tmp = c.keys_tmp; a.keys_w = c.keys;
     a.simple = (c.p->flags & SGR_FLAG_SIMPLE_BLEND) ? 1 : 0;
     a.header = c.header; a.blk_off = c.blk_off; a.blk_cnt = c.blk_cnt;
-    a.brec0 = c.brec0; a.brec1 = c.brec1; a.brec2 = c.brec2; a.bids = c.bids; a.blk_capacity = c.blk_capacity;
+    a.bidx = c.bidx; a.blk_capacity = c.blk_capacity;
     const int dslot = current_device_slot();
     static int num_sms_dev[kMaxDevices] = {};
     static bool attr_set_dev[kMaxDevices] = {};

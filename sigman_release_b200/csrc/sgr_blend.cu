@@ -125,39 +125,50 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 
 constexpr int kListPad = 16;                   // keeps the rows 16-byte aligned
 
-template <int kStashes, int kDepth, int kNumStages, int kBatch>
-struct WarpSmem {
-    static constexpr int stages = kNumStages;
-    float4 r0[kNumStages][kBatch + 1];          // slot kBatch of every stage = the sentinel record (never blends)
+constexpr int kIxStages = 2;                   // backward index batches: one being walked, one in flight
+
+// Forward: a 2-stage ring of gathered records; the index entries travel through registers.
+template <int kNumStages, int kBatch>
+struct FwdWarpSmem {
+    float4 r0[kNumStages][kBatch + 1];          // gathered records; slot kBatch of every stage = the sentinel record
     float4 r1[kNumStages][kBatch + 1];
     float4 r2[kNumStages][kBatch + 1];
-    float stash[kStashes][kDepth][32];
-    float dpix[4][32];                          // backward: dL/dcolor (3) and dL/ddepth of the block's pixels
     // per quarter: batch-local indices of the survivors, sentinel-filled; the trip loops read whole groups of 4 / 8
     // entries starting at multiples of their size, which stays inside kBatch — the pad is a safety margin
     unsigned char list[4][kBatch + kListPad];
-    unsigned int hit[kBatch + 1];               // forward: byte q of word j != 0 <=> quarter q blended record j
-    uint64_t full[kNumStages];
+    unsigned int hit[kBatch + 1];               // byte q of word j != 0 <=> quarter q blended record j
+};
+// Backward: one stage of gathered records, the index entries in a TMA-fed ring, the phase B -> C stash.
+template <int kDepth, int kBatch>
+struct BwdWarpSmem {
+    float4 r0[1][kBatch + 1];
+    float4 r1[1][kBatch + 1];
+    float4 r2[1][kBatch + 1];
+    alignas(16) unsigned int ix[kIxStages][kBatch];   // block-list entries (tile-list position << 4 | quarter mask)
+    float stash[2][kDepth][32];
+    float dpix[4][32];                          // dL/dcolor (3) and dL/ddepth of the block's pixels
+    unsigned char list[4][kBatch + kListPad];
+    unsigned int hit[kBatch + 1];               // Gaussian id of record j of the batch (gathered with it)
+    uint64_t ixbar[kIxStages];
 };
 
-// Cull a batch of m <= kBatch block records against the four 4x2 quarters of the warp's 8x4 pixel block:
-// 32 records per round (lane = record) read their 4-bit quarter mask (low bits of rec0.z, built by the tile sort
-// from sgr_common.cuh::quarter_mask), one ballot per quarter, warp-parallel compaction of the survivors'
+// Cull a batch of m <= kBatch block-list entries against the four 4x2 quarters of the warp's 8x4 pixel block:
+// 32 entries per round (lane = entry) read their 4-bit quarter mask (low bits of the entry, built by the tile sort
+// from sgr_common.cuh::quarter_mask and refined by the forward), one ballot per quarter, warp-parallel compaction of the survivors'
 // batch-local indices into list[quarter][...] (ascending; descending with kReverse — the backward walks back to front);
 // unused list entries point at the sentinel record.  Returns the four survivor counts.
 template <bool kReverse, int kBatch>
-__device__ __forceinline__ uint4 cull_batch(const float4* r0, unsigned int m,
+__device__ __forceinline__ uint4 cull_batch(const unsigned int (&ent)[kBatch / 32], unsigned int m,
                                             unsigned char (*list)[kBatch + kListPad],
                                             int lane, unsigned int (&bits)[kBatch / 32]) {
     // Straight-line code (the per-batch overhead is latency, not work): all mask words are loaded first, then all
-    // ballots, then the compaction stores.  bits[r] = this lane's 4-bit quarter mask of record 32 * r + lane.
+    // ballots, then the compaction stores.  ent[r] = this lane's entry 32 * r + lane of the batch, bits[r] = its 4-bit quarter mask.
     constexpr int R = kBatch / 32;
     const unsigned int lt = kReverse ? ~((2u << lane) - 1u) : (1u << lane) - 1u;   // lanes before / after this one
-    const unsigned int* words = reinterpret_cast<const unsigned int*>(r0);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const unsigned int e = 32u * r + lane;
-        bits[r] = (e < m) ? (words[4 * e + 2] & 0xfu) : 0u;
+        bits[r] = (e < m) ? (ent[r] & 0xfu) : 0u;
     }
     {                             // every list entry the compaction does not overwrite points at the sentinel record
         constexpr unsigned int fill = kBatch * 0x01010101u;
@@ -189,19 +200,63 @@ __device__ __forceinline__ uint4 cull_batch(const float4* r0, unsigned int m,
     return make_uint4(n[0], n[1], n[2], n[3]);
 }
 
-// Per-warp TMA ring: `issued` / `consumed` count batches over the whole kernel (stage = k % stages,
-// parity = (k / stages) & 1), so the mbarriers never need re-initialisation between work items.
+// Per-warp index ring: the k-th index batch of the kernel's lifetime goes to stage k % kIxStages and completes phase
+// (k / kIxStages) & 1 of that stage's mbarrier, so the barriers never need re-initialisation between work items.
+// One 1-D TMA bulk copy of the batch's entries, rounded up to a multiple of 4 (lists start 16-byte aligned and are
+// padded to a multiple of 4 entries by the tile sort).
 template <typename Smem>
-__device__ __forceinline__ void ring_issue(Smem& sm, unsigned int issued, const float4* g0, const float4* g1,
-                                           const float4* g2, unsigned int m, int lane) {
+__device__ __forceinline__ void ix_issue(Smem& sm, unsigned int k, const unsigned int* src, unsigned int m, int lane) {
     if (lane == 0) {
-        const int s = issued % Smem::stages;
-        const uint32_t bytes = m * 16u;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the slot are done
-        mbar_arrive_expect_tx(&sm.full[s], 3u * bytes);
-        tma_load_1d(sm.r0[s], g0, bytes, &sm.full[s]);
-        tma_load_1d(sm.r1[s], g1, bytes, &sm.full[s]);
-        tma_load_1d(sm.r2[s], g2, bytes, &sm.full[s]);
+        const int st = k % kIxStages;
+        const uint32_t bytes = ((m + 3u) & ~3u) * 4u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the stage are done
+        mbar_arrive_expect_tx(&sm.ixbar[st], bytes);
+        tma_load_1d(sm.ix[st], src, bytes, &sm.ixbar[st]);
+    }
+}
+template <typename Smem>
+__device__ __forceinline__ void ix_wait(Smem& sm, unsigned int k) {
+    mbar_wait(&sm.ixbar[k % kIxStages], (k / kIxStages) & 1);
+}
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Gathers the records of a batch of block-list entries from the tile's depth-ordered stream into ring stage rs
+// (lane = entry; asynchronous 16-byte copies, one commit group per batch).  Entries whose quarter mask is 0 (pads,
+// and — in the backward — records the forward found not to blend) are not fetched: the cull never selects them.
+template <bool kIds, int kRounds, typename Smem>
+__device__ __forceinline__ void gather_batch(Smem& sm, int rs, const unsigned int (&ent)[kRounds], unsigned int m,
+                                             const float4* t0, const float4* t1, const float4* t2,
+                                             const unsigned int* tids, int lane) {
+#pragma unroll
+    for (int rr = 0; rr < kRounds; ++rr) {
+        const unsigned int e = 32u * rr + lane;
+        if (e < m && (ent[rr] & 0xfu)) {
+            const unsigned int p = ent[rr] >> 4;
+            cp_async16(&sm.r0[rs][e], t0 + p);
+            cp_async16(&sm.r1[rs][e], t1 + p);
+            cp_async16(&sm.r2[rs][e], t2 + p);
+            if (kIds) cp_async4(&sm.hit[e], tids + p);
+        }
+    }
+    cp_async_commit();
+}
+
+// This lane's entries 32 * r + lane of a batch of m <= kBatch block-list entries (coalesced loads; 0 beyond the batch).
+template <int kRounds>
+__device__ __forceinline__ void load_entries(unsigned int (&ent)[kRounds], const unsigned int* src, unsigned int m, int lane) {
+#pragma unroll
+    for (int rr = 0; rr < kRounds; ++rr) {
+        const unsigned int e = 32u * rr + lane;
+        ent[rr] = e < m ? __ldg(src + e) : 0u;
     }
 }
 
@@ -213,15 +268,6 @@ __device__ __forceinline__ unsigned int pop_item(unsigned int* cursor, unsigned 
     return w < n_items ? w : 0xffffffffu;
 }
 
-#ifdef SGR_PHASE_TIMING
-// Experiment build only: cycles spent per phase by lane 0 of (a) all items, (b) block 7 of the first (longest) tile.
-__device__ unsigned long long g_phase[16];
-#define PHASE_T0() const long long pt0__ = clock64()
-#define PHASE_ADD(k) do { const long long d__ = clock64() - pt0__; ph[k] += d__; } while (0)
-#else
-#define PHASE_T0()
-#define PHASE_ADD(k)
-#endif
 
 // ------------------------------------------------------------------------------------------------ forward
 struct FwdArgs {
@@ -230,8 +276,9 @@ struct FwdArgs {
     const unsigned int* blk_off;  // [R*T*8] block lists (sgr_binning.cu step 5)
     const unsigned int* blk_cnt;
     unsigned int* blk_eff;        // out: records of the block list the backward has to replay
-    const float4 *rec0, *rec1, *rec2;   // block records
-    unsigned int* rec0_words;     // rec0 as words: the forward refines the quarter masks (word 2 of every record)
+    const unsigned int* tile_off; // [R*T] start of the tile's depth-ordered records
+    const float4 *rec0, *rec1, *rec2;   // tile-level records
+    unsigned int* bidx;           // block-list entries; the forward refines their quarter masks in place
     int refine_masks;
     const float* bg;
     unsigned int* n_contrib;
@@ -321,8 +368,8 @@ __device__ __forceinline__ void write_pixel(const FwdArgs& a, int r, size_t P, i
     }
 }
 
-using FwdSmem = WarpSmem<1, 1, kFwdStages, kFwdBatch>;      // the forward needs no stash
-using BwdSmem = WarpSmem<3, kBwdSlots, kBwdStages, kBwdBatch>;
+using FwdSmem = FwdWarpSmem<kFwdStages, kFwdBatch>;
+using BwdSmem = BwdWarpSmem<kBwdSlots, kBwdBatch>;
 
 #ifndef SGR_FWD_GROUP8
 #define SGR_FWD_GROUP8 1
@@ -350,16 +397,9 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
     const size_t P = size_t(a.g.H) * a.g.W;
     const float bg0 = a.bg[0], bg1 = a.bg[1], bg2 = a.bg[2];
     const unsigned int n_items = a.wc->n_blend * kBlocksPerTile, n_empty_items = a.wc->n_empty * kBlocksPerTile;
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < kFwdStages; ++s) mbar_init(&sm.full[s], 1);
-        fence_barrier_init();
-    }
-    __syncwarp();
     const int qsel = ((lane >> 2) & 1) | ((lane >> 3) & 2);        // 4x2 pixel quarter of this lane: x half | 2 * y half
     const unsigned int qmask = 0x00000f0fu << ((lane & 4) | (lane & 16));   // the quarter's 8 lanes
     const unsigned char* mylist = sm.list[qsel];
-    unsigned int issued = 0, consumed = 0;       // ring counters (warp-uniform)
     const bool refine = a.refine_masks != 0;
     unsigned char* hit_bytes = reinterpret_cast<unsigned char*>(sm.hit) + qsel;       // indexed with 4 * j
 #pragma unroll
@@ -410,31 +450,33 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
         const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
         const bool inside = px < a.g.W && py < a.g.H;
         const float pxf = float(px), pyf = float(py);
-        const float4 *g0 = a.rec0 + off, *g1 = a.rec1 + off, *g2 = a.rec2 + off;
+        const size_t toff = a.tile_off[tg];
+        const float4 *g0 = a.rec0 + toff, *g1 = a.rec1 + toff, *g2 = a.rec2 + toff;
+        const unsigned int* lst = a.bidx + off;
 
         float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, D = 0.0f, Wt = 0.0f;
         unsigned int last = 0;
         bool done = !inside;
-        unsigned int b_issued = 0;
         unsigned int seg_hits = 0, eff = 0;      // records of the current segment that blended; last such record + 1
-#ifdef SGR_PHASE_TIMING
-        long long ph[5] = {0, 0, 0, 0, 0};
-        unsigned long long ntrips = 0;
-#endif
-        while (b_issued < nb && b_issued < unsigned(kFwdStages - 1)) {
-            ring_issue(sm, issued, g0 + b_issued * kFwdBatch, g1 + b_issued * kFwdBatch, g2 + b_issued * kFwdBatch,
-                       min(unsigned(kFwdBatch), n - b_issued * kFwdBatch), lane);
-            ++issued; ++b_issued;
-        }
+        // Pipeline per batch b: this lane's block-list entries are loaded two batches ahead (registers), the records
+        // they point at are gathered one batch ahead (while batch b - 1 is walked), and the batch is walked once its
+        // gather group has completed.
+        constexpr int kR = kFwdBatch / 32;
+        unsigned int ent0[kR], ent1[kR], ent2[kR];   // entries of batch b, b + 1, b + 2
+        load_entries(ent0, lst, min(unsigned(kFwdBatch), n), lane);
+        load_entries(ent1, lst + kFwdBatch, nb > 1 ? min(unsigned(kFwdBatch), n - kFwdBatch) : 0u, lane);
+        if (nb) gather_batch<false>(sm, 0, ent0, min(unsigned(kFwdBatch), n), g0, g1, g2, nullptr, lane);
         for (unsigned int b = 0; b < nb; ++b) {
-            if (b_issued < nb) {                 // refill the slot consumed in the previous iteration
-                ring_issue(sm, issued, g0 + b_issued * kFwdBatch, g1 + b_issued * kFwdBatch, g2 + b_issued * kFwdBatch,
-                           min(unsigned(kFwdBatch), n - b_issued * kFwdBatch), lane);
-                ++issued; ++b_issued;
+            load_entries(ent2, lst + (b + 2) * kFwdBatch, b + 2 < nb ? min(unsigned(kFwdBatch), n - (b + 2) * kFwdBatch) : 0u, lane);
+            if (b + 1 < nb) {
+                gather_batch<false>(sm, (b + 1) % kFwdStages, ent1, min(unsigned(kFwdBatch), n - (b + 1) * kFwdBatch),
+                                    g0, g1, g2, nullptr, lane);
+                cp_async_wait<1>();              // everything but the group just committed: batch b has landed
+            } else {
+                cp_async_wait<0>();
             }
-            const int s = consumed % kFwdStages;
-            { PHASE_T0(); mbar_wait(&sm.full[s], (consumed / kFwdStages) & 1); PHASE_ADD(0); }
-            ++consumed;
+            __syncwarp();
+            const int s = b % kFwdStages;
             const unsigned int m = min(unsigned(kFwdBatch), n - b * kFwdBatch);
             const unsigned int cbase = b * kFwdBatch;
             const float4* r0 = sm.r0[s];
@@ -442,7 +484,7 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
             const float4* r2 = sm.r2[s];
             uint4 cnt;
             unsigned int qbits[kFwdBatch / 32];
-            { PHASE_T0(); cnt = cull_batch<false, kFwdBatch>(r0, m, sm.list, lane, qbits); PHASE_ADD(1); }
+            cnt = cull_batch<false, kFwdBatch>(ent0, m, sm.list, lane, qbits);
             // quarters whose 8 pixels are all finished need no further evaluation
             const unsigned int dmask = __ballot_sync(kFull, done);
             const unsigned int my_n = ((dmask & qmask) == qmask) ? 0u : (qsel == 0 ? cnt.x : qsel == 1 ? cnt.y : qsel == 2 ? cnt.z : cnt.w);
@@ -452,10 +494,6 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
             // recurrence.  List entries past a quarter's count point at the sentinel record (alpha = 0): no bounds
             // checks in the loop.  Quarters that are finished still walk (ok = false for all their lanes).
             unsigned int lastj = 0xffffffffu;
-#ifdef SGR_PHASE_TIMING
-            const long long pt_trips = clock64();
-            ntrips += total;
-#endif
             // A group of G trips: G independent alpha chains (loads first), then the compositing recurrence with the
             // colour records fetched as they are needed.  Groups of 8 while at least 5 trips remain (a single warp's
             // issue rate is bounded by the dependent-issue latency, so the long lists that run alone at the end of the
@@ -512,13 +550,9 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
 #endif
                 for (; t0 < total; t0 += 4) trip_group(t0, std::integral_constant<int, 4>{});
             }
-            // n_contrib counts positions in the TILE's list (upstream's contributor index): bits 4.. of word 2
-            if (lastj != 0xffffffffu) last = (__float_as_uint(r0[lastj].z) >> 4) + 1u;
+            // n_contrib counts positions in the TILE's list (upstream's contributor index): word 2 of rec0
+            if (lastj != 0xffffffffu) last = __float_as_uint(r0[lastj].z) + 1u;
             __syncwarp();
-#ifdef SGR_PHASE_TIMING
-            ph[2] += clock64() - pt_trips;
-            const long long pt_ref = clock64();
-#endif
             // Mask refinement for the backward pass: clear the (block, quarter) bits of the records that no pixel of
             // the quarter blended (alpha test, finished pixels) — the backward walk culls on the same word.
             if (refine) {
@@ -532,7 +566,7 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
                         const unsigned int exact = ((hw[rr] & 0x01010101u) * 0x10204080u) >> 28;
                         const unsigned int clear = qbits[rr] & ~exact;      // qbits = 0 beyond the batch
                         // the block owns its records: a plain store of the refined word
-                        if (clear) a.rec0_words[4 * (off + cbase + e) + 2] = __float_as_uint(r0[e].z) & ~clear;
+                        if (clear) a.bidx[off + cbase + e] = ent0[rr] & ~clear;
                         if (hw[rr]) sm.hit[e] = 0u;
                         const unsigned int hb = __ballot_sync(kFull, exact != 0u);
                         if (hb) { seg_hits += __popc(hb); eff = cbase + 32u * rr + (32u - __clz(hb)); }
@@ -557,24 +591,10 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
                 a.ck0[ci] = make_float4(T, C0, C1, C2);
                 a.ck1[ci] = D;
             }
-#ifdef SGR_PHASE_TIMING
-            ph[3] += clock64() - pt_ref;
-#endif
             if (__all_sync(kFull, done)) break;
+#pragma unroll
+            for (int rr = 0; rr < kR; ++rr) { ent0[rr] = ent1[rr]; ent1[rr] = ent2[rr]; }
         }
-#ifdef SGR_PHASE_TIMING
-        if (lane == 0) {
-            const long long tot = clock64() - (long long)0;
-            (void)tot;
-            for (int k = 0; k < 4; ++k) atomicAdd(&g_phase[k], (unsigned long long)ph[k]);
-            atomicAdd(&g_phase[4], ntrips);
-            atomicAdd(&g_phase[5], (unsigned long long)nb);
-            if (item / kBlocksPerTile == 0 && blk == 7) {
-                for (int k = 0; k < 4; ++k) g_phase[8 + k] = (unsigned long long)ph[k];
-                g_phase[12] = ntrips; g_phase[13] = nb; g_phase[14] = n;
-            }
-        }
-#endif
         if (n > unsigned(kSegB)) {                    // final state, read by the backward's non-final segments
             const size_t ci = (off / (kSegB / 2) + (n + kSegB - 1) / kSegB - 1) * 32 + lane;
             a.ck0[ci] = make_float4(T, C0, C1, C2);
@@ -590,11 +610,7 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
             }
             if (lane == 0) a.blk_eff[bi] = eff;
         }
-        // drain: copies already in flight must land before their slots are reused by the next item
-        while (consumed < issued) {
-            mbar_wait(&sm.full[consumed % kFwdStages], (consumed / kFwdStages) & 1);
-            ++consumed;
-        }
+        cp_async_wait<0>();                      // early exit: a gather in flight must land before its stage is reused
         __syncwarp();
         if (a.loss_target) {
             float part = 0.0f;
@@ -647,8 +663,10 @@ struct BwdArgs {
     const unsigned int* blk_off;
     const unsigned int* blk_cnt;
     const unsigned int* blk_eff;
-    const unsigned int* bids;
-    const float4 *rec0, *rec1, *rec2;     // block records (masks refined by the forward)
+    const unsigned int* tile_off;         // [R*T] start of the tile's depth-ordered records
+    const unsigned int* sorted_ids;       // Gaussian id of every tile-level record
+    const unsigned int* bidx;             // block-list entries (quarter masks refined by the forward)
+    const float4 *rec0, *rec1, *rec2;     // tile-level records
     const float* bg;
     const unsigned int* n_contrib;
     const unsigned char* clamp_mask;      // NULL: the forward did not clamp
@@ -689,7 +707,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
     const float gscale = a.dL_scale ? *a.dL_scale : 1.0f;
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < kBwdStages; ++s) mbar_init(&sm.full[s], 1);
+        for (int s = 0; s < kIxStages; ++s) mbar_init(&sm.ixbar[s], 1);
         fence_barrier_init();
     }
     __syncwarp();
@@ -700,11 +718,10 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
         sm.r2[lane][kBwdBatch] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     __syncwarp();
-    float (*stA)[32] = sm.stash[0];             // phase A: alpha; phase B overwrites it with dL/dalpha
+    float (*stA)[32] = sm.stash[0];             // dL/dalpha * G (every geometric term carries this product)
     float (*stW)[32] = sm.stash[1];             // blend weight alpha * T (0 = the pixel did not blend this Gaussian)
-    float (*stG)[32] = sm.stash[2];             // G = exp(power)
     const unsigned char* mylist = sm.list[qsel];
-    unsigned int issued = 0, consumed = 0;
+    unsigned int ix_issued = 0, ix_waited = 0;   // index ring counters over the kernel's lifetime (warp-uniform)
     // Stash rows are XOR-swizzled by trip, column = lane ^ swz(t): conflict-free both for lane = pixel (phases A, B)
     // and for lane = (trip, quarter) pairs reading one pixel of their quarter (phase C).
 
@@ -769,14 +786,17 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
         const unsigned int nb = (hi - lo + kBwdBatch - 1) / kBwdBatch;
         const float pxf = float(px), pyf = float(py);
         const float wx0 = float(bx0), wy0 = float(by0);
-        const float4 *g0 = a.rec0 + off + lo, *g1 = a.rec1 + off + lo, *g2 = a.rec2 + off + lo;
+        const size_t toff = a.tile_off[tg];
+        const float4 *g0 = a.rec0 + toff, *g1 = a.rec1 + toff, *g2 = a.rec2 + toff;
+        const unsigned int* lst = a.bidx + off + lo;
+        const unsigned int* tids = a.sorted_ids + toff;
         float T = T_final;
         float U = 0.0f;
         // A pixel has contributors behind this segment iff its last contributor sits at or behind the first record
         // after the segment (records are in tile-list order; word 2 >> 4 = position in the tile list).
         bool resume = false;
         if (lo + unsigned(kSegB) < n) {
-            const unsigned int next_pos = __float_as_uint(__ldg(&a.rec0[off + lo + kSegB].z)) >> 4;
+            const unsigned int next_pos = __ldg(a.bidx + off + lo + kSegB) >> 4;
             resume = last > next_pos;
         }
         if (resume) {                            // resume from the checkpoints
@@ -794,47 +814,39 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
         const float bg_dot = (bg0 * dp0 + bg1 * dp1) + bg2 * dp2;
         const float K = T_final * (bg_dot - dalp);
         float* acc = a.accum + size_t(rl) * a.g.N;
-        const unsigned int* ids = a.bids + off;
 
-        // walk step k handles list batch (nb - 1 - k)
-        unsigned int b_issued = 0;
-        if constexpr (kBwdStages > 1) {              // prefetch depth of the ring (none with a single stage)
-            while (b_issued < nb && b_issued < unsigned(kBwdStages - 1)) {
-                const unsigned int lb = nb - 1 - b_issued;
-                ring_issue(sm, issued, g0 + lb * kBwdBatch, g1 + lb * kBwdBatch, g2 + lb * kBwdBatch,
-                           min(unsigned(kBwdBatch), hi - lo - lb * kBwdBatch), lane);
-                ++issued; ++b_issued;
-            }
+        // walk step k handles list batch (nb - 1 - k): its index entries arrive by TMA one step ahead; its records
+        // (and Gaussian ids) are gathered at the start of the step — only those the forward found to blend
+        const unsigned int ixk0 = ix_issued;
+        if (nb) {
+            const unsigned int lb = nb - 1;
+            ix_issue(sm, ix_issued, lst + lb * kBwdBatch, min(unsigned(kBwdBatch), hi - lo - lb * kBwdBatch), lane);
+            ++ix_issued;
         }
         for (unsigned int b = 0; b < nb; ++b) {
-            if (b_issued < nb) {
-                const unsigned int lb = nb - 1 - b_issued;
-                ring_issue(sm, issued, g0 + lb * kBwdBatch, g1 + lb * kBwdBatch, g2 + lb * kBwdBatch,
-                           min(unsigned(kBwdBatch), hi - lo - lb * kBwdBatch), lane);
-                ++issued; ++b_issued;
+            if (b + 1 < nb) {
+                const unsigned int lb = nb - 2 - b;
+                ix_issue(sm, ix_issued, lst + lb * kBwdBatch, unsigned(kBwdBatch), lane);
+                ++ix_issued;
             }
-            const int s = consumed % kBwdStages;
-#ifdef SGR_PHASE_TIMING
-            long long bt = clock64();
-#define BPH(k) do { const long long n__ = clock64(); if (lane == 0) atomicAdd(&g_phase[k], (unsigned long long)(n__ - bt)); bt = n__; } while (0)
-#else
-#define BPH(k)
-#endif
-            mbar_wait(&sm.full[s], (consumed / kBwdStages) & 1);
-            ++consumed;
-            BPH(0);
             const unsigned int cbase = lo + (nb - 1 - b) * kBwdBatch;     // list index of the batch's first record
             const unsigned int m = min(unsigned(kBwdBatch), hi - cbase);
-            const float4* r0 = sm.r0[s];
-            const float4* r1 = sm.r1[s];
-            const float4* r2 = sm.r2[s];
+            ix_wait(sm, ixk0 + b); ++ix_waited;
+            unsigned int ent[kBwdBatch / 32];
+#pragma unroll
+            for (int rr = 0; rr < kBwdBatch / 32; ++rr) {
+                const unsigned int e = 32u * rr + lane;
+                ent[rr] = e < m ? sm.ix[(ixk0 + b) % kIxStages][e] : 0u;
+            }
+            gather_batch<true>(sm, 0, ent, m, g0, g1, g2, tids, lane);
+            cp_async_wait<0>();
+            __syncwarp();
+            const float4* r0 = sm.r0[0];
+            const float4* r1 = sm.r1[0];
+            const float4* r2 = sm.r2[0];
             unsigned int qbits[kBwdBatch / 32];
-            const uint4 cnt = cull_batch<true, kBwdBatch>(r0, m, sm.list, lane, qbits);
+            const uint4 cnt = cull_batch<true, kBwdBatch>(ent, m, sm.list, lane, qbits);
             const int total = int(max(max(cnt.x, cnt.y), max(cnt.z, cnt.w)));
-            BPH(1);
-#ifdef SGR_PHASE_TIMING
-            if (lane == 0) { atomicAdd(&g_phase[4], (unsigned long long)total); atomicAdd(&g_phase[5], 1ull); }
-#endif
             // trip t of the batch handles the quarter's survivor number (my_n - 1 - t): back to front
             for (int base = 0; base < total; base += kBwdSlots) {
                 const int trips = min(kBwdSlots, total - base);
@@ -849,7 +861,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
                     for (int u = 0; u < 4; ++u) {
                         const unsigned int j = (packed >> (8 * u)) & 0xffu;
                         q0[u] = r0[j];
-                        has[u] = (__float_as_uint(q0[u].z) >> 4) < last;
+                        has[u] = __float_as_uint(q0[u].z) < last;
                         q1[u] = r1[j];
                         q2[u] = r2[j];
                     }
@@ -887,13 +899,11 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
                     for (int u = 0; u < 4; ++u) {
                         const int t = t0 + u;
                         const int col = lane ^ ((t & 3) | ((t & 4) << 1));
-                        stA[t][col] = dl[u];
+                        stA[t][col] = dl[u] * gg[u];
                         stW[t][col] = wg[u];
-                        stG[t][col] = gg[u];
                     }
                 }
                 __syncwarp();
-                BPH(2);
                 // ---- phase C: the roles flip to lane = (trip, quarter) pair, i.e. one Gaussian of one quarter; the
                 // lane sums the gradient terms of the quarter's 8 pixels in registers (no shuffles) and issues the
                 // atomics.  The pass's pairs are enumerated quarter by quarter and taken 32 at a time.
@@ -919,26 +929,24 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
                             const int pl = cpl0 + (p & 3) + ((p >> 2) << 3);       // pixel lane inside the quarter
                             const int col = pl ^ cswz;
                             const float w = cvalid ? stW[ct][col] : 0.0f;
-                            const float dal = cvalid ? stA[ct][col] : 0.0f;
-                            const float G = stG[ct][col];
+                            const float qv = cvalid ? stA[ct][col] : 0.0f;          // dL/dalpha * G
                             const float dx = q0.x - (bxq + float(p & 3)), dy = q0.y - (byq + float(p >> 2));
-                            const float dL_dG = q1.w * dal;
-                            const float gdx = G * dx, gdy = G * dy;
-                            // -gdx*A - gdy*B = 2*gdx*hA + gdy*nB   (rec1 = (-A/2, -B, -C/2, o))
-                            s0 = fmaf(dL_dG, fmaf(hA2, gdx, q1.y * gdy), s0);
-                            s1 = fmaf(dL_dG, fmaf(hC2, gdy, q1.y * gdx), s1);
-                            s2 = fmaf(gdx * dx, dL_dG, s2);
-                            s3 = fmaf(gdx * dy, dL_dG, s3);
-                            s4 = fmaf(gdy * dy, dL_dG, s4);
-                            s5 = fmaf(G, dal, s5);
+                            const float Q = q1.w * qv;                               // dL/dG * G
+                            const float qx = Q * dx, qy = Q * dy;
+                            // -dx*A - dy*B = 2*dx*hA + dy*nB   (rec1 = (-A/2, -B, -C/2, o))
+                            s0 = fmaf(hA2, qx, fmaf(q1.y, qy, s0));
+                            s1 = fmaf(hC2, qy, fmaf(q1.y, qx, s1));
+                            s2 = fmaf(qx, dx, s2);
+                            s3 = fmaf(qx, dy, s3);
+                            s4 = fmaf(qy, dy, s4);
+                            s5 += qv;
                             s6 = fmaf(w, sm.dpix[0][pl], s6);
                             s7 = fmaf(w, sm.dpix[1][pl], s7);
                             s8 = fmaf(w, sm.dpix[2][pl], s8);
                             if (kDepthAlphaGrads) s9 = fmaf(w, sm.dpix[3][pl], s9);
                         }
                         if (cvalid) {
-                            const unsigned int id = __ldg(ids + cbase + j);
-                            float* g = acc + id;
+                            float* g = acc + sm.hit[j];              // the record's Gaussian id, gathered with it
                             if (s0 != 0.0f) atomicAdd(g + 0 * a.plane, s0 * ddelx_dx);
                             if (s1 != 0.0f) atomicAdd(g + 1 * a.plane, s1 * ddely_dy);
                             if (s2 != 0.0f) atomicAdd(g + 2 * a.plane, -0.5f * s2);
@@ -953,7 +961,6 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
                     }
                 }
                 __syncwarp();
-                BPH(3);
             }
         }
         __syncwarp();
@@ -1003,8 +1010,8 @@ cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out
                                  float* out_feed) {
     FwdArgs a;
     a.g = c.g; a.render_base = c.render_base; a.blk_off = c.blk_off; a.blk_cnt = c.blk_cnt; a.blk_eff = c.blk_eff;
-    a.rec0 = c.brec0; a.rec1 = c.brec1; a.rec2 = c.brec2; a.bg = c.p->bg; a.n_contrib = c.n_contrib;
-    a.rec0_words = reinterpret_cast<unsigned int*>(c.brec0);
+    a.tile_off = c.tile_off; a.rec0 = c.rec0; a.rec1 = c.rec1; a.rec2 = c.rec2; a.bidx = c.bidx;
+    a.bg = c.p->bg; a.n_contrib = c.n_contrib;
     a.refine_masks = (c.p->flags & SGR_FLAG_FORWARD_ONLY) ? 0 : 1;
     a.tile_time = (c.p->flags & SGR_FLAG_TILE_TIMING) ? c.tile_time : nullptr;
     a.out_color = out_color; a.out_depth = out_depth; a.out_alpha = out_alpha; a.out_feed = out_feed;
@@ -1057,7 +1064,8 @@ cudaError_t launch_bwd_variant(const BwdArgs& a, long long want, cudaStream_t st
 cudaError_t launch_blend_backward(const ChunkCtx& c, const SgrBackwardArgs& b) {
     BwdArgs a;
     a.g = c.g; a.render_base = c.render_base; a.blk_off = c.blk_off; a.blk_cnt = c.blk_cnt; a.blk_eff = c.blk_eff;
-    a.bids = c.bids; a.rec0 = c.brec0; a.rec1 = c.brec1; a.rec2 = c.brec2; a.bg = c.p->bg;
+    a.tile_off = c.tile_off; a.sorted_ids = c.sorted_ids; a.bidx = c.bidx;
+    a.rec0 = c.rec0; a.rec1 = c.rec1; a.rec2 = c.rec2; a.bg = c.p->bg;
     a.n_contrib = c.n_contrib; a.out_alpha = b.out_alpha; a.dL_dcolor = b.dL_dcolor; a.dL_ddepth = b.dL_ddepth;
     a.dL_dalpha = b.dL_dalpha; a.loss_dL_dcolor = b.loss_dL_dcolor; a.dL_dfeed = b.dL_dlpips_feed;
     a.clamp_mask = ((c.p->flags & SGR_FLAG_CLAMP_COLOR) || b.fused_clamp) ? c.clamp_mask : nullptr;
@@ -1074,11 +1082,3 @@ cudaError_t launch_blend_backward(const ChunkCtx& c, const SgrBackwardArgs& b) {
 
 }  // namespace sgr
 
-#ifdef SGR_PHASE_TIMING
-extern "C" int sgr_debug_phase_counters(unsigned long long* out16, int reset) {
-    cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out16, sgr::g_phase, sizeof(unsigned long long) * 16);
-    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(sgr::g_phase, z, sizeof(z)); }
-    return 0;
-}
-#endif

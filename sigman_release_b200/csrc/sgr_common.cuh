@@ -13,8 +13,9 @@ constexpr int kTilePixels = kTile * kTile;
 constexpr int kDefaultRendersPerChunk = 16;
 constexpr int kBlocksPerTile = 8;            // a 16x16 tile = eight 8x4 pixel blocks (blk = (y block) * 2 + (x block))
 // Block lists: the per-tile sort emits, for every 8x4 pixel block of a tile, the depth-ordered sub-list of the tile's
-// instances whose conservative extent touches the block ("block records": the 48-byte record + the Gaussian id).  The
-// blend kernels stream block lists, so a warp never fetches or culls a record that cannot touch its pixels.
+// instances whose conservative extent touches the block, as 4-byte entries (position in the tile list << 4 | the
+// block's 4-bit quarter mask).  The blend kernels stream the entries (1-D TMA) and gather exactly those records from
+// the tile-level stream (cp.async), so a warp never fetches or culls a record that cannot touch its pixels.
 // Backward work granularity: a block list is replayed in independent segments of kSegB block records (multiple of the
 // blend kernels' batch).  The forward blend checkpoints every pixel's running state at the segment boundaries of
 // lists longer than one segment; slot (block list, s) = blk_off / (kSegB / 2) + s, s < #segments, the last slot
@@ -50,7 +51,7 @@ struct ChunkPlan {
 // Layout of `state` (kept forward -> backward) for a problem shape.
 struct StateLayout {
     uint64_t header, tile_off, tile_cnt, tile_time, n_contrib, clamp_mask, sorted_ids, rec0, rec1, rec2, blk_off, blk_cnt,
-        blk_eff, brec0, brec1, brec2, bids, ck0, ck1, plan, bwd_items, bwd_items_stride, total;
+        blk_eff, bidx, ck0, ck1, plan, bwd_items, bwd_items_stride, total;
 };
 // Layout of `scratch` (valid only inside one call).
 struct ScratchLayout {
@@ -68,7 +69,7 @@ inline uint64_t ckpt_slots(uint64_t capB) { return capB / (kSegB / 2) + 2; }
 inline StateLayout make_state_layout(int B, int V, int N, int H, int W, uint64_t cap, uint64_t capB, bool simple) {
     (void)N;
     const uint64_t R = uint64_t(B) * V, T = uint64_t(tiles_x(W)) * tiles_y(H), P = uint64_t(H) * W;
-    const uint64_t rec_cap = simple ? cap : 0, blk_cap = simple ? 0 : capB;
+    const uint64_t rec_cap = cap, blk_cap = simple ? 0 : capB;
     StateLayout L;
     uint64_t o = 0;
     L.header = o;      o = align_up(o + sizeof(StateHeader));
@@ -84,10 +85,7 @@ inline StateLayout make_state_layout(int B, int V, int N, int H, int W, uint64_t
     L.blk_off = o;     o = align_up(o + R * T * kBlocksPerTile * 4);
     L.blk_cnt = o;     o = align_up(o + R * T * kBlocksPerTile * 4);
     L.blk_eff = o;     o = align_up(o + R * T * kBlocksPerTile * 4);
-    L.brec0 = o;       o = align_up(o + blk_cap * 16);
-    L.brec1 = o;       o = align_up(o + blk_cap * 16);
-    L.brec2 = o;       o = align_up(o + blk_cap * 16);
-    L.bids = o;        o = align_up(o + blk_cap * 4);
+    L.bidx = o;        o = align_up(o + blk_cap * 4);
     L.ck0 = o;         o = align_up(o + ckpt_slots(blk_cap) * kCkptPerSlot * 16);   // (T, C0, C1, C2) per pixel and slot
     L.ck1 = o;         o = align_up(o + ckpt_slots(blk_cap) * kCkptPerSlot * 4);    // D
     L.plan = o;        o = align_up(o + R * sizeof(ChunkPlan));                     // one per chunk (at most R chunks)
@@ -244,11 +242,10 @@ struct ChunkCtx {
     uint2* tile_time;         // [R*T]
     unsigned int* n_contrib;  // [R*P]
     unsigned int* sorted_ids; // [cap]
-    float4 *rec0, *rec1, *rec2;   // [cap] tile-level records (SGR_FLAG_SIMPLE_BLEND only)
+    float4 *rec0, *rec1, *rec2;   // [cap] tile-level records in depth order
     unsigned char* clamp_mask; // [R*P]
     unsigned int *blk_off, *blk_cnt, *blk_eff;   // [R*T*8] block lists: start, records, records the backward replays
-    float4 *brec0, *brec1, *brec2;               // [capB] block records
-    unsigned int* bids;                          // [capB] Gaussian id of every block record
+    unsigned int* bidx;                          // [capB] block-list entries (tile-list position << 4 | quarter mask)
     unsigned long long blk_capacity;
     float4* ck0;              // [ckpt_slots][32] forward checkpoints (T, C0, C1, C2)
     float* ck1;               // [ckpt_slots][32] forward checkpoints D

@@ -59,15 +59,16 @@ def test_buffer_size_queries(lib):
     b = lib.sgr_state_bytes(1, 8, 100_000, 512, 512, 2_000_000, 6_000_000, 0)
     c = lib.sgr_state_bytes(1, 8, 100_000, 512, 512, 4_000_000, 6_000_000, 0)
     assert 0 < a < b < c and a % 256 == 0
-    # per block record: three 16-byte record streams + 4-byte id; per 128 block records one checkpoint slot of 32 pixels
-    # x 20 B; per 256 block records one 8-byte backward work item in each of the 4 classes (regions 256-byte aligned)
-    growth = 3_000_000 * 52 + (6_000_000 // 128 - 3_000_000 // 128) * 32 * 20 + (6_000_000 // 256 - 3_000_000 // 256) * 8 * 4
+    # per block-list entry: 4 bytes; per 128 entries one checkpoint slot of 32 pixels x 20 B; per 256 entries one 8-byte
+    # backward work item in each of the 4 classes (regions 256-byte aligned)
+    growth = 3_000_000 * 4 + (6_000_000 // 128 - 3_000_000 // 128) * 32 * 20 + (6_000_000 // 256 - 3_000_000 // 256) * 8 * 4
     assert abs((b - a) - growth) <= 8 * 256
-    assert abs((c - b) - 2_000_000 * 4) <= 256                  # per instance: the 4-byte id of the tile-level point list
-    # SGR_FLAG_SIMPLE_BLEND keeps tile-level records (48 B per instance) and no block lists
+    # per instance: the 4-byte id of the tile-level point list + the 48-byte depth-ordered record
+    assert abs((c - b) - 2_000_000 * 52) <= 4 * 256
+    # SGR_FLAG_SIMPLE_BLEND keeps no block lists
     d = lib.sgr_state_bytes(1, 8, 100_000, 512, 512, 2_000_000, 3_000_000, _native.FLAG_SIMPLE_BLEND)
-    e = lib.sgr_state_bytes(1, 8, 100_000, 512, 512, 4_000_000, 3_000_000, _native.FLAG_SIMPLE_BLEND)
-    assert abs((e - d) - 2_000_000 * 52) <= 4 * 256
+    e = lib.sgr_state_bytes(1, 8, 100_000, 512, 512, 2_000_000, 6_000_000, _native.FLAG_SIMPLE_BLEND)
+    assert d == e < a
     assert lib.sgr_state_bytes(0, 8, 10, 64, 64, 10, 10, 0) == 0
     s16 = lib.sgr_scratch_bytes(8, 10, 100_000, 512, 512, 20_000_000, 16)
     s80 = lib.sgr_scratch_bytes(8, 10, 100_000, 512, 512, 20_000_000, 80)
