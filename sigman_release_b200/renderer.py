@@ -119,6 +119,8 @@ class GaussianRenderer:
         self.tan_half_fov = np.tan(0.5 * self.opt.FoVy)
         # True reproduces the bf16 rounding the reference's get_covariance bmm's see under accelerate's autocast
         self.bf16_autocast = False
+        # True: exp(power) as the oracle's fixed IEEE sequence (bit-exact parity mode, include/sgr.h SGR_FLAG_EXACT_EXP)
+        self.exact_exp = False
 
     def prepare(self, gaussians):
         """Per-subject preparation of gs.py:64-73, batched over B: returns (means3D, cov3D [B,N,6], rgb, opacity)."""
@@ -145,5 +147,5 @@ class GaussianRenderer:
         # rasteriser state and is applied inside the backward kernel (no clamp kernel, no saved image).
         image, _radii, _depth, alpha = rasterize_batch(
             means3D, cov3D, rgbs, opacity, cam_view.float(), cam_view_proj.float(), bg, H, W,
-            self.tan_half_fov, self.tan_half_fov, clamp_color=True)
+            self.tan_half_fov, self.tan_half_fov, clamp_color=True, exact_exp=self.exact_exp)
         return {"image": image, "alpha": alpha}
