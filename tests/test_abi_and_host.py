@@ -2,6 +2,7 @@
 validation works without a GPU, and the host-side mirror of the reference API behaves like upstream's."""
 import ctypes
 import os
+import sys
 import re
 
 import numpy as np
