@@ -105,6 +105,8 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ reference arm
 def oracle_step_fn(sc, n_views):
+    """One CPU step = oracle forward + backward of `n_views` views.  The image gradient (L1 on the clamped RGB) is
+    computed once outside the timed step: the step times the rasteriser path only, like the GPU arm's stage times."""
     import oracle
     from sigman_release_b200 import cameras
 
@@ -113,16 +115,27 @@ def oracle_step_fn(sc, n_views):
     rng = np.random.default_rng(1)
     target = rng.uniform(0, 1, (3, H, W)).astype(np.float32)
     rs = [oracle.Rasterizer(np.float32) for _ in range(n_views)]
+    grads = []
+    for v in range(n_views):
+        c = rs[v].forward(sc["means3D"], sc["cov3D"], sc["colors"], sc["opacities"], vm[v].reshape(-1), pm[v].reshape(-1),
+                          tan, tan, (1, 1, 1), H, W).color
+        grads.append((np.sign(np.clip(c, 0, 1) - target) * ((c >= 0) & (c <= 1)) / (target.size * n_views)).astype(np.float32))
 
     def step():
         for v in range(n_views):
-            o = rs[v].forward(sc["means3D"], sc["cov3D"], sc["colors"], sc["opacities"], vm[v].reshape(-1),
-                              pm[v].reshape(-1), tan, tan, (1, 1, 1), H, W)
-            c = o.color
-            g = (np.sign(np.clip(c, 0, 1) - target) * ((c >= 0) & (c <= 1)) / (target.size * n_views)).astype(np.float32)
-            rs[v].backward(g)
+            rs[v].forward(sc["means3D"], sc["cov3D"], sc["colors"], sc["opacities"], vm[v].reshape(-1),
+                          pm[v].reshape(-1), tan, tan, (1, 1, 1), H, W)
+            rs[v].backward(grads[v])
 
     return step
+
+
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1: the CPU arm overrides it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def run_reference(args):
@@ -133,6 +146,7 @@ def run_reference(args):
     from sigman_release_b200 import scenes
 
     oracle.build()
+    oracle.set_num_threads(host_threads())
     sc = scenes.body_gaussians(N_GAUSS, seed=0)
     sample_views = 1
     step = oracle_step_fn(sc, sample_views)
@@ -155,8 +169,8 @@ def run_reference(args):
         "views_per_sec": sample_views / dt,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU oracle (oracle/sgr_oracle.cpp): restatement of the published algorithm; the reference's own "
-                "rasteriser is an un-vendored third-party CUDA package (parity unpinned)",
+        "note": "CPU oracle (oracle/sgr_oracle.cpp, -O3, OpenMP over all host threads): restatement of the published "
+                "algorithm; the reference's own rasteriser is an un-vendored third-party CUDA package (parity unpinned)",
     }))
 
 
@@ -358,6 +372,58 @@ def run_ours(args):
     build_e2e_graphs()
     ms_e2e = timed(e2e_step, args.steps, 2, finish=e2e_finish)
     clocks = sampler.stop()
+    host_enqueue = {"eager_step": host_ms[0], "value_leg": host_ms[-2], "e2e_leg": host_ms[-1]}
+
+    # ---- the same workload driven like the reference drives it (gs.py:62-109): a Python loop of single-view calls of
+    # the drop-in GaussianRasterizer module, forward + backward.  "simple_blend" swaps in the upstream-shaped blend
+    # kernels (one CTA per tile, every thread walks the whole tile list): the closest stand-in for the reference's own
+    # CUDA path, whose source is not available.
+    from sigman_release_b200 import GaussianRasterizationSettings, GaussianRasterizer
+
+    def per_view_loop(simple):
+        for v in d.values():
+            v.grad = None
+        imgs = []
+        for v in range(V):
+            if simple:
+                c = rasterizer.rasterize_batch(d["means3D"], d["cov3D"], d["colors"], d["opacities"], vmt[:, v:v + 1],
+                                               pmt[:, v:v + 1], bg, H, W, tan, tan, simple_blend=True)[0][0, 0]
+            else:
+                st = GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=tan, tanfovy=tan, bg=bg,
+                                                   scale_modifier=0.5, viewmatrix=vmt[0, v], projmatrix=pmt[0, v], sh_degree=0,
+                                                   campos=bg, prefiltered=False, debug=False)
+                c = GaussianRasterizer(st)(means3D=d["means3D"][0], means2D=torch.zeros_like(d["means3D"][0]), shs=None,
+                                           colors_precomp=d["colors"][0], opacities=d["opacities"][0][:, None],
+                                           cov3D_precomp=d["cov3D"][0])[0]
+            imgs.append(c.clamp(0, 1))
+        (torch.stack(imgs) - target[0]).abs().mean().backward()
+
+    loop_steps = max(3, min(args.steps, 20))
+    ms_loop = timed(lambda: per_view_loop(False), loop_steps, 2)
+    ms_loop_simple = timed(lambda: per_view_loop(True), loop_steps, 2)
+
+    # ---- BASELINE config 4: 90-view orbit of one subject, RGB + depth + alpha, views sharded over the ranks, chunks
+    # all-gathered while the next chunk renders (sigman_release_b200.orbit.render_orbit_overlapped)
+    from sigman_release_b200 import orbit as orbit_mod
+
+    def orbit_leg():
+        osc = scenes.body_gaussians(N_GAUSS, seed=0)                 # the same subject on every rank
+        ot = [f32(osc[k])[None].to(dev) for k in ("means3D", "cov3D", "colors")] + [f32(osc["opacities"]).reshape(1, -1).to(dev)]
+        ovm, opm, _ = cameras.orbit_cameras(list(range(90)))
+        fn = orbit_mod.rasterizer_planes(ot[0], ot[1], ot[2], ot[3], bg, H, W, tan, f32(ovm).to(dev), f32(opm).to(dev))
+        res = {}
+        with torch.no_grad():
+            for name, wire in (("exact_fp32", orbit_mod.WIRE_EXACT), ("compact_u8_f16", orbit_mod.WIRE_COMPACT)):
+                ms = timed(lambda: orbit_mod.render_orbit_overlapped(fn, 90, H, W, dev, wire=wire, chunk=4), 5, 2)
+                per_px = sum(torch.empty((), dtype=dt).element_size() * ch for dt, ch in zip(wire, (3, 1, 1)))
+                per = (90 + world - 1) // world
+                gathered = world * per * per_px * H * W              # bytes every rank receives
+                res[name] = {"ms": ms, "views_per_sec": 90 / (ms * 1e-3), "gathered_bytes": gathered,
+                             "busbw_gbs": (gathered * (world - 1) / world) / (ms * 1e-3) / 1e9 if world > 1 else None}
+        rasterizer.check_status()
+        return res
+
+    orbit = orbit_leg()
 
     # roofline leg: per-stage device time with events around every stage launch (separate pass, same workload)
     L.sgr_profile_enable(1)
@@ -384,7 +450,7 @@ def run_ours(args):
     achieved = dom_bytes / (dom_launch_ms * 1e-3) / 1e9
     step_bytes = (ab["forward"] + ab["backward"]) * V
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")          # tools/summarise_profiles.py (ncu --set full)
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")          # tools/summarise_profiles.py (ncu --set full)
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         if dom in tj:
@@ -392,7 +458,7 @@ def run_ours(args):
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-        "note": "the blend kernels are instruction-issue bound (ncu: issue slots busy 66-77 %, DRAM throughput 5 %); "
+        "note": "the blend kernels are instruction-issue / latency bound (ncu, profiles/r2_*: DRAM throughput < 10 %); "
                 "the HBM fraction is reported as the contract asks, see DESIGN.md section 4",
         "algorithmic_bytes_per_launch": dom_bytes,
         "definition": f"SURVEY 8(d) {side} bytes per (subject, view) x {V} renders per launch / mean launch duration",
@@ -425,13 +491,26 @@ def run_ours(args):
                    "eager_ms_per_step": ms_eager,
                    "note": "gpu_launches = kernels of libsgr_b200.so launched in the eager timed pass of the same "
                            "`steps` steps (a graph replay launches the same kernels without passing the counter)"},
-        "host_enqueue_ms_per_step": {"eager_step": host_ms[0], "value_leg": host_ms[-2], "e2e_leg": host_ms[-1]},
+        "host_enqueue_ms_per_step": host_enqueue,
+        "value_eager": N_GAUSS * V * world / (ms_eager * 1e-3),
+        "dropin_per_view_ms": ms_loop / V,
+        "reference_shaped_gpu": {
+            "what": "Python loop of single-view drop-in module calls (gs.py:62-109 shape), forward + backward, same "
+                    "workload; simple_blend = upstream-shaped blend kernels (one CTA per tile) as the stand-in for "
+                    "the reference's own CUDA path (source unavailable)",
+            "per_view_loop_ms_per_step": ms_loop, "value": N_GAUSS * V * world / (ms_loop * 1e-3),
+            "per_view_loop_simple_blend_ms_per_step": ms_loop_simple,
+            "value_simple_blend": N_GAUSS * V * world / (ms_loop_simple * 1e-3)},
+        "orbit": dict(orbit, views=90, image=[H, W], planes="RGB + depth + alpha", n_gpus=world,
+                      note="BASELINE config 4: views sharded contiguously, chunked render overlapped with a per-chunk "
+                           "all-gather (exact: bitwise equal to one GPU; compact: uint8 RGB + fp16 depth / alpha)"),
         "status": rasterizer.last_status(),
     }
     if world == 1 and not args.no_cpu_baseline:
         import oracle
 
         oracle.build()
+        oracle.set_num_threads(host_threads())
         step = oracle_step_fn(sc, 1)
         step()
         reps, t0 = 0, time.perf_counter()

@@ -226,6 +226,20 @@ uint64_t sgr_knn_scratch_bytes_batched(int32_t num_subjects, int32_t num_points)
 int sgr_knn_mean_dist2_batched(const float* points, int32_t num_subjects, int32_t num_points, float* out_mean_dist2,
                                void* scratch, uint64_t scratch_bytes, void* stream);
 
+/* Wire formats of the multi-GPU image gather (BASELINE config 4; replaces the fp32
+ * `self.accelerator.gather(out['images_pred'])` of /root/reference/core/loss/eval.py:81-82).  A chunk of n rendered views
+ * travels as one byte buffer [RGB n*3*P | depth n*P | alpha n*P]: exact = float32 (the forward can write its outputs
+ * straight into it: 20 bytes per pixel), compact = uint8 RGB (trunc(clamp(c, 0, 1) * 255 + 0.5)) + fp16 depth / alpha
+ * (7 bytes per pixel).  `pixels` (H*W) must be a multiple of 4.
+ * sgr_wire_pack: float32 planes -> the compact layout.
+ * sgr_wire_unpack: the all-gathered buffers of `world` ranks (rank r at recv + r * rank_stride_bytes, either layout) ->
+ * float32 final_stack[world][views_per_rank][5][pixels] at views first_view .. first_view + num_views of every rank. */
+uint64_t sgr_wire_chunk_bytes(int32_t num_views, int64_t pixels, int32_t compact);
+int sgr_wire_pack(const float* color, const float* depth, const float* alpha, int32_t num_views, int64_t pixels,
+                  void* out_bytes, void* stream);
+int sgr_wire_unpack(const void* recv, int32_t world, int64_t rank_stride_bytes, int32_t num_views, int64_t pixels,
+                    int32_t compact, float* final_stack, int64_t views_per_rank, int64_t first_view, void* stream);
+
 /* Measurement hooks (bench.py): per-stage device time with CUDA events recorded on the launch stream around every
  * stage of sgr_forward / sgr_backward while enabled, and a counter of the kernels this library has launched.
  * Stage order: preprocess, plan, scatter, sort, blend_forward, blend_backward, preprocess_backward.

@@ -134,6 +134,10 @@ SYMBOLS = {
     "sgr_knn_mean_dist2": (ctypes.c_int, [_vp, _i32, _vp, _vp, _u64, _vp]),
     "sgr_knn_scratch_bytes_batched": (_u64, [_i32, _i32]),
     "sgr_knn_mean_dist2_batched": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _u64, _vp]),
+    "sgr_wire_chunk_bytes": (_u64, [_i32, ctypes.c_int64, _i32]),
+    "sgr_wire_pack": (ctypes.c_int, [_vp, _vp, _vp, _i32, ctypes.c_int64, _vp, _vp]),
+    "sgr_wire_unpack": (ctypes.c_int, [_vp, _i32, ctypes.c_int64, _i32, ctypes.c_int64, _i32, _vp, ctypes.c_int64,
+                                       ctypes.c_int64, _vp]),
     "sgr_profile_enable": (None, [ctypes.c_int]),
     "sgr_profile_collect": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint32)]),
     "sgr_launch_count": (_u64, []),

@@ -11,7 +11,7 @@ OBJ="$(mktemp -d)"
 trap 'rm -rf "$OBJ"' EXIT
 COMMON=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC ${SGR_NVCC_EXTRA:-})
 EXACT="sgr_api sgr_preprocess sgr_binning sgr_blend sgr_blend_simple sgr_knn"
-FAST="sgr_gaussian_bwd sgr_attrs"
+FAST="sgr_gaussian_bwd sgr_attrs sgr_wire"
 pids=()
 for f in $EXACT; do "$NVCC" "${COMMON[@]}" --fmad=false -c "$HERE/$f.cu" -o "$OBJ/$f.o" & pids+=($!); done
 for f in $FAST; do "$NVCC" "${COMMON[@]}" -c "$HERE/$f.cu" -o "$OBJ/$f.o" & pids+=($!); done

@@ -12,7 +12,7 @@ from typing import Callable, Sequence
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_views", "render_orbit_sharded", "to_wire", "from_wire"]
+__all__ = ["shard_views", "shard_range", "render_orbit_sharded", "render_orbit_overlapped", "to_wire", "from_wire"]
 
 
 def shard_views(num_views: int, rank: int, world: int) -> list[int]:
@@ -64,3 +64,137 @@ def render_orbit_sharded(render_fn: Callable[[Sequence[int]], torch.Tensor], num
     idx_r = torch.arange(num_views, device=local.device) % world
     idx_k = torch.arange(num_views, device=local.device) // world
     return from_wire(out[idx_r, idx_k], wire_dtype)
+
+
+def shard_range(num_views: int, rank: int, world: int) -> tuple[int, int, int]:
+    """Contiguous shards: rank r renders views [r * per, min((r + 1) * per, num_views)); returns (first, count, per).
+    With this split a gather of the per-rank stacks IS the view-ordered stack (no permutation)."""
+    if not 0 <= rank < world:
+        raise ValueError("rank outside [0, world)")
+    per = (num_views + world - 1) // world
+    first = min(rank * per, num_views)
+    return first, max(0, min(num_views - first, per)), per
+
+
+# wire formats of the overlapped gather: (RGB, depth, alpha) element types
+WIRE_EXACT = (torch.float32, torch.float32, torch.float32)       # bitwise equal to a single-GPU render
+WIRE_COMPACT = (torch.uint8, torch.float16, torch.float16)       # 7 instead of 20 bytes per pixel (evaluation renders)
+
+
+def render_orbit_overlapped(render_planes: Callable, num_views: int, height: int, width: int, device, group=None,
+                            wire=WIRE_EXACT, chunk: int = 0) -> torch.Tensor:
+    """Orbit render of BASELINE config 4 with the gather overlapped with the rendering (mirrors
+    ``self.accelerator.gather(out['images_pred'])``, /root/reference/core/loss/eval.py:81-82).
+
+    ``render_planes(view_ids, out) -> (color [n,3,H,W], depth [n,1,H,W], alpha [n,1,H,W])`` renders the given views;
+    ``out`` (a tuple of three contiguous float32 tensors of those shapes, or None) is where it should write — they
+    are slices of this rank's gather buffer, so with the exact wire format nothing is copied (no ``torch.cat``).
+    Views are sharded contiguously; every rank renders its shard in chunks of ``chunk`` views (0 = a third of the
+    shard, at least 4), and while chunk k + 1 renders on the current stream, chunk k is all-gathered (as bytes, one
+    collective per chunk) and unpacked into the view-ordered result on a side stream — packing and unpacking are one
+    kernel each of the CUDA library (``sgr_wire_pack`` / ``sgr_wire_unpack``).  Returns ``[num_views, 5, H, W]``
+    float32 (RGB, depth, alpha) on every rank; with ``wire=WIRE_EXACT`` it is bitwise equal to a single-process
+    render, ``WIRE_COMPACT`` sends uint8 RGB (colours in [0, 1]) and fp16 depth / alpha.  CPU tensors (the gloo tests
+    of the host logic) take the same route with torch ops instead of the two kernels."""
+    distributed = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if distributed else 1
+    rank = dist.get_rank(group) if distributed else 0
+    first, count, per = shard_range(num_views, rank, world)
+    device = torch.device(device)
+    P = height * width
+    planes = (3, 1, 1)
+    wire = tuple(wire)
+    if wire not in (WIRE_EXACT, WIRE_COMPACT):
+        raise ValueError("wire must be WIRE_EXACT or WIRE_COMPACT")
+    exact = wire == WIRE_EXACT
+    sizes = [torch.empty((), dtype=dt).element_size() for dt in wire]
+    on_cuda = device.type == "cuda"
+    if chunk <= 0:
+        chunk = max(4, (per + 2) // 3)
+    if on_cuda:
+        import ctypes
+
+        from . import _native
+        L = _native.lib()
+        if P % 4:
+            raise ValueError("height * width must be a multiple of 4")
+    final = torch.empty((world * per, 5, height, width), dtype=torch.float32, device=device)
+    final5 = final.view(world, per, 5, height, width)
+    side = torch.cuda.Stream(device=device) if on_cuda else None
+    keep = []                                    # buffers stay alive until the side stream has consumed them
+    for k0 in range(0, per, chunk):
+        c = min(chunk, per - k0)
+        # this rank's views of the chunk; shards are padded (with the last valid view) to equal length
+        ids = [min(first + k0 + i, max(first + count - 1, 0), num_views - 1) for i in range(c)]
+        nbytes = [c * ch * P * es for ch, es in zip(planes, sizes)]
+        send = torch.empty((sum(nbytes),), dtype=torch.uint8, device=device)
+        offs = [0, nbytes[0], nbytes[0] + nbytes[1]]
+        if exact:                                # the renderer writes straight into the send buffer
+            outs = tuple(send[o:o + nb].view(torch.float32).view(c, ch, height, width)
+                         for o, nb, ch in zip(offs, nbytes, planes))
+            got = render_planes(ids, outs)
+            for t, o in zip(got, outs):          # a renderer that ignored `out` (CPU tests): copy its result in
+                if t.data_ptr() != o.data_ptr():
+                    o.copy_(t)
+        else:
+            got = [t.contiguous() for t in render_planes(ids, None)]
+            if on_cuda:
+                with torch.cuda.device(device):
+                    st = torch.cuda.current_stream(device)
+                    _native.check(L.sgr_wire_pack(ctypes.c_void_p(got[0].data_ptr()), ctypes.c_void_p(got[1].data_ptr()),
+                                                  ctypes.c_void_p(got[2].data_ptr()), c, P, ctypes.c_void_p(send.data_ptr()),
+                                                  ctypes.c_void_p(st.cuda_stream)))
+            else:
+                for t, o, nb, dt in zip(got, offs, nbytes, wire):
+                    send[o:o + nb].view(dt).copy_(to_wire(t, dt).reshape(-1))
+        recv = torch.empty((world, send.numel()), dtype=torch.uint8, device=device) if distributed else send.view(1, -1)
+        if on_cuda:
+            ready = torch.cuda.Event()
+            ready.record()
+            side.wait_event(ready)
+        ctx = torch.cuda.stream(side) if on_cuda else _NullCtx()
+        with ctx:
+            if distributed:
+                dist.all_gather_into_tensor(recv.view(-1), send, group=group)
+            if on_cuda:
+                with torch.cuda.device(device):
+                    _native.check(L.sgr_wire_unpack(ctypes.c_void_p(recv.data_ptr()), world, send.numel(), c, P,
+                                                    0 if exact else 1, ctypes.c_void_p(final.data_ptr()), per, k0,
+                                                    ctypes.c_void_p(side.cuda_stream)))
+            else:
+                for pi, (o, nb, ch, dt) in enumerate(zip(offs, nbytes, planes, wire)):
+                    blk = recv[:, o:o + nb].view(dt).view(world, c, ch, height, width)
+                    c0 = (0, 3, 4)[pi]
+                    final5[:, k0:k0 + c, c0:c0 + ch] = from_wire(blk, dt)
+        keep.append((send, recv, got))
+    if on_cuda:
+        torch.cuda.current_stream(device).wait_stream(side)
+        for bufs in keep:                        # the caching allocator must not hand them out before the side stream is done
+            for t in bufs[:2]:
+                t.record_stream(side)
+    return final[:num_views]
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def rasterizer_planes(means3D, cov3D, colors, opacities, bg, height, width, tanfov, view_matrices, proj_matrices):
+    """``render_planes`` for ``render_orbit_overlapped`` over this package's rasteriser: one subject ([1,N,..] tensors),
+    cameras ``view_matrices`` / ``proj_matrices`` [num_views,4,4] (device tensors); RGB is clamped to [0, 1] like
+    gs.py:107.  The kernels write straight into ``out`` when it is given."""
+    from .rasterizer import rasterize_batch
+
+    def render(view_ids, out):
+        idx = torch.as_tensor(list(view_ids), device=means3D.device)
+        vm, pm = view_matrices[idx][None], proj_matrices[idx][None]
+        o = None if out is None else tuple(t.unsqueeze(0) for t in out)
+        c, _r, d, a = rasterize_batch(means3D, cov3D, colors, opacities, vm, pm, bg, height, width, tanfov, tanfov,
+                                      clamp_color=True, out=o)
+        return c[0], d[0], a[0]
+
+    return render

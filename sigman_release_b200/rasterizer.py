@@ -245,7 +245,7 @@ class _RasterizeBatch(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, cov3D, colors, opacities, means2D, viewmatrix, projmatrix, bg, H, W, tanfovx, tanfovy,
                 flags, renders_per_chunk, loss_target=None, loss_mask=None, loss_scale=None, force_sync=False,
-                want_feed=False):
+                want_feed=False, out=None):
         global _last_status
         L = _native.lib()
         B, N = int(means3D.shape[0]), int(means3D.shape[1])
@@ -254,9 +254,12 @@ class _RasterizeBatch(torch.autograd.Function):
         dev = means3D.device
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev)
-            color = torch.empty((B, V, 3, H, W), dtype=torch.float32, device=dev)
-            depth = torch.empty((B, V, 1, H, W), dtype=torch.float32, device=dev)
-            alpha = torch.empty((B, V, 1, H, W), dtype=torch.float32, device=dev)
+            if out is None:
+                color = torch.empty((B, V, 3, H, W), dtype=torch.float32, device=dev)
+                depth = torch.empty((B, V, 1, H, W), dtype=torch.float32, device=dev)
+                alpha = torch.empty((B, V, 1, H, W), dtype=torch.float32, device=dev)
+            else:                                # caller-owned output planes (e.g. slices of an all-gather buffer)
+                color, depth, alpha = out
             radii = torch.empty((B, V, N), dtype=torch.int32, device=dev)
             fused = loss_target is not None
             loss = torch.empty((), dtype=torch.float32, device=dev) if fused else None
@@ -331,7 +334,7 @@ class _RasterizeBatch(torch.autograd.Function):
     def backward(ctx, g_color, _g_radii, g_depth, g_alpha, g_loss, g_feed):
         if g_color is None and g_depth is None and g_alpha is None and g_feed is None and \
                 (g_loss is None or ctx.g_fused is None):
-            return (None,) * 19
+            return (None,) * 20
         L = _native.lib()
         means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg, alpha, radii, state = ctx.saved_tensors
         B, V, N, H, W, tanfovx, tanfovy, caps, flags, rpc, state_bytes = ctx.dims
@@ -375,7 +378,7 @@ class _RasterizeBatch(torch.autograd.Function):
         # the GPU now works on the queued backward while the host waits for the forward's 64-byte status copy: an
         # overflowed step raises here, out of loss.backward(), before anything can consume its gradients
         _verify(ctx.pending)
-        return (d_means3D, d_cov3D, d_colors, d_opac, d_means2D) + (None,) * 14
+        return (d_means3D, d_cov3D, d_colors, d_opac, d_means2D) + (None,) * 15
 
 
 def _checked(means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg):
@@ -407,7 +410,7 @@ _EXACT_EXP_ENV = os.environ.get("SGR_EXACT_EXP", "0") not in ("", "0")
 
 def rasterize_batch(means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg, image_height, image_width,
                     tanfovx, tanfovy, means2D=None, clamp_color=False, simple_blend=False, renders_per_chunk=0,
-                    sync_if_no_grad=False, exact_exp=False, lpips_feed=False):
+                    sync_if_no_grad=False, exact_exp=False, lpips_feed=False, out=None):
     """Render B subjects x V views in one launch set.
 
     means3D [B,N,3], cov3D [B,N,6] (xx,xy,xz,yy,yz,zz — gs.py:32-37), colors [B,N,3], opacities [B,N] or [B,N,1],
@@ -425,6 +428,8 @@ def rasterize_batch(means3D, cov3D, colors, opacities, viewmatrix, projmatrix, b
       ``oracle/``); the default uses the SFU like upstream's own ``exp`` (see include/sgr.h SGR_FLAG_EXACT_EXP).
     * ``sync_if_no_grad``: a call that no backward can follow checks its instance capacity synchronously (grow and
       retry inside the call) instead of deferring the check — see the workspace policy at the top of this module.
+    * ``out=(color, depth, alpha)``: caller-owned contiguous float32 CUDA tensors of the result shapes that the
+      kernels write directly (no copy) — e.g. slices of an all-gather send buffer (``orbit.py``).
     """
     B, N, V, means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg = _checked(
         means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg)
@@ -435,9 +440,17 @@ def rasterize_batch(means3D, cov3D, colors, opacities, viewmatrix, projmatrix, b
     flags = (_native.FLAG_CLAMP_COLOR if clamp_color else 0) | (_native.FLAG_SIMPLE_BLEND if simple_blend else 0)
     flags |= _common_flags((means3D, cov3D, colors, opacities, means2D), exact_exp)
     force_sync = bool(sync_if_no_grad) and bool(flags & _native.FLAG_FORWARD_ONLY)
+    if out is not None:
+        H_, W_ = int(image_height), int(image_width)
+        for t, ch, name in zip(out, (3, 1, 1), ("color", "depth", "alpha")):
+            if (not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()
+                    or tuple(t.shape) != (B, V, ch, H_, W_)):
+                raise ValueError(f"out[{name}] must be a contiguous float32 CUDA tensor of shape {(B, V, ch, H_, W_)}")
+        out = tuple(out)
     color, radii, depth, alpha, _loss, feed = _RasterizeBatch.apply(
         means3D, cov3D, colors, opacities, means2D, viewmatrix, projmatrix, bg, int(image_height), int(image_width),
-        float(tanfovx), float(tanfovy), flags, int(renders_per_chunk), None, None, None, force_sync, bool(lpips_feed))
+        float(tanfovx), float(tanfovy), flags, int(renders_per_chunk), None, None, None, force_sync, bool(lpips_feed),
+        out)
     return (color, radii, depth, alpha, feed) if lpips_feed else (color, radii, depth, alpha)
 
 
@@ -489,7 +502,7 @@ def render_l1_loss(means3D, cov3D, colors, opacities, viewmatrix, projmatrix, bg
     flags = _common_flags((means3D, cov3D, colors, opacities), exact_exp)
     color, radii, depth, alpha, loss, feed = _RasterizeBatch.apply(
         means3D, cov3D, colors, opacities, None, viewmatrix, projmatrix, bg, H, W, float(tanfovx), float(tanfovy),
-        flags, int(renders_per_chunk), target, mask, _loss_scale(reduction, B, V, H, W), False, bool(lpips_feed))
+        flags, int(renders_per_chunk), target, mask, _loss_scale(reduction, B, V, H, W), False, bool(lpips_feed), None)
     return (loss, color, radii, depth, alpha, feed) if lpips_feed else (loss, color, radii, depth, alpha)
 
 

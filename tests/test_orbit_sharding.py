@@ -66,3 +66,58 @@ def test_two_rank_gather_with_compact_wire_format(wire, tol):
     want = _fake_render(list(range(num_views))) / 100.0
     for r in range(world):
         assert ret[r].dtype == torch.float32 and float((ret[r] - want).abs().max()) <= tol
+
+
+# ---------------------------------------------------------------------------------------------- overlapped gather
+def _fake_planes(ids, out):
+    """(colour, depth, alpha) that encode the view id; colours in [0, 1] (uint8 wire format)."""
+    c = torch.stack([torch.full((3, 4, 6), float(v) / 100.0) + torch.arange(3.0).view(3, 1, 1) * 0.001 for v in ids])
+    d = torch.stack([torch.full((1, 4, 6), float(v) * 0.5) for v in ids])
+    a = torch.stack([torch.full((1, 4, 6), float(v) / 200.0) for v in ids])
+    return c, d, a
+
+
+def _worker_overlapped(rank, world, port, num_views, chunk, compact, ret):
+    from sigman_release_b200.orbit import WIRE_COMPACT, WIRE_EXACT, render_orbit_overlapped
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ret[rank] = render_orbit_overlapped(_fake_planes, num_views, 4, 6, "cpu", wire=WIRE_COMPACT if compact else WIRE_EXACT,
+                                            chunk=chunk)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_range_partition():
+    from sigman_release_b200.orbit import shard_range
+    for world in (1, 2, 4, 8):
+        for n in (1, 7, 90, 91):
+            got = []
+            for r in range(world):
+                first, count, per = shard_range(n, r, world)
+                assert per == (n + world - 1) // world and count <= per
+                got += list(range(first, first + count))
+            assert got == list(range(n))                       # contiguous shards in rank order = view order
+
+
+@pytest.mark.parametrize("num_views,chunk", [(7, 2), (90, 4), (91, 16)])
+def test_two_rank_overlapped_gather_equals_single_process(num_views, chunk):
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_overlapped, args=(world, _free_port(), num_views, chunk, False, ret), nprocs=world, join=True)
+    c, d, a = _fake_planes(range(num_views), None)
+    expect = torch.cat([c, d, a], dim=1)
+    for r in range(world):
+        assert torch.equal(ret[r], expect)                     # exact wire format: bitwise
+
+
+def test_two_rank_overlapped_gather_compact_wire():
+    world, num_views = 2, 9
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_overlapped, args=(world, _free_port(), num_views, 2, True, ret), nprocs=world, join=True)
+    c, d, a = _fake_planes(range(num_views), None)
+    for r in range(world):
+        assert float((ret[r][:, 0:3] - c).abs().max()) <= 0.5 / 255 + 1e-6      # uint8 RGB
+        assert float((ret[r][:, 3:4] - d).abs().max()) <= 4e-3                   # fp16 depth
+        assert float((ret[r][:, 4:5] - a).abs().max()) <= 1e-4                   # fp16 alpha
