@@ -50,111 +50,161 @@ __device__ __forceinline__ int size_class(unsigned int c) {
     return 2 * (msb + 1) + half;
 }
 
+constexpr int kPlanIpt = 8;          // tiles per thread and strip of the scan sweep
+
 __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
-    // Both scanned quantities travel in one 64-bit word: instances (high 40 bits) and empty tiles (low 24 bits) —
-    // most tiles of a human render are empty, so their list positions come from the scan, not from atomics.
+    // The kernel is a latency chain on one SM, so it is written as TWO sweeps over tile_cnt whose loads are all
+    // independent (one exposed L2 latency each), with the header fields fetched ahead:
+    //   sweep 1 (coalesced): totals (instances, empty tiles, longest list, non-empty tiles) and the size-class histogram;
+    //   thread 0: device-side reservation of the instance range, class starts, counters;
+    //   sweep 2 (strips of 1024 * kPlanIpt tiles, carried scan): tile_off, zeroed cursors, and the two
+    //   work lists — empty tiles at their scanned position, non-empty tiles at a shared-memory cursor of their class.
+    // Both scanned quantities travel in one 64-bit word: instances (high 40 bits) and empty tiles (low 24 bits).
     __shared__ unsigned long long s_warp[32];
-    __shared__ unsigned long long s_total;
+    __shared__ unsigned long long s_total, s_base;
+    __shared__ unsigned long long s_red[32];
     __shared__ unsigned int s_max, s_nonempty, s_dropped;
-    __shared__ unsigned long long s_base;
     __shared__ unsigned int s_hist[kSizeClasses], s_start[kSizeClasses];
     const int t = threadIdx.x;
-    const int ipt = (a.n + kScanThreads - 1) / kScanThreads;
-    const int lo = min(a.n, t * ipt), hi = min(a.n, lo + ipt);
-    unsigned int mx = 0, ne = 0;
-    unsigned long long sum = 0;
-    for (int k = lo; k < hi; ++k) {
-        const unsigned int c = a.tile_cnt[k];
-        sum += (static_cast<unsigned long long>(c) << 24) + (c == 0 ? 1ull : 0ull);
-        mx = max(mx, c); ne += (c != 0);
-    }
-    if (t == 0) { s_max = 0; s_nonempty = 0; }
-    if (t < kSizeClasses) s_hist[t] = 0;
-    // block exclusive scan of `sum`
-    unsigned long long inc = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, d);
-        if ((t & 31) >= d) inc += v;
-    }
-    if ((t & 31) == 31) s_warp[t >> 5] = inc;
-    __syncthreads();
-    if (t < 32) {
-        unsigned long long w = s_warp[t], wi = w;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned long long v = __shfl_up_sync(0xffffffffu, wi, d);
-            if (t >= d) wi += v;
-        }
-        s_warp[t] = wi - w;                       // exclusive warp prefix
-        if (t == 31) s_total = wi;
-    }
-    __syncthreads();
-    const unsigned long long excl64 = inc - sum + s_warp[t >> 5];
-    const unsigned int excl = static_cast<unsigned int>(excl64 >> 24);
-    unsigned int empty_pos = static_cast<unsigned int>(excl64 & 0xffffffull);
+    // header fields of earlier chunks (their kernels precede this one in the stream), fetched ahead of the sweeps
+    unsigned long long h_cursor = 0, h_capacity = 0, h_required = 0, h_blk_required = 0, h_blk_capacity = 0;
+    unsigned int h_overflow = 0, h_max = 0, h_nonempty = 0;
     if (t == 0) {
         if (a.first_chunk) {
-            a.header->inst_required = 0; a.header->capacity = a.capacity; a.header->overflow = 0;
-            a.header->max_tile_instances = 0; a.header->nonempty_tiles = 0; a.header->pad = 0;
-            a.header->inst_cursor = 0;
-            a.header->blk_required = 0; a.header->blk_capacity = a.blk_capacity;
-        }
-        const unsigned long long base = a.header->inst_cursor;
-        const unsigned long long total = s_total >> 24;
-        a.header->inst_required += total;
-        const bool fits = base + total <= a.header->capacity;
-        s_dropped = fits ? 0u : 1u;
-        s_base = base;
-        if (fits) a.header->inst_cursor = base + total; else a.header->overflow |= 1u;
-    }
-    __syncthreads();
-    const bool dropped = s_dropped != 0;
-    unsigned int run = static_cast<unsigned int>(s_base) + excl;
-    for (int k = lo; k < hi; ++k) {
-        unsigned int c = a.tile_cnt[k];
-        a.cursor[k] = 0;
-        if (dropped) {                            // render(s) emitted as background; reported via the status block
-            a.tile_cnt[k] = 0;
-            a.tile_off[k] = static_cast<unsigned int>(s_base);
-            c = 0;
+            h_capacity = a.capacity; h_blk_capacity = a.blk_capacity;
         } else {
-            a.tile_off[k] = run;
-            run += c;
+            h_cursor = a.header->inst_cursor; h_capacity = a.header->capacity; h_required = a.header->inst_required;
+            h_blk_required = a.header->blk_required; h_blk_capacity = a.header->blk_capacity;
+            h_overflow = a.header->overflow; h_max = a.header->max_tile_instances; h_nonempty = a.header->nonempty_tiles;
         }
-        if (c != 0) atomicAdd(&s_hist[size_class(c)], 1u);
+        s_max = 0; s_nonempty = 0;
     }
-    atomicMax(&s_max, mx);
-    atomicAdd(&s_nonempty, ne);
+    if (t < kSizeClasses) s_hist[t] = 0;
+    __syncthreads();
+    // ---- sweep 1
+    {
+        unsigned int mx = 0, ne = 0;
+        unsigned long long sum = 0;
+        for (int k0 = 0; k0 < a.n; k0 += kScanThreads * kPlanIpt) {
+            unsigned int c[kPlanIpt];
+#pragma unroll
+            for (int j = 0; j < kPlanIpt; ++j) {
+                const int k = k0 + j * kScanThreads + t;
+                c[j] = k < a.n ? a.tile_cnt[k] : 0xffffffffu;
+            }
+#pragma unroll
+            for (int j = 0; j < kPlanIpt; ++j) {
+                if (c[j] == 0xffffffffu) continue;          // beyond the chunk (a real count never reaches 2^32 - 1)
+                sum += (static_cast<unsigned long long>(c[j]) << 24) + (c[j] == 0 ? 1ull : 0ull);
+                mx = max(mx, c[j]);
+                if (c[j] != 0) { ++ne; atomicAdd(&s_hist[size_class(c[j])], 1u); }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, d);
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+            ne += __shfl_xor_sync(0xffffffffu, ne, d);
+        }
+        if ((t & 31) == 0) { s_red[t >> 5] = sum; atomicMax(&s_max, mx); atomicAdd(&s_nonempty, ne); }
+    }
     __syncthreads();
     if (t == 0) {
-        a.wc->chunk_instances = dropped ? 0u : static_cast<unsigned int>(s_total >> 24);
-        a.wc->chunk_dropped = s_dropped;
-        if (!dropped) {
-            a.header->max_tile_instances = max(a.header->max_tile_instances, s_max);
-            a.header->nonempty_tiles += s_nonempty;
-        }
+        unsigned long long tot = 0;
+#pragma unroll
+        for (int w = 0; w < 32; ++w) tot += s_red[w];
+        const unsigned long long total = tot >> 24;
+        const bool fits = h_cursor + total <= h_capacity;
+        s_dropped = fits ? 0u : 1u;
+        s_base = h_cursor;
+        a.header->inst_required = h_required + total;
+        a.header->capacity = h_capacity;
+        a.header->overflow = h_overflow | (fits ? 0u : 1u);
+        a.header->max_tile_instances = fits ? max(h_max, s_max) : h_max;
+        a.header->nonempty_tiles = h_nonempty + (fits ? s_nonempty : 0u);
+        a.header->pad = 0;
+        a.header->inst_cursor = fits ? h_cursor + total : h_cursor;
+        if (a.first_chunk) { a.header->blk_required = 0; a.header->blk_capacity = h_blk_capacity; }
+        a.wc->chunk_instances = fits ? static_cast<unsigned int>(total) : 0u;
+        a.wc->chunk_dropped = fits ? 0u : 1u;
         unsigned int r1 = 0;
         for (int c = kSizeClasses - 1; c >= 1; --c) { s_start[c] = r1; r1 += s_hist[c]; }
         s_start[0] = 0;
-        a.wc->n_big = s_start[size_class(kSmallSortCap) - 1];    // tiles of the classes >= class(kSmallSortCap)
+        a.wc->n_big = fits ? s_start[size_class(kSmallSortCap) - 1] : 0u;   // tiles of the classes >= class(kSmallSortCap)
         a.wc->sort_cursor = 0;
-        a.wc->n_blend = r1;
-        a.wc->n_empty = dropped ? unsigned(a.n) : static_cast<unsigned int>(s_total & 0xffffffull);
+        a.wc->n_blend = fits ? r1 : 0u;
+        a.wc->n_empty = fits ? static_cast<unsigned int>(tot & 0xffffffull) : unsigned(a.n);
         a.wc->blend_cursor = 0;
         a.wc->empty_cursor = 0;
         // the block-record cursor is final for all earlier chunks here (their sorts precede this kernel in the stream)
 #pragma unroll
         for (int c = 0; c < kBwdClasses; ++c) a.plan->n_items[c] = 0;
-        const unsigned long long used = min(a.header->blk_required, a.header->blk_capacity);   // records really stored
+        const unsigned long long used = min(h_blk_required, h_blk_capacity);   // records really stored
         a.plan->item_base = a.item_region + static_cast<unsigned int>(used / kSegB);
         a.plan->cursor = 0;
     }
     __syncthreads();
-    for (int k = lo; k < hi; ++k) {
-        const unsigned int c = dropped ? 0u : a.tile_cnt[k];
-        if (c == 0) { a.work_empty[dropped ? unsigned(k) : empty_pos++] = k; continue; }
-        a.work_blend[atomicAdd(&s_start[size_class(c)], 1u)] = k;
+    const bool dropped = s_dropped != 0;
+    const unsigned int base = static_cast<unsigned int>(s_base);
+    // ---- sweep 2: warp w of a strip owns 32 * kPlanIpt consecutive tiles, lane l the tiles base + 32 j + l — every
+    // load and store of the sweep is coalesced (a single SM executes this kernel: its load/store unit is the limit)
+    const int warp = t >> 5, lane = t & 31;
+    unsigned long long carry = 0;                 // (instances << 24 | empty tiles) of the strips before this one
+    for (int k0 = 0; k0 < a.n; k0 += kScanThreads * kPlanIpt) {
+        const int wbase = k0 + warp * 32 * kPlanIpt;
+        unsigned int c[kPlanIpt];
+#pragma unroll
+        for (int j = 0; j < kPlanIpt; ++j) {
+            const int k = wbase + 32 * j + lane;
+            c[j] = k < a.n ? a.tile_cnt[k] : 0xffffffffu;
+        }
+        unsigned long long ex[kPlanIpt];           // exclusive prefix inside the warp's range
+        unsigned long long wsum = 0;
+#pragma unroll
+        for (int j = 0; j < kPlanIpt; ++j) {
+            const unsigned long long v =
+                c[j] == 0xffffffffu ? 0ull : (static_cast<unsigned long long>(c[j]) << 24) + (c[j] == 0 ? 1ull : 0ull);
+            unsigned long long inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += u;
+            }
+            ex[j] = wsum + inc - v;
+            wsum += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        __syncthreads();                          // s_warp / s_total of the previous strip have been read
+        if (lane == 0) s_warp[warp] = wsum;
+        __syncthreads();
+        if (t < 32) {
+            unsigned long long w = s_warp[t], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long u = __shfl_up_sync(0xffffffffu, wi, d);
+                if (t >= d) wi += u;
+            }
+            s_warp[t] = wi - w;                   // exclusive warp prefix
+            if (t == 31) s_total = wi;
+        }
+        __syncthreads();
+        const unsigned long long wex = carry + s_warp[warp];
+#pragma unroll
+        for (int j = 0; j < kPlanIpt; ++j) {
+            if (c[j] == 0xffffffffu) continue;
+            const int k = wbase + 32 * j + lane;
+            const unsigned long long e64 = wex + ex[j];
+            a.cursor[k] = 0;
+            if (dropped) {                        // render(s) emitted as background; reported via the status block
+                a.tile_cnt[k] = 0;
+                a.tile_off[k] = base;
+                a.work_empty[k] = k;
+            } else {
+                a.tile_off[k] = base + static_cast<unsigned int>(e64 >> 24);
+                if (c[j] == 0) a.work_empty[static_cast<unsigned int>(e64 & 0xffffffull)] = k;
+                else a.work_blend[atomicAdd(&s_start[size_class(c[j])], 1u)] = k;
+            }
+        }
+        carry += s_total;
     }
 }
 
@@ -164,7 +214,6 @@ struct SortArgs {
     const unsigned int* tile_off;    // global arrays
     const unsigned int* tile_cnt;
     const unsigned long long* keys;
-    unsigned long long* keys_w;      // the same buffer, writable: (mask, id) pairs of spilled tiles after their keys are dead
     unsigned long long* keys_tmp;    // second key buffer [cap]: bucket-ordered keys of lists beyond the shared memory
     unsigned int* sorted_ids;
     float4 *rec0, *rec1, *rec2;      // tile-level records in depth order
@@ -179,6 +228,16 @@ struct SortArgs {
     unsigned int* bidx;              // block-list entries (position in the tile list << 4 | quarter mask)
     unsigned long long blk_capacity;
 };
+
+// Experiment build (-DSGR_SORT_TIMING, tools/sort_timing.py): per-tile phase timestamps of the tile sorts.
+#ifdef SGR_SORT_TIMING
+constexpr int kSortMarks = 10;
+__device__ unsigned long long g_sort_marks[4096][kSortMarks + 2];
+__device__ unsigned int g_sort_mark_cursor;
+#define SORT_MARK(i) do { if (threadIdx.x == 0 && mark_slot < 4096u) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); g_sort_marks[mark_slot][i] = tt; } } while (0)
+#else
+#define SORT_MARK(i) do {} while (0)
+#endif
 
 template <int THREADS>
 __device__ __forceinline__ void block_minmax(unsigned long long& mn, unsigned long long& mx, unsigned long long* s_red) {
@@ -250,7 +309,7 @@ __device__ __forceinline__ void block_exclusive_scan(unsigned int* hist, unsigne
 // over the unsorted keys (range, histogram, scatter) cost ONE exposed global-memory latency instead of three (the
 // per-tile sort is a latency chain, not a bandwidth problem); KPT == 0 re-reads the keys from global memory.
 template <int THREADS, int NB, int KPT>
-__device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local, unsigned long long* kb, unsigned int* aux,
+__device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local, unsigned long long* kb,
                                               unsigned int* hist, unsigned int* s_warp, unsigned long long* s_red) {
     const int t = threadIdx.x;
     const int rl = tile_local / a.num_tiles;
@@ -260,6 +319,16 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
     const unsigned long long* keys = a.keys + off;
     constexpr int KR = KPT > 0 ? KPT : 1;
     unsigned long long kr[KR];
+#ifdef SGR_SORT_TIMING
+    __shared__ unsigned int s_mark_slot;
+    if (t == 0) {
+        s_mark_slot = atomicAdd(&g_sort_mark_cursor, 1u);
+        if (s_mark_slot < 4096u) { g_sort_marks[s_mark_slot][kSortMarks] = n; g_sort_marks[s_mark_slot][kSortMarks + 1] = THREADS; }
+    }
+    __syncthreads();
+    const unsigned int mark_slot = s_mark_slot;
+#endif
+    SORT_MARK(0);
 
     // 0. key range
     unsigned long long mn = ~0ull, mx = 0ull;
@@ -287,6 +356,7 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
     static_assert((1 << LOG_NB) == NB, "NB must be 1024, 2048 or 4096");
     const int shift = max(0, bits - LOG_NB);
 
+    SORT_MARK(1);
     // 1. bucket histogram
     if (KPT > 0) {
 #pragma unroll
@@ -297,8 +367,10 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
             atomicAdd(&hist[static_cast<unsigned int>((keys[k] - mn) >> shift)], 1u);
     }
     __syncthreads();
+    SORT_MARK(2);
     // 2. bucket starts
     block_exclusive_scan<THREADS, NB>(hist, s_warp);
+    SORT_MARK(3);
     // 3. scatter into bucket order (arbitrary order inside a bucket); afterwards hist[b] = end of bucket b
     if (KPT > 0) {
 #pragma unroll
@@ -313,9 +385,8 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
         }
     }
     __syncthreads();
-    // 4. exact rank inside the bucket -> final position of the id (upstream's point_list).  Unrolled so that several
-    //    independent chains are in flight per thread (the step is L2-latency bound).  With `simple` the owner of an
-    //    element also gathers its 48-byte record into depth order (tile-level stream of the upstream-shaped kernels).
+    SORT_MARK(4);
+    // 4a. exact rank inside the bucket -> final position of the id (upstream's point_list).
     const size_t gb = size_t(rl) * a.N;
     const int tile = tile_local - rl * a.num_tiles;
     const float X0 = float((tile % a.tiles_x) * kTile), Y0 = float((tile / a.tiles_x) * kTile);
@@ -327,20 +398,32 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
         const unsigned int e = hist[b];
         unsigned int cnt = 0;
         for (unsigned int j = s; j < e; ++j) cnt += (kb[j] < key) ? 1u : 0u;
-        const unsigned int id = static_cast<unsigned int>(key & 0xffffffffull);
-        const size_t pos = off + s + cnt;
-        a.sorted_ids[pos] = id;
-        // the owner of an element gathers its 48-byte record into depth order (the tile-level stream); word 2 of rec0
-        // becomes the instance's position in the tile list (upstream's contributor index)
+        a.sorted_ids[off + s + cnt] = static_cast<unsigned int>(key & 0xffffffffull);
+    }
+    __syncthreads();                             // the CTA's own global stores are visible to it behind the barrier
+    SORT_MARK(5);
+    // 4b. gather the 48-byte records into depth order (the tile-level stream): thread = sorted position, so the id
+    //     loads and the record stores are coalesced.  Word 2 of rec0 becomes the position in the tile list (upstream's
+    //     contributor index).  The key buffer is dead after the ranking: its first 4 n bytes take the quarter masks
+    //     in sorted order.
+    unsigned int* masks = reinterpret_cast<unsigned int*>(kb);
+#pragma unroll 4
+    for (unsigned int p = t; p < n; p += THREADS) {
+        const unsigned int id = a.sorted_ids[off + p];
         float4 v0 = __ldg(a.g0 + gb + id);
+        const float4 v1 = __ldg(a.g1 + gb + id);
+        const float4 v2 = __ldg(a.g2 + gb + id);
         const unsigned int mask = quarter_mask(v0.x, v0.y, v0.z, X0, Y0);   // the instance's cull mask for this tile
-        v0.z = __uint_as_float(s + cnt);
-        a.rec0[pos] = v0;
-        a.rec1[pos] = __ldg(a.g1 + gb + id);
-        a.rec2[pos] = __ldg(a.g2 + gb + id);
-        if (!a.simple) aux[s + cnt] = mask;              // masks in sorted order for the block-list emission
+        if (!a.simple) masks[p] = mask;
+        // an instance whose extent touches no pixel of the tile enters no block list: its record is never read
+        if (!a.simple && mask == 0u) continue;
+        v0.z = __uint_as_float(p);
+        a.rec0[off + p] = v0;
+        a.rec1[off + p] = v1;
+        a.rec2[off + p] = v2;
     }
     __syncthreads();
+    SORT_MARK(6);
     if (a.simple) return;
 
     // 5. block lists.  Every instance is appended to the list of each 8x4 pixel block of the tile that its
@@ -352,7 +435,7 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
     //    Every list starts at a multiple of 4 entries (16-byte aligned: the index batches travel by 1-D TMA).
     const size_t tgb = tg * kBlocksPerTile;
     const unsigned int nchunks = (n + 31u) >> 5;
-    unsigned int* cpre = reinterpret_cast<unsigned int*>(kb);              // [nchunks][8] counts -> exclusive prefixes
+    unsigned int* cpre = masks + ((n + 31u) & ~31u);                       // [nchunks][8] counts -> exclusive prefixes (n more bytes of kb)
     const int warp = t >> 5, lane = t & 31;
     constexpr int kWarps = THREADS / 32;
     for (unsigned int c0 = warp; c0 < nchunks; c0 += 4 * kWarps) {      // four chunks in flight per warp
@@ -360,7 +443,7 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const unsigned int p = 32u * (c0 + k * kWarps) + lane;
-            mk[k] = p < n ? aux[p] : 0u;
+            mk[k] = p < n ? masks[p] : 0u;
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -376,6 +459,7 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
         }
     }
     __syncthreads();
+    SORT_MARK(7);
     if (warp < kBlocksPerTile) {                 // warp w: exclusive scan of block w's chunk counts
         unsigned int running = 0;
         for (unsigned int c0 = 0; c0 < nchunks; c0 += 32) {
@@ -411,6 +495,7 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
         s_warp[16] = fits ? 1u : 0u;
     }
     __syncthreads();
+    SORT_MARK(8);
     if (s_warp[16]) {
         const unsigned int lt = (1u << lane) - 1u;
         for (unsigned int c0 = warp; c0 < nchunks; c0 += 4 * kWarps) {      // four chunks in flight per warp
@@ -418,7 +503,7 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const unsigned int p = 32u * (c0 + k * kWarps) + lane;
-                mk[k] = p < n ? aux[p] : 0u;
+                mk[k] = p < n ? masks[p] : 0u;
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -441,14 +526,16 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
         }
     }
     __syncthreads();                             // the buffers are reused by the CTA's next tile
+    SORT_MARK(9);
 }
 
 #ifndef SGR_SORT_SMALL_MIN_CTAS
 #define SGR_SORT_SMALL_MIN_CTAS 3
 #endif
 __global__ void __launch_bounds__(kSmallSortThreads, SGR_SORT_SMALL_MIN_CTAS) sort_small_kernel(SortArgs a) {
-    __shared__ unsigned long long kb[kSmallSortCap];
-    __shared__ unsigned int hist[kSmallSortBuckets];
+    extern __shared__ __align__(16) unsigned char smem_raw[];                // kSmallSortSmem bytes
+    unsigned long long* kb = reinterpret_cast<unsigned long long*>(smem_raw);                   // kSmallSortCap keys
+    unsigned int* hist = reinterpret_cast<unsigned int*>(kb + kSmallSortCap);                   // kSmallSortBuckets
     __shared__ unsigned int s_warp[32];
     __shared__ unsigned long long s_red[2 * (kSmallSortThreads / 32) + 2];
     __shared__ unsigned int s_item;
@@ -462,13 +549,11 @@ __global__ void __launch_bounds__(kSmallSortThreads, SGR_SORT_SMALL_MIN_CTAS) so
         const int tile_local = a.work[w];
         const size_t tg = size_t(a.render_base) * a.num_tiles + tile_local;
         const unsigned int n = a.tile_cnt[tg];
-        // (quarter mask, Gaussian id) pairs in sorted order: the tile's own key segment, dead once the keys sit in kb
-        unsigned int* aux = reinterpret_cast<unsigned int*>(a.keys_w + a.tile_off[tg]);
         if (n <= 4u * kSmallSortThreads)
-            sort_one_tile<kSmallSortThreads, kSmallSortBuckets, 4>(a, tile_local, kb, aux, hist, s_warp, s_red);
+            sort_one_tile<kSmallSortThreads, kSmallSortBuckets, 4>(a, tile_local, kb, hist, s_warp, s_red);
         else
             sort_one_tile<kSmallSortThreads, kSmallSortBuckets, kSmallSortCap / kSmallSortThreads>(
-                a, tile_local, kb, aux, hist, s_warp, s_red);
+                a, tile_local, kb, hist, s_warp, s_red);
     }
     // Programmatic dependent launch (launch_sort_tiles): this grid started before sort_big_kernel finished.  The
     // blend behind it in the stream is ordered after THIS grid only, so every CTA waits here for the long-list
@@ -492,19 +577,28 @@ __global__ void __launch_bounds__(kBigSortThreads) sort_big_kernel(SortArgs a) {
         const int tile_local = a.work[w];
         const size_t tg = size_t(a.render_base) * a.num_tiles + tile_local;
         const unsigned int n = a.tile_cnt[tg];
-        // lists that do not fit in shared memory use their segment of the second global key buffer; the (mask, id)
-        // pairs in sorted order go to the tile's own segment of the first one, dead once the keys sit in kb
+        // lists that do not fit in shared memory use their segment of the second global key buffer
         const bool spill = n > a.big_smem_keys;
         unsigned long long* kb = spill ? a.keys_tmp + a.tile_off[tg] : kb_s;
-        unsigned int* aux = reinterpret_cast<unsigned int*>(a.keys_w + a.tile_off[tg]);
         if (n <= 8u * kBigSortThreads && !spill)
-            sort_one_tile<kBigSortThreads, kBigSortBuckets, 8>(a, tile_local, kb, aux, hist, s_warp, s_red);
+            sort_one_tile<kBigSortThreads, kBigSortBuckets, 8>(a, tile_local, kb, hist, s_warp, s_red);
         else
-            sort_one_tile<kBigSortThreads, kBigSortBuckets, 0>(a, tile_local, kb, aux, hist, s_warp, s_red);
+            sort_one_tile<kBigSortThreads, kBigSortBuckets, 0>(a, tile_local, kb, hist, s_warp, s_red);
     }
 }
 
 }  // namespace
+
+#ifdef SGR_SORT_TIMING
+extern "C" int sgr_debug_sort_marks(unsigned long long* out, unsigned int* count) {   // experiment build only
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(count, g_sort_mark_cursor, sizeof(unsigned int));
+    cudaMemcpyFromSymbol(out, g_sort_marks, sizeof(unsigned long long) * 4096 * (kSortMarks + 2));
+    unsigned int zero = 0;
+    cudaMemcpyToSymbol(g_sort_mark_cursor, &zero, sizeof(zero));
+    return 0;
+}
+#endif
 
 cudaError_t launch_plan(const ChunkCtx& c) {
     PlanArgs a;
@@ -534,7 +628,7 @@ cudaError_t launch_sort_tiles(const ChunkCtx& c) {
     a.tile_off = c.tile_off; a.tile_cnt = c.tile_cnt; a.keys = c.keys; a.sorted_ids = c.sorted_ids;
     a.rec0 = c.rec0; a.rec1 = c.rec1; a.rec2 = c.rec2; a.g0 = c.g0; a.g1 = c.g1; a.g2 = c.g2;
     a.work = c.work_blend; a.wc = c.work_counts;
-    a.keys_tmp = c.keys_tmp; a.keys_w = c.keys;
+    a.keys_tmp = c.keys_tmp;
     a.simple = (c.p->flags & SGR_FLAG_SIMPLE_BLEND) ? 1 : 0;
     a.header = c.header; a.blk_off = c.blk_off; a.blk_cnt = c.blk_cnt;
     a.bidx = c.bidx; a.blk_capacity = c.blk_capacity;
@@ -562,7 +656,9 @@ cudaError_t launch_sort_tiles(const ChunkCtx& c) {
         cudaError_t e = cudaFuncSetAttribute(sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              int(size_t(kBigSortSmemCap) * 8 + size_t(kBigSortBuckets) * 4));
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&small_per_sm, sort_small_kernel, kSmallSortThreads, 0);
+        e = cudaFuncSetAttribute(sort_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmallSortSmem));
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&small_per_sm, sort_small_kernel, kSmallSortThreads, kSmallSortSmem);
         if (e != cudaSuccess) return e;
         if (small_per_sm <= 0) small_per_sm = 1;
         attr_set = true;
@@ -573,7 +669,7 @@ cudaError_t launch_sort_tiles(const ChunkCtx& c) {
     if (mode < 0) { const char* m = getenv("SGR_SORT_MODE"); mode = m ? atoi(m) : 0; }
     if (mode >= 1 && mode <= 3) {
         if (mode != 2) sort_big_kernel<<<min(num_sms, total_tiles), kBigSortThreads, big_smem, c.stream>>>(a);
-        if (mode != 3) sort_small_kernel<<<min(num_sms * small_per_sm, total_tiles), kSmallSortThreads, 0, c.stream>>>(a);
+        if (mode != 3) sort_small_kernel<<<min(num_sms * small_per_sm, total_tiles), kSmallSortThreads, kSmallSortSmem, c.stream>>>(a);
         return cudaGetLastError();
     }
     // The long-list kernel goes first (it is the longer pole and a 1024-thread CTA cannot share an SM with the
@@ -587,7 +683,7 @@ cudaError_t launch_sort_tiles(const ChunkCtx& c) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(min(num_sms * small_per_sm, total_tiles));
         cfg.blockDim = dim3(kSmallSortThreads);
-        cfg.dynamicSmemBytes = 0;
+        cfg.dynamicSmemBytes = kSmallSortSmem;
         cfg.stream = c.stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -610,7 +706,7 @@ cudaError_t launch_sort_tiles(const ChunkCtx& c) {
     if ((e = cudaStreamWaitEvent(side, ev_fork, 0)) != cudaSuccess) return e;
     sort_big_kernel<<<min(num_sms, total_tiles), kBigSortThreads, big_smem, c.stream>>>(a);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    sort_small_kernel<<<min(num_sms * small_per_sm, total_tiles), kSmallSortThreads, 0, side>>>(a);
+    sort_small_kernel<<<min(num_sms * small_per_sm, total_tiles), kSmallSortThreads, kSmallSortSmem, side>>>(a);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if ((e = cudaEventRecord(ev_join, side)) != cudaSuccess) return e;
     return cudaStreamWaitEvent(c.stream, ev_join, 0);

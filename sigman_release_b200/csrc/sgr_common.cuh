@@ -131,12 +131,13 @@ struct WorkCounts {
     unsigned int empty_cursor;
 };
 
-constexpr int kSmallSortCap = 4096;       // lists shorter than this are sorted in a 40 KB shared-memory CTA (power of two)
+constexpr int kSmallSortCap = 4096;       // lists shorter than this are sorted in a 36 KB shared-memory CTA (power of two)
 constexpr int kSmallSortThreads = 256;
 constexpr int kSmallSortBuckets = 1024;
 constexpr int kBigSortThreads = 1024;
 constexpr int kBigSortBuckets = 4096;
 constexpr int kBigSortSmemCap = 26 * 1024;  // instances whose keys fit in shared memory next to the histogram
+constexpr size_t kSmallSortSmem = size_t(kSmallSortCap) * 8 + size_t(kSmallSortBuckets) * 4;    // keys, histogram
 
 // ------------------------------------------------------------------------------------------------
 // Per-render constants handed to kernels by value.
@@ -202,16 +203,24 @@ __device__ __forceinline__ float2 unpack_extent(float packed) {
 // blk = (y block 0..3) * 2 + (x block 0..1), q = (x half) | (y half) << 1 — the blend kernels' work decomposition.
 // NaN coordinates give an empty mask (all comparisons false): such a record can never pass the alpha test.
 __device__ __forceinline__ unsigned int quarter_mask(float x, float y, float packed_ext, float X0, float Y0) {
+    // Pixel centres are integers, so "xh >= first centre of the column" is floor(xh) >= it, and "xl <= last centre" is
+    // ceil(xl) <= it: the overlapped columns / rows are integer ranges (exact; the clamps only keep the conversions
+    // in range and map NaN to an empty range), turned into the mask with shifts and one carry-free multiply.
     const float2 ext = unpack_extent(packed_ext);
-    const float xl = x - ext.x, xh = x + ext.x, yl = y - ext.y, yh = y + ext.y;
-    unsigned int row = 0, mask = 0;
-#pragma unroll
-    for (int qc = 0; qc < 4; ++qc)
-        if (xh >= X0 + float(4 * qc) && xl <= X0 + float(4 * qc + 3)) row |= 1u << ((qc & 1) | ((qc >> 1) << 2));
-#pragma unroll
-    for (int qr = 0; qr < 8; ++qr)
-        if (yh >= Y0 + float(2 * qr) && yl <= Y0 + float(2 * qr + 1)) mask |= row << ((qr >> 1) * 8 + (qr & 1) * 2);
-    return mask;
+    const int X0i = __float2int_rz(X0), Y0i = __float2int_rz(Y0);
+    const int cxl = __float2int_ru(fminf(fmaxf(x - ext.x, -1.0e6f), 1.0e6f)) - X0i;
+    const int fxh = __float2int_rd(fminf(fmaxf(x + ext.x, -1.0e6f), 1.0e6f)) - X0i;
+    const int cyl = __float2int_ru(fminf(fmaxf(y - ext.y, -1.0e6f), 1.0e6f)) - Y0i;
+    const int fyh = __float2int_rd(fminf(fmaxf(y + ext.y, -1.0e6f), 1.0e6f)) - Y0i;
+    const int clo = max(0, cxl >> 2), chi = min(3, fxh >> 2);      // 4-pixel columns qc: clo <= qc <= chi
+    const int rlo = max(0, cyl >> 1), rhi = min(7, fyh >> 1);      // 2-pixel rows qr
+    if (clo > chi || rlo > rhi) return 0u;
+    const unsigned int col4 = (2u << chi) - (1u << clo);           // bits clo..chi
+    const unsigned int row = (col4 & 3u) | ((col4 & 0xcu) << 2);   // column qc -> bit (qc & 1) | (qc >> 1) << 2
+    const unsigned int r8 = (2u << rhi) - (1u << rlo);             // bits rlo..rhi
+    const unsigned int t2 = (r8 & 0x03u) | ((r8 & 0x0cu) << 6) | ((r8 & 0x30u) << 12) | ((r8 & 0xc0u) << 18);
+    const unsigned int m = (t2 & 0x01010101u) | ((t2 & 0x02020202u) << 1);   // row qr -> bit (qr >> 1) * 8 + (qr & 1) * 2
+    return row * m;                                                // disjoint bit groups: the product is the OR of the shifts
 }
 
 constexpr float kAlphaMin = 1.0f / 255.0f;

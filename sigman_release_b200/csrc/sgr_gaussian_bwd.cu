@@ -50,19 +50,25 @@ __global__ void __launch_bounds__(32 * kPreBwdSlots, SGR_PREBWD_MIN_CTAS) prepro
     float gm[3] = {0, 0, 0}, gcov[6] = {0, 0, 0, 0, 0, 0}, gcol[3] = {0, 0, 0}, gop = 0;
     for (int r = r_lo + slot; r < r_hi; r += kPreBwdSlots) {
         const size_t oi = size_t(r - a.render_base) * N + i;
-        const bool vis = a.radii[size_t(r) * N + i] > 0;
+        // all loads of the iteration are issued together (one exposed memory latency): nearly every Gaussian of a
+        // framed subject is visible, so waiting for the radius before fetching the accumulators only serialises them
+        const int rad = a.radii[size_t(r) * N + i];
+        float acc[kAccumPlanes];
+#pragma unroll
+        for (int k = 0; k < kAccumPlanes; ++k) acc[k] = a.accum[k * a.plane + oi];
+        const bool vis = rad > 0;
         if (a.d_means2D && live) {
             float* o = a.d_means2D + (size_t(r) * N + i) * 3;
-            o[0] = vis ? a.accum[0 * a.plane + oi] : 0.0f;
-            o[1] = vis ? a.accum[1 * a.plane + oi] : 0.0f;
+            o[0] = vis ? acc[0] : 0.0f;
+            o[1] = vis ? acc[1] : 0.0f;
             o[2] = 0.0f;
         }
         if (!vis) continue;
-        const float g2x = a.accum[0 * a.plane + oi], g2y = a.accum[1 * a.plane + oi];
-        const float dA = a.accum[2 * a.plane + oi], dB = a.accum[3 * a.plane + oi], dC = a.accum[4 * a.plane + oi];
-        gop += a.accum[5 * a.plane + oi];
-        gcol[0] += a.accum[6 * a.plane + oi]; gcol[1] += a.accum[7 * a.plane + oi]; gcol[2] += a.accum[8 * a.plane + oi];
-        const float dz = a.accum[9 * a.plane + oi];
+        const float g2x = acc[0], g2y = acc[1];
+        const float dA = acc[2], dB = acc[3], dC = acc[4];
+        gop += acc[5];
+        gcol[0] += acc[6]; gcol[1] += acc[7]; gcol[2] += acc[8];
+        const float dz = acc[9];
         const float* view = a.view + size_t(r) * 16;
         const float* proj = a.proj + size_t(r) * 16;
         Cov2D c2;
