@@ -115,7 +115,7 @@ void fill_ctx(ChunkCtx& c, const SgrProblem& p, void* state, void* scratch, cuda
     c.blk_off = reinterpret_cast<unsigned int*>(s + S.blk_off);
     c.blk_cnt = reinterpret_cast<unsigned int*>(s + S.blk_cnt);
     c.blk_eff = reinterpret_cast<unsigned int*>(s + S.blk_eff);
-    c.bidx = reinterpret_cast<unsigned int*>(s + S.bidx);
+    c.bidx = reinterpret_cast<uint2*>(s + S.bidx);
     c.blk_capacity = (p.flags & SGR_FLAG_SIMPLE_BLEND) ? 0ull : p.max_block_records;
     c.ck0 = reinterpret_cast<float4*>(s + S.ck0);
     c.ck1 = reinterpret_cast<float*>(s + S.ck1);
@@ -125,9 +125,9 @@ void fill_ctx(ChunkCtx& c, const SgrProblem& p, void* state, void* scratch, cuda
     c.chunk_index = 0;
     c.keys = reinterpret_cast<unsigned long long*>(x + X.keys);
     c.keys_tmp = reinterpret_cast<unsigned long long*>(x + X.keys_tmp);
-    c.g0 = reinterpret_cast<float4*>(x + X.g0);
-    c.g1 = reinterpret_cast<float4*>(x + X.g1);
-    c.g2 = reinterpret_cast<float4*>(x + X.g2);
+    c.g0 = reinterpret_cast<float4*>(s + S.g0);       // set_chunk() moves the three to the chunk's first render
+    c.g1 = reinterpret_cast<float4*>(s + S.g1);
+    c.g2 = reinterpret_cast<float4*>(s + S.g2);
     c.rect = reinterpret_cast<uint2*>(x + X.rect);
     c.cursor = reinterpret_cast<unsigned int*>(x + X.cursor);
     c.work_blend = reinterpret_cast<unsigned int*>(x + X.work_blend);
@@ -137,6 +137,20 @@ void fill_ctx(ChunkCtx& c, const SgrProblem& p, void* state, void* scratch, cuda
     c.accum = reinterpret_cast<float*>(x + X.accum);
     c.loss_target = nullptr; c.loss_mask = nullptr; c.loss_dL_dcolor = nullptr; c.loss_scale = 0.0f;
     c.stream = stream;
+}
+
+// Points the context at the chunk of renders [r0, r0 + rpc): plan slot and slice of the per-Gaussian records.
+void set_chunk(ChunkCtx& c, const SgrProblem& p, void* state, int r0, int rpc, int R) {
+    const StateLayout S = state_layout(p);
+    char* s = static_cast<char*>(state);
+    c.render_base = r0;
+    c.num_renders = (R - r0 < rpc) ? (R - r0) : rpc;
+    c.chunk_index = r0 / rpc;
+    c.plan = reinterpret_cast<ChunkPlan*>(s + S.plan) + c.chunk_index;
+    const size_t first = size_t(r0) * p.num_gaussians;
+    c.g0 = reinterpret_cast<float4*>(s + S.g0) + first;
+    c.g1 = reinterpret_cast<float4*>(s + S.g1) + first;
+    c.g2 = reinterpret_cast<float4*>(s + S.g2) + first;
 }
 
 __global__ void debug_ranges_kernel(const unsigned int* tile_off, const unsigned int* tile_cnt, int num_tiles,
@@ -223,12 +237,8 @@ int sgr_forward(const SgrForwardArgs* args) {
     // tile_cnt and tile_time are adjacent in `state`: one memset (the status header is initialised by the plan kernel)
     SGR_CUDA(cudaMemsetAsync(c.tile_cnt, 0, (reinterpret_cast<char*>(c.tile_time) - reinterpret_cast<char*>(c.tile_cnt)) +
                                                 size_t(R) * c.g.num_tiles * ((p.flags & SGR_FLAG_TILE_TIMING) ? 8 : 0), stream));
-    ChunkPlan* plan0 = c.plan;
     for (int r0 = 0; r0 < R; r0 += rpc) {
-        c.render_base = r0;
-        c.num_renders = (R - r0 < rpc) ? (R - r0) : rpc;
-        c.chunk_index = r0 / rpc;
-        c.plan = plan0 + c.chunk_index;
+        set_chunk(c, p, args->state, r0, rpc, R);
         if (p.num_gaussians > 0) SGR_STAGE(kStPreprocess, launch_preprocess(c, args->radii));
         SGR_STAGE(kStPlan, launch_plan(c));
         if (p.num_gaussians > 0) {
@@ -279,12 +289,8 @@ int sgr_backward(const SgrBackwardArgs* args) {
     const int R = p.num_subjects * p.views_per_subject;
     const size_t BN = size_t(p.num_subjects) * p.num_gaussians;
     (void)BN;   // the per-subject gradients are stored (not accumulated) by the chunk holding the subject's first view
-    ChunkPlan* plan0 = c.plan;
     for (int r0 = 0; r0 < R; r0 += rpc) {
-        c.render_base = r0;
-        c.num_renders = (R - r0 < rpc) ? (R - r0) : rpc;
-        c.chunk_index = r0 / rpc;
-        c.plan = plan0 + c.chunk_index;
+        set_chunk(c, p, args->state, r0, rpc, R);
         SGR_CUDA(cudaMemsetAsync(c.accum, 0, size_t(c.num_renders) * p.num_gaussians * 4 * kAccumPlanes, stream));
         if (p.flags & SGR_FLAG_SIMPLE_BLEND) {
             SGR_STAGE(kStBlendBwd, launch_blend_backward_simple(c, args->out_alpha, args->dL_dcolor, args->dL_ddepth, args->dL_dalpha));

@@ -214,6 +214,7 @@ struct SortArgs {
     const unsigned int* tile_off;    // global arrays
     const unsigned int* tile_cnt;
     const unsigned long long* keys;
+    unsigned long long* keys_w;      // the first key buffer, writable (scratch of spilled lists once their keys are dead)
     unsigned long long* keys_tmp;    // second key buffer [cap]: bucket-ordered keys of lists beyond the shared memory
     unsigned int* sorted_ids;
     float4 *rec0, *rec1, *rec2;      // tile-level records in depth order
@@ -225,7 +226,7 @@ struct SortArgs {
     // block lists (simple == 0)
     StateHeader* header;
     unsigned int *blk_off, *blk_cnt;
-    unsigned int* bidx;              // block-list entries (position in the tile list << 4 | quarter mask)
+    uint2* bidx;                     // block-list entries (Gaussian id, position in the tile list << 4 | quarter mask)
     unsigned long long blk_capacity;
 };
 
@@ -310,7 +311,7 @@ __device__ __forceinline__ void block_exclusive_scan(unsigned int* hist, unsigne
 // per-tile sort is a latency chain, not a bandwidth problem); KPT == 0 re-reads the keys from global memory.
 template <int THREADS, int NB, int KPT>
 __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local, unsigned long long* kb,
-                                              unsigned int* hist, unsigned int* s_warp, unsigned long long* s_red) {
+                                              unsigned int* cpre_buf, unsigned int* hist, unsigned int* s_warp, unsigned long long* s_red) {
     const int t = threadIdx.x;
     const int rl = tile_local / a.num_tiles;
     const size_t tg = size_t(a.render_base) * a.num_tiles + tile_local;      // global tile index
@@ -402,25 +403,28 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
     }
     __syncthreads();                             // the CTA's own global stores are visible to it behind the barrier
     SORT_MARK(5);
-    // 4b. gather the 48-byte records into depth order (the tile-level stream): thread = sorted position, so the id
-    //     loads and the record stores are coalesced.  Word 2 of rec0 becomes the position in the tile list (upstream's
-    //     contributor index).  The key buffer is dead after the ranking: its first 4 n bytes take the quarter masks
-    //     in sorted order.
-    unsigned int* masks = reinterpret_cast<unsigned int*>(kb);
+    // 4b. thread = sorted position: the instance's cull mask for this tile from word 0 of its Gaussian's record
+    //     (one random 16-byte load; the ids are read back coalesced).  The key buffer is dead after the ranking: it
+    //     takes the ids and the quarter masks in sorted order for the block-list emission.  SGR_FLAG_SIMPLE_BLEND
+    //     instead copies the 48-byte records into depth order (the tile-level stream of the upstream-shaped kernels;
+    //     word 2 of rec0 becomes the position in the tile list, upstream's contributor index).
+    unsigned int* ids_s = reinterpret_cast<unsigned int*>(kb);
+    unsigned int* masks = ids_s + n;
 #pragma unroll 4
     for (unsigned int p = t; p < n; p += THREADS) {
         const unsigned int id = a.sorted_ids[off + p];
         float4 v0 = __ldg(a.g0 + gb + id);
-        const float4 v1 = __ldg(a.g1 + gb + id);
-        const float4 v2 = __ldg(a.g2 + gb + id);
-        const unsigned int mask = quarter_mask(v0.x, v0.y, v0.z, X0, Y0);   // the instance's cull mask for this tile
-        if (!a.simple) masks[p] = mask;
-        // an instance whose extent touches no pixel of the tile enters no block list: its record is never read
-        if (!a.simple && mask == 0u) continue;
-        v0.z = __uint_as_float(p);
-        a.rec0[off + p] = v0;
-        a.rec1[off + p] = v1;
-        a.rec2[off + p] = v2;
+        if (a.simple) {
+            const float4 v1 = __ldg(a.g1 + gb + id);
+            const float4 v2 = __ldg(a.g2 + gb + id);
+            v0.z = __uint_as_float(p);
+            a.rec0[off + p] = v0;
+            a.rec1[off + p] = v1;
+            a.rec2[off + p] = v2;
+        } else {
+            ids_s[p] = id;
+            masks[p] = quarter_mask(v0.x, v0.y, v0.z, X0, Y0);
+        }
     }
     __syncthreads();
     SORT_MARK(6);
@@ -428,14 +432,14 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
 
     // 5. block lists.  Every instance is appended to the list of each 8x4 pixel block of the tile that its
     //    conservative alpha >= 1/255 extent touches (quarter_mask), keeping the depth order: per chunk of 32 sorted
-    //    instances (lane = record) one ballot per block, a scan of the per-chunk counts, then the copies.  The key
-    //    buffer is dead after the ranking and holds the counts.  A block-list entry is 4 bytes: (position in the tile
-    //    list << 4 | the block's 4-bit quarter mask); the blend kernels gather the records themselves from the
-    //    tile-level stream (cp.async), so the 48-byte records are written once per instance, not once per block.
-    //    Every list starts at a multiple of 4 entries (16-byte aligned: the index batches travel by 1-D TMA).
+    //    instances (lane = record) one ballot per block, a scan of the per-chunk counts, then the copies.  A block-list
+    //    entry is 8 bytes: (Gaussian id, position in the tile list << 4 | the block's 4-bit quarter mask); the blend
+    //    kernels gather the Gaussians' records themselves (cp.async) from the per-(render, Gaussian) arrays, so the
+    //    48-byte records are never copied per instance.  Every list starts at a multiple of 4 entries (the index
+    //    batches travel by 1-D TMA: 16-byte granularity).
     const size_t tgb = tg * kBlocksPerTile;
     const unsigned int nchunks = (n + 31u) >> 5;
-    unsigned int* cpre = masks + ((n + 31u) & ~31u);                       // [nchunks][8] counts -> exclusive prefixes (n more bytes of kb)
+    unsigned int* cpre = cpre_buf;                // [nchunks][8] counts -> exclusive prefixes
     const int warp = t >> 5, lane = t & 31;
     constexpr int kWarps = THREADS / 32;
     for (unsigned int c0 = warp; c0 < nchunks; c0 += 4 * kWarps) {      // four chunks in flight per warp
@@ -499,30 +503,33 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
     if (s_warp[16]) {
         const unsigned int lt = (1u << lane) - 1u;
         for (unsigned int c0 = warp; c0 < nchunks; c0 += 4 * kWarps) {      // four chunks in flight per warp
-            unsigned int mk[4];
+            unsigned int mk[4], idk[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const unsigned int p = 32u * (c0 + k * kWarps) + lane;
                 mk[k] = p < n ? masks[p] : 0u;
+                idk[k] = p < n ? ids_s[p] : 0u;
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const unsigned int c = c0 + k * kWarps;
                 if (c >= nchunks) break;
                 const unsigned int p = 32u * c + lane;
+                // lane b < 8 holds where block b's entries of this chunk start
+                const unsigned int mybase = lane < kBlocksPerTile ? s_warp[8 + lane] + cpre[c * kBlocksPerTile + lane] : 0u;
 #pragma unroll
                 for (int b = 0; b < kBlocksPerTile; ++b) {
                     const unsigned int nib = (mk[k] >> (4 * b)) & 0xfu;
                     const unsigned int bal = __ballot_sync(0xffffffffu, nib);
-                    if (nib)
-                        a.bidx[size_t(s_warp[8 + b]) + cpre[c * kBlocksPerTile + b] + __popc(bal & lt)] = (p << 4) | nib;
+                    const unsigned int base = __shfl_sync(0xffffffffu, mybase, b);
+                    if (nib) a.bidx[base + __popc(bal & lt)] = make_uint2(idk[k], (p << 4) | nib);
                 }
             }
         }
         // the pad entries (up to 3 per list) are read by the 16-byte granular index copies: quarter mask 0
         if (t < kBlocksPerTile) {
             const unsigned int cnt_b = s_warp[t];
-            for (unsigned int k = cnt_b; k < ((cnt_b + 3u) & ~3u); ++k) a.bidx[size_t(s_warp[8 + t]) + k] = 0u;
+            for (unsigned int k = cnt_b; k < ((cnt_b + 3u) & ~3u); ++k) a.bidx[size_t(s_warp[8 + t]) + k] = make_uint2(0u, 0u);
         }
     }
     __syncthreads();                             // the buffers are reused by the CTA's next tile
@@ -550,10 +557,10 @@ __global__ void __launch_bounds__(kSmallSortThreads, SGR_SORT_SMALL_MIN_CTAS) so
         const size_t tg = size_t(a.render_base) * a.num_tiles + tile_local;
         const unsigned int n = a.tile_cnt[tg];
         if (n <= 4u * kSmallSortThreads)
-            sort_one_tile<kSmallSortThreads, kSmallSortBuckets, 4>(a, tile_local, kb, hist, s_warp, s_red);
+            sort_one_tile<kSmallSortThreads, kSmallSortBuckets, 4>(a, tile_local, kb, hist, hist, s_warp, s_red);
         else
             sort_one_tile<kSmallSortThreads, kSmallSortBuckets, kSmallSortCap / kSmallSortThreads>(
-                a, tile_local, kb, hist, s_warp, s_red);
+                a, tile_local, kb, hist, hist, s_warp, s_red);
     }
     // Programmatic dependent launch (launch_sort_tiles): this grid started before sort_big_kernel finished.  The
     // blend behind it in the stream is ordered after THIS grid only, so every CTA waits here for the long-list
@@ -580,10 +587,13 @@ __global__ void __launch_bounds__(kBigSortThreads) sort_big_kernel(SortArgs a) {
         // lists that do not fit in shared memory use their segment of the second global key buffer
         const bool spill = n > a.big_smem_keys;
         unsigned long long* kb = spill ? a.keys_tmp + a.tile_off[tg] : kb_s;
+        // per-chunk block counts: the bucket histogram (dead after the ranking, 4 bytes per bucket >= 1 byte per key);
+        // a spilled list uses its own segment of the first key buffer, dead once the keys sit in kb
+        unsigned int* cpre = spill ? reinterpret_cast<unsigned int*>(a.keys_w + a.tile_off[tg]) : hist;
         if (n <= 8u * kBigSortThreads && !spill)
-            sort_one_tile<kBigSortThreads, kBigSortBuckets, 8>(a, tile_local, kb, hist, s_warp, s_red);
+            sort_one_tile<kBigSortThreads, kBigSortBuckets, 8>(a, tile_local, kb, cpre, hist, s_warp, s_red);
         else
-            sort_one_tile<kBigSortThreads, kBigSortBuckets, 0>(a, tile_local, kb, hist, s_warp, s_red);
+            sort_one_tile<kBigSortThreads, kBigSortBuckets, 0>(a, tile_local, kb, cpre, hist, s_warp, s_red);
     }
 }
 
@@ -628,7 +638,7 @@ cudaError_t launch_sort_tiles(const ChunkCtx& c) {
     a.tile_off = c.tile_off; a.tile_cnt = c.tile_cnt; a.keys = c.keys; a.sorted_ids = c.sorted_ids;
     a.rec0 = c.rec0; a.rec1 = c.rec1; a.rec2 = c.rec2; a.g0 = c.g0; a.g1 = c.g1; a.g2 = c.g2;
     a.work = c.work_blend; a.wc = c.work_counts;
-    a.keys_tmp = c.keys_tmp;
+    a.keys_tmp = c.keys_tmp; a.keys_w = c.keys;
     a.simple = (c.p->flags & SGR_FLAG_SIMPLE_BLEND) ? 1 : 0;
     a.header = c.header; a.blk_off = c.blk_off; a.blk_cnt = c.blk_cnt;
     a.bidx = c.bidx; a.blk_capacity = c.blk_capacity;

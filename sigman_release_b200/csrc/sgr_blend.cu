@@ -4,9 +4,11 @@
 // /root/reference/core/gaussians/gs.py:99-106).  Design (DESIGN.md "blend"):
 //   * the unit of work is one 8x4 pixel block of one tile of one render.  Every WARP is autonomous: it pops work items
 //     from a device-side queue ordered longest-list-first (sgr_binning.cu::plan_kernel), streams the BLOCK's
-//     depth-ordered 48-byte records (three float4 streams; the per-tile sort emits one contiguous list per block that
-//     holds only the instances whose extent touches the block) through its own shared-memory ring with 1-D TMA bulk
-//     copies (cp.async.bulk) completing on its own mbarriers, and never waits for another warp — no block-wide
+//     depth-ordered list of 8-byte entries (Gaussian id, tile-list position << 4 | quarter mask; the per-tile sort
+//     emits one contiguous list per block that holds only the instances whose extent touches the block) and gathers
+//     those Gaussians' 48-byte records (three float4 arrays written once per (render, Gaussian) by the preprocess
+//     kernel) into its own shared-memory ring with asynchronous copies (cp.async; the backward's index ring is fed
+//     by 1-D TMA bulk copies completing on its own mbarriers), and never waits for another warp — no block-wide
 //     barrier, no producer/consumer hand-off, early exit as soon as its 32 pixels are finished;
 //   * a block is four 4x2 quarters.  A batch of 128 records is culled in straight-line code (lane = record): the
 //     per-record 4-bit quarter masks built by the tile sort are read, one ballot per (round, quarter), and the
@@ -144,11 +146,10 @@ struct BwdWarpSmem {
     float4 r0[1][kBatch + 1];
     float4 r1[1][kBatch + 1];
     float4 r2[1][kBatch + 1];
-    alignas(16) unsigned int ix[kIxStages][kBatch];   // block-list entries (tile-list position << 4 | quarter mask)
+    alignas(16) uint2 ix[kIxStages][kBatch];    // block-list entries (Gaussian id, tile-list position << 4 | quarter mask)
     float stash[2][kDepth][32];
     float dpix[4][32];                          // dL/dcolor (3) and dL/ddepth of the block's pixels
     unsigned char list[4][kBatch + kListPad];
-    unsigned int hit[kBatch + 1];               // Gaussian id of record j of the batch (gathered with it)
     uint64_t ixbar[kIxStages];
 };
 
@@ -158,17 +159,17 @@ struct BwdWarpSmem {
 // batch-local indices into list[quarter][...] (ascending; descending with kReverse — the backward walks back to front);
 // unused list entries point at the sentinel record.  Returns the four survivor counts.
 template <bool kReverse, int kBatch>
-__device__ __forceinline__ uint4 cull_batch(const unsigned int (&ent)[kBatch / 32], unsigned int m,
+__device__ __forceinline__ uint4 cull_batch(const uint2 (&ent)[kBatch / 32], unsigned int m,
                                             unsigned char (*list)[kBatch + kListPad],
                                             int lane, unsigned int (&bits)[kBatch / 32]) {
     // Straight-line code (the per-batch overhead is latency, not work): all mask words are loaded first, then all
-    // ballots, then the compaction stores.  ent[r] = this lane's entry 32 * r + lane of the batch, bits[r] = its 4-bit quarter mask.
+    // ballots, then the compaction stores.  ent[r] = this lane's entry 32 * r + lane of the batch (word y = position << 4 | mask), bits[r] = its mask.
     constexpr int R = kBatch / 32;
     const unsigned int lt = kReverse ? ~((2u << lane) - 1u) : (1u << lane) - 1u;   // lanes before / after this one
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const unsigned int e = 32u * r + lane;
-        bits[r] = (e < m) ? (ent[r] & 0xfu) : 0u;
+        bits[r] = (e < m) ? (ent[r].y & 0xfu) : 0u;
     }
     {                             // every list entry the compaction does not overwrite points at the sentinel record
         constexpr unsigned int fill = kBatch * 0x01010101u;
@@ -205,10 +206,10 @@ __device__ __forceinline__ uint4 cull_batch(const unsigned int (&ent)[kBatch / 3
 // One 1-D TMA bulk copy of the batch's entries, rounded up to a multiple of 4 (lists start 16-byte aligned and are
 // padded to a multiple of 4 entries by the tile sort).
 template <typename Smem>
-__device__ __forceinline__ void ix_issue(Smem& sm, unsigned int k, const unsigned int* src, unsigned int m, int lane) {
+__device__ __forceinline__ void ix_issue(Smem& sm, unsigned int k, const uint2* src, unsigned int m, int lane) {
     if (lane == 0) {
         const int st = k % kIxStages;
-        const uint32_t bytes = ((m + 3u) & ~3u) * 4u;
+        const uint32_t bytes = ((m + 3u) & ~3u) * 8u;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the stage are done
         mbar_arrive_expect_tx(&sm.ixbar[st], bytes);
         tma_load_1d(sm.ix[st], src, bytes, &sm.ixbar[st]);
@@ -222,41 +223,47 @@ __device__ __forceinline__ void ix_wait(Smem& sm, unsigned int k) {
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Gathers the records of a batch of block-list entries from the tile's depth-ordered stream into ring stage rs
+// Gathers the records of a batch of block-list entries from the render's per-Gaussian arrays into ring stage rs
 // (lane = entry; asynchronous 16-byte copies, one commit group per batch).  Entries whose quarter mask is 0 (pads,
 // and — in the backward — records the forward found not to blend) are not fetched: the cull never selects them.
-template <bool kIds, int kRounds, typename Smem>
-__device__ __forceinline__ void gather_batch(Smem& sm, int rs, const unsigned int (&ent)[kRounds], unsigned int m,
-                                             const float4* t0, const float4* t1, const float4* t2,
-                                             const unsigned int* tids, int lane) {
+template <int kRounds, typename Smem>
+__device__ __forceinline__ void gather_batch(Smem& sm, int rs, const uint2 (&ent)[kRounds], unsigned int m,
+                                             const float4* t0, const float4* t1, const float4* t2, int lane) {
 #pragma unroll
     for (int rr = 0; rr < kRounds; ++rr) {
         const unsigned int e = 32u * rr + lane;
-        if (e < m && (ent[rr] & 0xfu)) {
-            const unsigned int p = ent[rr] >> 4;
+        if (e < m && (ent[rr].y & 0xfu)) {
+            const unsigned int p = ent[rr].x;
             cp_async16(&sm.r0[rs][e], t0 + p);
             cp_async16(&sm.r1[rs][e], t1 + p);
             cp_async16(&sm.r2[rs][e], t2 + p);
-            if (kIds) cp_async4(&sm.hit[e], tids + p);
         }
     }
     cp_async_commit();
 }
 
-// This lane's entries 32 * r + lane of a batch of m <= kBatch block-list entries (coalesced loads; 0 beyond the batch).
-template <int kRounds>
-__device__ __forceinline__ void load_entries(unsigned int (&ent)[kRounds], const unsigned int* src, unsigned int m, int lane) {
+// Once a batch's gather has landed: word 2 of rec0 (the packed extent, used by the tile sort only) is replaced by the
+// record's position in the tile list (upstream's contributor index), which the walk compares with / reports as n_contrib.
+template <int kRounds, typename Smem>
+__device__ __forceinline__ void patch_positions(Smem& sm, int rs, const uint2 (&ent)[kRounds], unsigned int m, int lane) {
 #pragma unroll
     for (int rr = 0; rr < kRounds; ++rr) {
         const unsigned int e = 32u * rr + lane;
-        ent[rr] = e < m ? __ldg(src + e) : 0u;
+        if (e < m && (ent[rr].y & 0xfu)) sm.r0[rs][e].z = __uint_as_float(ent[rr].y >> 4);
+    }
+}
+
+// This lane's entries 32 * r + lane of a batch of m <= kBatch block-list entries (coalesced loads; 0 beyond the batch).
+template <int kRounds>
+__device__ __forceinline__ void load_entries(uint2 (&ent)[kRounds], const uint2* src, unsigned int m, int lane) {
+#pragma unroll
+    for (int rr = 0; rr < kRounds; ++rr) {
+        const unsigned int e = 32u * rr + lane;
+        ent[rr] = e < m ? __ldg(src + e) : make_uint2(0u, 0u);
     }
 }
 
@@ -276,9 +283,8 @@ struct FwdArgs {
     const unsigned int* blk_off;  // [R*T*8] block lists (sgr_binning.cu step 5)
     const unsigned int* blk_cnt;
     unsigned int* blk_eff;        // out: records of the block list the backward has to replay
-    const unsigned int* tile_off; // [R*T] start of the tile's depth-ordered records
-    const float4 *rec0, *rec1, *rec2;   // tile-level records
-    unsigned int* bidx;           // block-list entries; the forward refines their quarter masks in place
+    const float4 *g0, *g1, *g2;   // [Rc*N] the chunk's per-(render, Gaussian) records
+    uint2* bidx;                  // block-list entries; the forward refines their quarter masks in place
     int refine_masks;
     const float* bg;
     unsigned int* n_contrib;
@@ -450,9 +456,9 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
         const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
         const bool inside = px < a.g.W && py < a.g.H;
         const float pxf = float(px), pyf = float(py);
-        const size_t toff = a.tile_off[tg];
-        const float4 *g0 = a.rec0 + toff, *g1 = a.rec1 + toff, *g2 = a.rec2 + toff;
-        const unsigned int* lst = a.bidx + off;
+        const size_t goff = size_t(rl) * a.g.N;
+        const float4 *g0 = a.g0 + goff, *g1 = a.g1 + goff, *g2 = a.g2 + goff;
+        const uint2* lst = a.bidx + off;
 
         float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, D = 0.0f, Wt = 0.0f;
         unsigned int last = 0;
@@ -462,23 +468,24 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
         // they point at are gathered one batch ahead (while batch b - 1 is walked), and the batch is walked once its
         // gather group has completed.
         constexpr int kR = kFwdBatch / 32;
-        unsigned int ent0[kR], ent1[kR], ent2[kR];   // entries of batch b, b + 1, b + 2
+        uint2 ent0[kR], ent1[kR], ent2[kR];          // entries of batch b, b + 1, b + 2
         load_entries(ent0, lst, min(unsigned(kFwdBatch), n), lane);
         load_entries(ent1, lst + kFwdBatch, nb > 1 ? min(unsigned(kFwdBatch), n - kFwdBatch) : 0u, lane);
-        if (nb) gather_batch<false>(sm, 0, ent0, min(unsigned(kFwdBatch), n), g0, g1, g2, nullptr, lane);
+        if (nb) gather_batch(sm, 0, ent0, min(unsigned(kFwdBatch), n), g0, g1, g2, lane);
         for (unsigned int b = 0; b < nb; ++b) {
             load_entries(ent2, lst + (b + 2) * kFwdBatch, b + 2 < nb ? min(unsigned(kFwdBatch), n - (b + 2) * kFwdBatch) : 0u, lane);
             if (b + 1 < nb) {
-                gather_batch<false>(sm, (b + 1) % kFwdStages, ent1, min(unsigned(kFwdBatch), n - (b + 1) * kFwdBatch),
-                                    g0, g1, g2, nullptr, lane);
+                gather_batch(sm, (b + 1) % kFwdStages, ent1, min(unsigned(kFwdBatch), n - (b + 1) * kFwdBatch),
+                             g0, g1, g2, lane);
                 cp_async_wait<1>();              // everything but the group just committed: batch b has landed
             } else {
                 cp_async_wait<0>();
             }
-            __syncwarp();
             const int s = b % kFwdStages;
             const unsigned int m = min(unsigned(kFwdBatch), n - b * kFwdBatch);
             const unsigned int cbase = b * kFwdBatch;
+            patch_positions(sm, s, ent0, m, lane);       // (each lane patches the records it gathered itself)
+            __syncwarp();
             const float4* r0 = sm.r0[s];
             const float4* r1 = sm.r1[s];
             const float4* r2 = sm.r2[s];
@@ -550,7 +557,7 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
 #endif
                 for (; t0 < total; t0 += 4) trip_group(t0, std::integral_constant<int, 4>{});
             }
-            // n_contrib counts positions in the TILE's list (upstream's contributor index): word 2 of rec0
+            // n_contrib counts positions in the TILE's list (upstream's contributor index): word 2 of rec0 (patched)
             if (lastj != 0xffffffffu) last = __float_as_uint(r0[lastj].z) + 1u;
             __syncwarp();
             // Mask refinement for the backward pass: clear the (block, quarter) bits of the records that no pixel of
@@ -566,7 +573,7 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
                         const unsigned int exact = ((hw[rr] & 0x01010101u) * 0x10204080u) >> 28;
                         const unsigned int clear = qbits[rr] & ~exact;      // qbits = 0 beyond the batch
                         // the block owns its records: a plain store of the refined word
-                        if (clear) a.bidx[off + cbase + e] = ent0[rr] & ~clear;
+                        if (clear) a.bidx[off + cbase + e].y = ent0[rr].y & ~clear;
                         if (hw[rr]) sm.hit[e] = 0u;
                         const unsigned int hb = __ballot_sync(kFull, exact != 0u);
                         if (hb) { seg_hits += __popc(hb); eff = cbase + 32u * rr + (32u - __clz(hb)); }
@@ -663,10 +670,8 @@ struct BwdArgs {
     const unsigned int* blk_off;
     const unsigned int* blk_cnt;
     const unsigned int* blk_eff;
-    const unsigned int* tile_off;         // [R*T] start of the tile's depth-ordered records
-    const unsigned int* sorted_ids;       // Gaussian id of every tile-level record
-    const unsigned int* bidx;             // block-list entries (quarter masks refined by the forward)
-    const float4 *rec0, *rec1, *rec2;     // tile-level records
+    const uint2* bidx;                    // block-list entries (quarter masks refined by the forward)
+    const float4 *g0, *g1, *g2;           // [Rc*N] the chunk's per-(render, Gaussian) records
     const float* bg;
     const unsigned int* n_contrib;
     const unsigned char* clamp_mask;      // NULL: the forward did not clamp
@@ -786,17 +791,16 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
         const unsigned int nb = (hi - lo + kBwdBatch - 1) / kBwdBatch;
         const float pxf = float(px), pyf = float(py);
         const float wx0 = float(bx0), wy0 = float(by0);
-        const size_t toff = a.tile_off[tg];
-        const float4 *g0 = a.rec0 + toff, *g1 = a.rec1 + toff, *g2 = a.rec2 + toff;
-        const unsigned int* lst = a.bidx + off + lo;
-        const unsigned int* tids = a.sorted_ids + toff;
+        const size_t goff = size_t(rl) * a.g.N;
+        const float4 *g0 = a.g0 + goff, *g1 = a.g1 + goff, *g2 = a.g2 + goff;
+        const uint2* lst = a.bidx + off + lo;
         float T = T_final;
         float U = 0.0f;
         // A pixel has contributors behind this segment iff its last contributor sits at or behind the first record
         // after the segment (records are in tile-list order; word 2 >> 4 = position in the tile list).
         bool resume = false;
         if (lo + unsigned(kSegB) < n) {
-            const unsigned int next_pos = __ldg(a.bidx + off + lo + kSegB) >> 4;
+            const unsigned int next_pos = __ldg(a.bidx + off + lo + kSegB).y >> 4;
             resume = last > next_pos;
         }
         if (resume) {                            // resume from the checkpoints
@@ -832,14 +836,16 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
             const unsigned int cbase = lo + (nb - 1 - b) * kBwdBatch;     // list index of the batch's first record
             const unsigned int m = min(unsigned(kBwdBatch), hi - cbase);
             ix_wait(sm, ixk0 + b); ++ix_waited;
-            unsigned int ent[kBwdBatch / 32];
+            const uint2* ixs = sm.ix[(ixk0 + b) % kIxStages];     // stays resident while the batch is walked
+            uint2 ent[kBwdBatch / 32];
 #pragma unroll
             for (int rr = 0; rr < kBwdBatch / 32; ++rr) {
                 const unsigned int e = 32u * rr + lane;
-                ent[rr] = e < m ? sm.ix[(ixk0 + b) % kIxStages][e] : 0u;
+                ent[rr] = e < m ? ixs[e] : make_uint2(0u, 0u);
             }
-            gather_batch<true>(sm, 0, ent, m, g0, g1, g2, tids, lane);
+            gather_batch(sm, 0, ent, m, g0, g1, g2, lane);
             cp_async_wait<0>();
+            patch_positions(sm, 0, ent, m, lane);
             __syncwarp();
             const float4* r0 = sm.r0[0];
             const float4* r1 = sm.r1[0];
@@ -946,7 +952,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
                             if (kDepthAlphaGrads) s9 = fmaf(w, sm.dpix[3][pl], s9);
                         }
                         if (cvalid) {
-                            float* g = acc + sm.hit[j];              // the record's Gaussian id, gathered with it
+                            float* g = acc + ixs[j].x;               // the record's Gaussian id
                             if (s0 != 0.0f) atomicAdd(g + 0 * a.plane, s0 * ddelx_dx);
                             if (s1 != 0.0f) atomicAdd(g + 1 * a.plane, s1 * ddely_dy);
                             if (s2 != 0.0f) atomicAdd(g + 2 * a.plane, -0.5f * s2);
@@ -1010,7 +1016,7 @@ cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out
                                  float* out_feed) {
     FwdArgs a;
     a.g = c.g; a.render_base = c.render_base; a.blk_off = c.blk_off; a.blk_cnt = c.blk_cnt; a.blk_eff = c.blk_eff;
-    a.tile_off = c.tile_off; a.rec0 = c.rec0; a.rec1 = c.rec1; a.rec2 = c.rec2; a.bidx = c.bidx;
+    a.g0 = c.g0; a.g1 = c.g1; a.g2 = c.g2; a.bidx = c.bidx;
     a.bg = c.p->bg; a.n_contrib = c.n_contrib;
     a.refine_masks = (c.p->flags & SGR_FLAG_FORWARD_ONLY) ? 0 : 1;
     a.tile_time = (c.p->flags & SGR_FLAG_TILE_TIMING) ? c.tile_time : nullptr;
@@ -1064,8 +1070,8 @@ cudaError_t launch_bwd_variant(const BwdArgs& a, long long want, cudaStream_t st
 cudaError_t launch_blend_backward(const ChunkCtx& c, const SgrBackwardArgs& b) {
     BwdArgs a;
     a.g = c.g; a.render_base = c.render_base; a.blk_off = c.blk_off; a.blk_cnt = c.blk_cnt; a.blk_eff = c.blk_eff;
-    a.tile_off = c.tile_off; a.sorted_ids = c.sorted_ids; a.bidx = c.bidx;
-    a.rec0 = c.rec0; a.rec1 = c.rec1; a.rec2 = c.rec2; a.bg = c.p->bg;
+    a.bidx = c.bidx;
+    a.g0 = c.g0; a.g1 = c.g1; a.g2 = c.g2; a.bg = c.p->bg;
     a.n_contrib = c.n_contrib; a.out_alpha = b.out_alpha; a.dL_dcolor = b.dL_dcolor; a.dL_ddepth = b.dL_ddepth;
     a.dL_dalpha = b.dL_dalpha; a.loss_dL_dcolor = b.loss_dL_dcolor; a.dL_dfeed = b.dL_dlpips_feed;
     a.clamp_mask = ((c.p->flags & SGR_FLAG_CLAMP_COLOR) || b.fused_clamp) ? c.clamp_mask : nullptr;

@@ -13,9 +13,11 @@ constexpr int kTilePixels = kTile * kTile;
 constexpr int kDefaultRendersPerChunk = 16;
 constexpr int kBlocksPerTile = 8;            // a 16x16 tile = eight 8x4 pixel blocks (blk = (y block) * 2 + (x block))
 // Block lists: the per-tile sort emits, for every 8x4 pixel block of a tile, the depth-ordered sub-list of the tile's
-// instances whose conservative extent touches the block, as 4-byte entries (position in the tile list << 4 | the
-// block's 4-bit quarter mask).  The blend kernels stream the entries (1-D TMA) and gather exactly those records from
-// the tile-level stream (cp.async), so a warp never fetches or culls a record that cannot touch its pixels.
+// instances whose conservative extent touches the block, as 8-byte entries (Gaussian id, position in the tile list
+// << 4 | the block's 4-bit quarter mask).  The blend kernels stream the entries and gather exactly those Gaussians'
+// 48-byte records from the per-(render, Gaussian) arrays the preprocess kernel wrote (cp.async) — a record is written
+// once per (render, Gaussian), never copied per tile or per block, and a warp never fetches or culls a record that
+// cannot touch its pixels.
 // Backward work granularity: a block list is replayed in independent segments of kSegB block records (multiple of the
 // blend kernels' batch).  The forward blend checkpoints every pixel's running state at the segment boundaries of
 // lists longer than one segment; slot (block list, s) = blk_off / (kSegB / 2) + s, s < #segments, the last slot
@@ -50,12 +52,12 @@ struct ChunkPlan {
 
 // Layout of `state` (kept forward -> backward) for a problem shape.
 struct StateLayout {
-    uint64_t header, tile_off, tile_cnt, tile_time, n_contrib, clamp_mask, sorted_ids, rec0, rec1, rec2, blk_off, blk_cnt,
-        blk_eff, bidx, ck0, ck1, plan, bwd_items, bwd_items_stride, total;
+    uint64_t header, tile_off, tile_cnt, tile_time, n_contrib, clamp_mask, sorted_ids, g0, g1, g2, rec0, rec1, rec2, blk_off,
+        blk_cnt, blk_eff, bidx, ck0, ck1, plan, bwd_items, bwd_items_stride, total;
 };
 // Layout of `scratch` (valid only inside one call).
 struct ScratchLayout {
-    uint64_t keys, keys_tmp, g0, g1, g2, rect, cursor, work_blend, work_empty, work_counts, loss_part, accum, total;
+    uint64_t keys, keys_tmp, rect, cursor, work_blend, work_empty, work_counts, loss_part, accum, total;
 };
 
 __host__ __device__ inline uint64_t align_up(uint64_t x, uint64_t a = 256) { return (x + a - 1) / a * a; }
@@ -64,12 +66,11 @@ inline int tiles_x(int W) { return (W + kTile - 1) / kTile; }
 inline int tiles_y(int H) { return (H + kTile - 1) / kTile; }
 inline uint64_t ckpt_slots(uint64_t capB) { return capB / (kSegB / 2) + 2; }
 
-// `simple`: SGR_FLAG_SIMPLE_BLEND keeps tile-level records (the upstream-shaped kernels walk whole tile lists) and no
-// block lists; the default path keeps block lists and no tile-level records.
+// `simple`: SGR_FLAG_SIMPLE_BLEND keeps tile-level copies of the records (the upstream-shaped kernels walk whole tile
+// lists) and no block lists; the default path keeps block lists and no tile-level records.
 inline StateLayout make_state_layout(int B, int V, int N, int H, int W, uint64_t cap, uint64_t capB, bool simple) {
-    (void)N;
     const uint64_t R = uint64_t(B) * V, T = uint64_t(tiles_x(W)) * tiles_y(H), P = uint64_t(H) * W;
-    const uint64_t rec_cap = cap, blk_cap = simple ? 0 : capB;
+    const uint64_t rec_cap = simple ? cap : 0, blk_cap = simple ? 0 : capB;
     StateLayout L;
     uint64_t o = 0;
     L.header = o;      o = align_up(o + sizeof(StateHeader));
@@ -79,13 +80,16 @@ inline StateLayout make_state_layout(int B, int V, int N, int H, int W, uint64_t
     L.n_contrib = o;   o = align_up(o + R * P * 4);
     L.clamp_mask = o;  o = align_up(o + R * P);         // bit c: channel c of the pixel was clamped (SGR_FLAG_CLAMP_COLOR)
     L.sorted_ids = o;  o = align_up(o + cap * 4);
+    L.g0 = o;          o = align_up(o + R * N * 16);    // per-(render, Gaussian) records written by the preprocess kernel:
+    L.g1 = o;          o = align_up(o + R * N * 16);    // (x, y, extent, power threshold), (-A/2, -B, -C/2, opacity),
+    L.g2 = o;          o = align_up(o + R * N * 16);    // (r, g, b, depth)
     L.rec0 = o;        o = align_up(o + rec_cap * 16);
     L.rec1 = o;        o = align_up(o + rec_cap * 16);
     L.rec2 = o;        o = align_up(o + rec_cap * 16);
     L.blk_off = o;     o = align_up(o + R * T * kBlocksPerTile * 4);
     L.blk_cnt = o;     o = align_up(o + R * T * kBlocksPerTile * 4);
     L.blk_eff = o;     o = align_up(o + R * T * kBlocksPerTile * 4);
-    L.bidx = o;        o = align_up(o + blk_cap * 4);
+    L.bidx = o;        o = align_up(o + blk_cap * 8);
     L.ck0 = o;         o = align_up(o + ckpt_slots(blk_cap) * kCkptPerSlot * 16);   // (T, C0, C1, C2) per pixel and slot
     L.ck1 = o;         o = align_up(o + ckpt_slots(blk_cap) * kCkptPerSlot * 4);    // D
     L.plan = o;        o = align_up(o + R * sizeof(ChunkPlan));                     // one per chunk (at most R chunks)
@@ -105,9 +109,6 @@ inline ScratchLayout make_scratch_layout(int B, int V, int N, int H, int W, uint
     uint64_t o = 0;
     L.keys = o;        o = align_up(o + cap * 8);
     L.keys_tmp = o;    o = align_up(o + cap * 8);
-    L.g0 = o;          o = align_up(o + Rc * N * 16);
-    L.g1 = o;          o = align_up(o + Rc * N * 16);
-    L.g2 = o;          o = align_up(o + Rc * N * 16);
     L.rect = o;        o = align_up(o + Rc * N * 8);
     L.cursor = o;      o = align_up(o + Rc * T * 4);
     L.work_blend = o;  o = align_up(o + Rc * T * 4);
@@ -136,7 +137,8 @@ constexpr int kSmallSortThreads = 256;
 constexpr int kSmallSortBuckets = 1024;
 constexpr int kBigSortThreads = 1024;
 constexpr int kBigSortBuckets = 4096;
-constexpr int kBigSortSmemCap = 26 * 1024;  // instances whose keys fit in shared memory next to the histogram
+constexpr int kBigSortSmemCap = 16 * 1024;  // instances whose keys fit in shared memory next to the histogram (<= 4 * kBigSortBuckets:
+                                            // the dead histogram later holds one byte per key of block counts)
 constexpr size_t kSmallSortSmem = size_t(kSmallSortCap) * 8 + size_t(kSmallSortBuckets) * 4;    // keys, histogram
 
 // ------------------------------------------------------------------------------------------------
@@ -251,10 +253,11 @@ struct ChunkCtx {
     uint2* tile_time;         // [R*T]
     unsigned int* n_contrib;  // [R*P]
     unsigned int* sorted_ids; // [cap]
-    float4 *rec0, *rec1, *rec2;   // [cap] tile-level records in depth order
+    float4 *g0, *g1, *g2;     // [Rc*N] this chunk's slice of the per-(render, Gaussian) records
+    float4 *rec0, *rec1, *rec2;   // [cap] tile-level copies in depth order (SGR_FLAG_SIMPLE_BLEND only)
     unsigned char* clamp_mask; // [R*P]
     unsigned int *blk_off, *blk_cnt, *blk_eff;   // [R*T*8] block lists: start, records, records the backward replays
-    unsigned int* bidx;                          // [capB] block-list entries (tile-list position << 4 | quarter mask)
+    uint2* bidx;                                 // [capB] block-list entries (Gaussian id, tile-list position << 4 | quarter mask)
     unsigned long long blk_capacity;
     float4* ck0;              // [ckpt_slots][32] forward checkpoints (T, C0, C1, C2)
     float* ck1;               // [ckpt_slots][32] forward checkpoints D
@@ -265,7 +268,6 @@ struct ChunkCtx {
     // scratch
     unsigned long long* keys; // [cap]
     unsigned long long* keys_tmp; // [cap] bucket-ordered keys of tile lists that exceed the sort's shared memory
-    float4 *g0, *g1, *g2;     // [Rc*N]
     uint2* rect;              // [Rc*N] packed tile rectangle
     unsigned int* cursor;     // [Rc*T]
     unsigned int *work_blend, *work_empty;
