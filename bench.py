@@ -414,7 +414,7 @@ def run_ours(args):
         res = {}
         with torch.no_grad():
             for name, wire in (("exact_fp32", orbit_mod.WIRE_EXACT), ("compact_u8_f16", orbit_mod.WIRE_COMPACT)):
-                ms = timed(lambda: orbit_mod.render_orbit_overlapped(fn, 90, H, W, dev, wire=wire, chunk=4), 5, 2)
+                ms = timed(lambda: orbit_mod.render_orbit_overlapped(fn, 90, H, W, dev, wire=wire), 5, 2)
                 per_px = sum(torch.empty((), dtype=dt).element_size() * ch for dt, ch in zip(wire, (3, 1, 1)))
                 per = (90 + world - 1) // world
                 gathered = world * per * per_px * H * W              # bytes every rank receives

@@ -90,7 +90,7 @@ def render_orbit_overlapped(render_planes: Callable, num_views: int, height: int
     ``out`` (a tuple of three contiguous float32 tensors of those shapes, or None) is where it should write — they
     are slices of this rank's gather buffer, so with the exact wire format nothing is copied (no ``torch.cat``).
     Views are sharded contiguously; every rank renders its shard in chunks of ``chunk`` views (0 = a third of the
-    shard, at least 4), and while chunk k + 1 renders on the current stream, chunk k is all-gathered (as bytes, one
+    shard, at least 6: below that a chunk's launch sequence costs the host more than the GPU needs to render it), and while chunk k + 1 renders on the current stream, chunk k is all-gathered (as bytes, one
     collective per chunk) and unpacked into the view-ordered result on a side stream — packing and unpacking are one
     kernel each of the CUDA library (``sgr_wire_pack`` / ``sgr_wire_unpack``).  Returns ``[num_views, 5, H, W]``
     float32 (RGB, depth, alpha) on every rank; with ``wire=WIRE_EXACT`` it is bitwise equal to a single-process
@@ -110,7 +110,7 @@ def render_orbit_overlapped(render_planes: Callable, num_views: int, height: int
     sizes = [torch.empty((), dtype=dt).element_size() for dt in wire]
     on_cuda = device.type == "cuda"
     if chunk <= 0:
-        chunk = max(4, (per + 2) // 3)
+        chunk = max(6, (per + 2) // 3)
     if on_cuda:
         import ctypes
 
@@ -190,8 +190,12 @@ def rasterizer_planes(means3D, cov3D, colors, opacities, bg, height, width, tanf
     from .rasterizer import rasterize_batch
 
     def render(view_ids, out):
-        idx = torch.as_tensor(list(view_ids), device=means3D.device)
-        vm, pm = view_matrices[idx][None], proj_matrices[idx][None]
+        ids = list(view_ids)
+        if ids == list(range(ids[0], ids[0] + len(ids))):      # a contiguous run: plain slices, no index upload
+            vm, pm = view_matrices[ids[0]:ids[0] + len(ids)][None], proj_matrices[ids[0]:ids[0] + len(ids)][None]
+        else:                                                  # (padded tail of the last shard)
+            idx = torch.as_tensor(ids, device=means3D.device)
+            vm, pm = view_matrices[idx][None], proj_matrices[idx][None]
         o = None if out is None else tuple(t.unsqueeze(0) for t in out)
         c, _r, d, a = rasterize_batch(means3D, cov3D, colors, opacities, vm, pm, bg, height, width, tanfov, tanfov,
                                       clamp_color=True, out=o)

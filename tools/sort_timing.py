@@ -39,6 +39,6 @@ for thr in (1024, 256):
         r = sel[i]
         d = [(r[k + 1] - r[k]) / 1e3 for k in range(9)]
         print(f"  n={r[10]:6d} start={(r[0] - t0) / 1e3:7.1f} total={(r[9] - r[0]) / 1e3:7.1f} us | " +
-              " ".join(f"{nm}={x:.1f}" for nm, x in zip(["load+minmax", "hist", "scan", "scatter", "rank", "gather", "blkcount", "blkscan", "blkemit"], d)))
+              " ".join(f"{nm}={x:.1f}" for nm, x in zip(["load+minmax", "hist", "scan", "scatter", "rank", "mask+count", "-", "blkscan", "blkemit"], d)))
     tot = [(sel[:, k + 1] - sel[:, k]).sum() / 1e3 for k in range(9)]
     print("  sum over tiles (us):", " ".join(f"{x:.0f}" for x in tot))
