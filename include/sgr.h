@@ -19,6 +19,9 @@
  *    upstream rasterizer call).  Render index r = b * V + v.
  *  - return value: 0 on success, negative SgrError otherwise; sgr_last_error() gives the message
  *    (thread-local).  The library never calls abort()/exit().
+ *  - threading: one host thread drives the library per process (one process per GPU, like the reference under
+ *    accelerate).  The error string is thread-local, but the profiling accumulators (sgr_profile_*), the launch
+ *    counter and the per-device launch caches are unsynchronised process globals.
  */
 #ifndef SGR_H_
 #define SGR_H_

@@ -60,16 +60,20 @@ def test_buffer_size_queries(lib):
     b = lib.sgr_state_bytes(1, 8, 100_000, 512, 512, 2_000_000, 6_000_000, 0)
     c = lib.sgr_state_bytes(1, 8, 100_000, 512, 512, 4_000_000, 6_000_000, 0)
     assert 0 < a < b < c and a % 256 == 0
-    # per block-list entry: 4 bytes; per 128 entries one checkpoint slot of 32 pixels x 20 B; per 256 entries one 8-byte
-    # backward work item in each of the 4 classes (regions 256-byte aligned)
-    growth = 3_000_000 * 4 + (6_000_000 // 128 - 3_000_000 // 128) * 32 * 20 + (6_000_000 // 256 - 3_000_000 // 256) * 8 * 4
+    # per block-list entry: 8 bytes (Gaussian id, tile-list position << 4 | quarter mask); per 128 entries one checkpoint
+    # slot of 32 pixels x 20 B; per 256 entries one 8-byte backward work item in each of the 4 classes (regions 256-byte
+    # aligned)
+    growth = 3_000_000 * 8 + (6_000_000 // 128 - 3_000_000 // 128) * 32 * 20 + (6_000_000 // 256 - 3_000_000 // 256) * 8 * 4
     assert abs((b - a) - growth) <= 8 * 256
-    # per instance: the 4-byte id of the tile-level point list + the 48-byte depth-ordered record
-    assert abs((c - b) - 2_000_000 * 52) <= 4 * 256
-    # SGR_FLAG_SIMPLE_BLEND keeps no block lists
+    # per instance: the 4-byte id of the tile-level point list (the 48-byte records are kept once per (render, Gaussian))
+    assert abs((c - b) - 2_000_000 * 4) <= 4 * 256
+    f = lib.sgr_state_bytes(1, 8, 200_000, 512, 512, 4_000_000, 6_000_000, 0)
+    assert abs((f - c) - 8 * 100_000 * 48) <= 4 * 256
+    # SGR_FLAG_SIMPLE_BLEND keeps no block lists, but a depth-ordered 48-byte copy of the record per instance
     d = lib.sgr_state_bytes(1, 8, 100_000, 512, 512, 2_000_000, 3_000_000, _native.FLAG_SIMPLE_BLEND)
     e = lib.sgr_state_bytes(1, 8, 100_000, 512, 512, 2_000_000, 6_000_000, _native.FLAG_SIMPLE_BLEND)
-    assert d == e < a
+    g = lib.sgr_state_bytes(1, 8, 100_000, 512, 512, 4_000_000, 6_000_000, _native.FLAG_SIMPLE_BLEND)
+    assert d == e and abs((g - e) - 2_000_000 * 52) <= 4 * 256
     assert lib.sgr_state_bytes(0, 8, 10, 64, 64, 10, 10, 0) == 0
     s16 = lib.sgr_scratch_bytes(8, 10, 100_000, 512, 512, 20_000_000, 16)
     s80 = lib.sgr_scratch_bytes(8, 10, 100_000, 512, 512, 20_000_000, 80)
