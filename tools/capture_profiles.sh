@@ -13,6 +13,9 @@ ncu --set full --clock-control none --import-source on -k regex:blend_ -s 4 -c 2
     python tools/prof_fwd.py bwd > $OUT/ncu_blend.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"preprocess|plan_kernel|scatter|sort_" -s 12 -c 6 -o $OUT/small \
     python tools/prof_fwd.py bwd > $OUT/ncu_small.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"knn_|prep_cov3d" -s 22 -c 11 -o $OUT/prep \
+    python tools/prof_prep.py > $OUT/ncu_prep.log 2>&1
+ncu -i $OUT/prep.ncu-rep --page details > $OUT/prep_details.txt 2>/dev/null
 ncu -i $OUT/blend.ncu-rep --page details > $OUT/blend_details.txt 2>/dev/null
 ncu -i $OUT/small.ncu-rep --page details > $OUT/small_details.txt 2>/dev/null
 ncu -i $OUT/blend.ncu-rep --page raw --csv > $OUT/blend_raw.csv 2>/dev/null

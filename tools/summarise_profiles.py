@@ -12,7 +12,7 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
 src = os.path.join(ROOT, "gpurun_out", "prof")
 dst = os.path.join(ROOT, "profiles")
 for a, b in (("bench.json", "bench.json"), ("bench_reference.json", "bench_reference.json"), ("launches.csv", "launches.csv"),
-             ("blend_details.txt", "blend_details.txt"), ("small_details.txt", "small_details.txt"),
+             ("blend_details.txt", "blend_details.txt"), ("small_details.txt", "small_details.txt"), ("prep_details.txt", "prep_details.txt"),
              ("blend_raw.csv", "blend_raw.csv")):
     if os.path.exists(os.path.join(src, a)):
         shutil.copy(os.path.join(src, a), os.path.join(dst, f"{tag}_{b}"))
