@@ -133,6 +133,7 @@ void fill_ctx(ChunkCtx& c, const SgrProblem& p, void* state, void* scratch, cuda
     c.work_blend = reinterpret_cast<unsigned int*>(x + X.work_blend);
     c.work_empty = reinterpret_cast<unsigned int*>(x + X.work_empty);
     c.work_counts = reinterpret_cast<WorkCounts*>(x + X.work_counts);
+    c.dense_items = reinterpret_cast<unsigned int*>(x + X.dense_items);
     c.loss_part = reinterpret_cast<float*>(x + X.loss_part);
     c.accum = reinterpret_cast<float*>(x + X.accum);
     c.loss_target = nullptr; c.loss_mask = nullptr; c.loss_dL_dcolor = nullptr; c.loss_scale = 0.0f;

@@ -136,6 +136,8 @@ __global__ void __launch_bounds__(kScanThreads) plan_kernel(PlanArgs a) {
         a.wc->n_empty = fits ? static_cast<unsigned int>(tot & 0xffffffull) : unsigned(a.n);
         a.wc->blend_cursor = 0;
         a.wc->empty_cursor = 0;
+        a.wc->n_dense = 0;
+        a.wc->dense_cursor = 0;
         // the block-record cursor is final for all earlier chunks here (their sorts precede this kernel in the stream)
 #pragma unroll
         for (int c = 0; c < kBwdClasses; ++c) a.plan->n_items[c] = 0;
@@ -228,6 +230,7 @@ struct SortArgs {
     unsigned int *blk_off, *blk_cnt;
     uint2* bidx;                     // block-list entries (Gaussian id, position in the tile list << 4 | quarter mask)
     unsigned long long blk_capacity;
+    unsigned int* dense_items;       // block items of the dense lists (sgr_common.cuh::kDenseEntries)
 };
 
 // Experiment build (-DSGR_SORT_TIMING, tools/sort_timing.py): per-tile phase timestamps of the tile sorts.
@@ -499,6 +502,8 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
         s_warp[16] = fits ? 1u : 0u;
     }
     __syncthreads();
+    if (t < kBlocksPerTile && s_warp[16] && s_warp[t] >= kDenseEntries)      // a dense list: queued separately
+        a.dense_items[atomicAdd(&a.wc->n_dense, 1u)] = unsigned(tile_local) * kBlocksPerTile + t;
     SORT_MARK(8);
     if (s_warp[16]) {
         const unsigned int lt = (1u << lane) - 1u;
@@ -641,7 +646,7 @@ cudaError_t launch_sort_tiles(const ChunkCtx& c) {
     a.keys_tmp = c.keys_tmp; a.keys_w = c.keys;
     a.simple = (c.p->flags & SGR_FLAG_SIMPLE_BLEND) ? 1 : 0;
     a.header = c.header; a.blk_off = c.blk_off; a.blk_cnt = c.blk_cnt;
-    a.bidx = c.bidx; a.blk_capacity = c.blk_capacity;
+    a.bidx = c.bidx; a.blk_capacity = c.blk_capacity; a.dense_items = c.dense_items;
     const int dslot = current_device_slot();
     static int num_sms_dev[kMaxDevices] = {};
     static bool attr_set_dev[kMaxDevices] = {};

@@ -59,18 +59,10 @@ constexpr int kFwdStages = SGR_FWD_STAGES;     // per-warp TMA ring depth, forwa
 constexpr int kBwdStages = SGR_BWD_STAGES;     // backward: one 128-record stage (the stash takes the rest of the budget)
 constexpr int kWarpsPerCta = 8;                // backward: two CTAs of 8 warps per SM
 constexpr int kBlendThreads = kWarpsPerCta * 32;
-// forward: ONE CTA of 16 warps per SM, so that the warps that share an SM sub-partition (warp % 4) can see each
-// other in shared memory: a warp that walks a dense block list gets its scheduler to itself (see "parking" below)
+// forward: ONE CTA of 16 warps per SM: the CTAs that take the dense block lists (sgr_common.cuh::kDenseEntries) keep
+// their other warps asleep meanwhile, so that a dense walk has a scheduler (almost) to itself
 constexpr int kFwdWarps = 16;
 constexpr int kFwdThreads = kFwdWarps * 32;
-#ifndef SGR_FWD_DENSE
-#define SGR_FWD_DENSE 640
-#endif
-#ifndef SGR_FWD_PARK
-#define SGR_FWD_PARK 0
-#endif
-constexpr unsigned int kDenseRecords = SGR_FWD_DENSE;   // block lists at least this long are "dense"
-constexpr int kParkLimit = SGR_FWD_PARK;                // scheduler mates that may park beside a dense warp (0 = off)
 constexpr int kBlockW = 8, kBlockH = 4;        // pixel block of one warp (four 4x2 quarters walk separate lists)
 #ifndef SGR_BWD_SLOTS
 #define SGR_BWD_SLOTS 16
@@ -298,6 +290,7 @@ struct FwdArgs {
     uint2* bwd_items;
     unsigned long long bwd_items_stride;
     const unsigned int *work_blend, *work_empty;
+    const unsigned int* dense_items;   // block items of the dense lists (queued by the tile sort)
     WorkCounts* wc;
     int clamp_color;
     // optional fused loss (include/sgr.h SgrForwardArgs::loss_*)
@@ -375,6 +368,12 @@ __device__ __forceinline__ void write_pixel(const FwdArgs& a, int r, size_t P, i
 }
 
 using FwdSmem = FwdWarpSmem<kFwdStages, kFwdBatch>;
+
+// Experiment build (-DSGR_FWD_TRACE, tools/fwd_trace.py): per work item of the forward blend (begin, end, entries, SM).
+#ifdef SGR_FWD_TRACE
+constexpr unsigned int kFwdTraceCap = 1u << 17;
+__device__ unsigned long long g_fwd_trace[kFwdTraceCap][4];
+#endif
 using BwdSmem = BwdWarpSmem<kBwdSlots, kBwdBatch>;
 
 #ifndef SGR_FWD_GROUP8
@@ -389,16 +388,13 @@ using BwdSmem = BwdWarpSmem<kBwdSlots, kBwdBatch>;
 template <bool kExact>
 __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_kernel(FwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // Parking: the launch is bounded by the walk of the densest block lists, and a warp that shares its scheduler
-    // with three others issues at a quarter of its possible rate.  Warps of one SM sub-partition (warp % 4) therefore
-    // keep a count of the dense lists being walked on it; a mate that finishes its item while the count is non-zero
-    // does not pop new work but sleeps (at most kParkLimit of them) until the dense walk is over.  Nothing depends on
-    // which warps share a scheduler: a wrong guess only parks the wrong warps.
-    __shared__ int s_dense[4], s_parked[4];
+    __shared__ int s_dense_busy;                  // warps of this CTA that still walk dense lists
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x < 4) { s_dense[threadIdx.x] = 0; s_parked[threadIdx.x] = 0; }
+    const unsigned int n_dense = a.wc->n_dense;
+    const bool dense_cta = blockIdx.x * unsigned(kDenseWarps) < n_dense;
+    bool dense_mode = dense_cta && warp < kDenseWarps;
+    if (threadIdx.x == 0) s_dense_busy = dense_cta ? kDenseWarps : 0;
     __syncthreads();
-    const int part = warp & 3;
     FwdSmem& sm = reinterpret_cast<FwdSmem*>(smem_raw)[warp];
     const size_t P = size_t(a.g.H) * a.g.W;
     const float bg0 = a.bg[0], bg1 = a.bg[1], bg2 = a.bg[2];
@@ -417,28 +413,103 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
     }
     __syncwarp();
 
+    // ---------------- tiles without instances: background only.  Whole tiles are popped; the fused loss's loads of
+    // four blocks are issued together (the phase is a chain of memory latencies, not work).  Called by every warp
+    // after the main queue, and before it by the warps that would otherwise sleep beside a dense walk.
+    auto empty_tiles = [&]() {
+        for (;;) {
+            unsigned int w = 0;
+            if (lane == 0) w = atomicAdd(&a.wc->empty_cursor, 1u);
+            w = __shfl_sync(kFull, w, 0);
+            if (w * kBlocksPerTile >= n_empty_items) break;
+            const unsigned int tile_local = a.work_empty[w];
+            const int rl = tile_local / a.g.num_tiles;
+            const int tile = tile_local - rl * a.g.num_tiles;
+            const int r = a.render_base + rl;
+            const int tx = tile % a.g.tiles_x, ty = tile / a.g.tiles_x;
+            const size_t rP = size_t(r) * P;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float tg[4][3], mk[4];
+                int pxs[4], pys[4];
+                bool in[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int blk = half * 4 + k;
+                    pxs[k] = tx * kTile + (blk & 1) * kBlockW + (lane & 7);
+                    pys[k] = ty * kTile + (blk >> 1) * kBlockH + (lane >> 3);
+                    in[k] = pxs[k] < a.g.W && pys[k] < a.g.H;
+                    if (a.loss_target && in[k]) {
+                        const size_t pix = size_t(pys[k]) * a.g.W + pxs[k];
+                        mk[k] = a.loss_mask ? a.loss_mask[rP + pix] : 1.0f;
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) tg[k][ch] = a.loss_target[3 * rP + ch * P + pix];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int blk = half * 4 + k;
+                    if (a.loss_target) {
+                        float part = 0.0f;
+                        if (in[k]) {
+                            const size_t pix = size_t(pys[k]) * a.g.W + pxs[k];
+                            const float gs = mk[k] * a.loss_scale;
+                            const float cs[3] = {bg0, bg1, bg2};
+#pragma unroll
+                            for (int ch = 0; ch < 3; ++ch) {    // loss_pixel() on the background colour
+                                const float c = cs[ch];
+                                const float cl = fminf(fmaxf(c, 0.0f), 1.0f);
+                                const float diff = cl * mk[k] - tg[k][ch] * mk[k];
+                                part += fabsf(diff);
+                                const bool pass = c >= 0.0f && c <= 1.0f;
+                                a.loss_dL_dcolor[3 * rP + ch * P + pix] = pass ? (diff > 0.0f ? gs : diff < 0.0f ? -gs : 0.0f) : 0.0f;
+                            }
+                        }
+                        part = warp_sum(part);
+                        if (lane == 0) a.loss_part[size_t(tile_local) * kBlocksPerTile + blk] = part;
+                    }
+                    write_pixel(a, r, P, pxs[k], pys[k], in[k], lane, bg0, bg1, bg2, 0.0f, 0.0f, 0u);
+                }
+            }
+        }
+    };
+
     // ---------------- blocks of tiles with instances
     for (;;) {
-        if (kParkLimit > 0) {                     // a dense walk is in progress on this sub-partition: stay out of its way
-            int go = 1;
-            if (lane == 0 && *reinterpret_cast<volatile int*>(&s_dense[part]) > 0) {
-                if (atomicAdd(&s_parked[part], 1) < kParkLimit)
-                    while (*reinterpret_cast<volatile int*>(&s_dense[part]) > 0) __nanosleep(200);
-                atomicSub(&s_parked[part], 1);
+        unsigned int bitem;                       // chunk-local tile * 8 + block
+        if (dense_mode) {
+            const unsigned int d = pop_item(&a.wc->dense_cursor, n_dense, lane);
+            if (d == 0xffffffffu) {               // no dense list left: wake the CTA's other warps, join the main queue
+                dense_mode = false;
+                if (lane == 0) atomicSub(&s_dense_busy, 1);
+                continue;
             }
-            go = __shfl_sync(kFull, go, 0);
-            (void)go;
+            bitem = a.dense_items[d];
+        } else {
+            int wait = 0;                         // (warp-uniform: read by one lane)
+            if (dense_cta && warp >= kDenseWarps)
+                wait = __shfl_sync(kFull, *reinterpret_cast<volatile int*>(&s_dense_busy), 0);
+            if (wait > 0) {
+                // this CTA's schedulers belong to its dense walks for now: background tiles (memory latency, hardly any
+                // instructions) are the only work taken meanwhile
+                empty_tiles();
+                if (lane == 0)
+                    while (*reinterpret_cast<volatile int*>(&s_dense_busy) > 0) __nanosleep(1000);
+                __syncwarp();
+            }
+            const unsigned int item = pop_item(&a.wc->blend_cursor, n_items, lane);
+            if (item == 0xffffffffu) break;
+            bitem = a.work_blend[item / kBlocksPerTile] * kBlocksPerTile + item % kBlocksPerTile;
         }
-        const unsigned int item = pop_item(&a.wc->blend_cursor, n_items, lane);
-        if (item == 0xffffffffu) break;
-        const unsigned int tile_local = a.work_blend[item / kBlocksPerTile];
-        const int blk = item % kBlocksPerTile;
+        const unsigned int tile_local = bitem / kBlocksPerTile;
+        const int blk = bitem % kBlocksPerTile;
         const int rl = tile_local / a.g.num_tiles;
         const int tile = tile_local - rl * a.g.num_tiles;
         const int r = a.render_base + rl;
         const size_t tg = size_t(r) * a.g.num_tiles + tile;
         const size_t bi = tg * kBlocksPerTile + blk;
         const unsigned int n = a.blk_cnt[bi];                       // records of this block's list
+        if (!dense_mode && n >= kDenseEntries) continue;            // queued as a dense list (same test as the tile sort)
         const size_t off = a.blk_off[bi];
         const unsigned int nb = (n + kFwdBatch - 1) / kFwdBatch;
         const int tx = tile % a.g.tiles_x, ty = tile / a.g.tiles_x;
@@ -450,8 +521,6 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
             }
             continue;
         }
-        const bool dense = kParkLimit > 0 && n >= kDenseRecords;
-        if (dense && lane == 0) atomicAdd(&s_dense[part], 1);
         const unsigned long long t_begin = global_timer_ns();
         const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
         const bool inside = px < a.g.W && py < a.g.H;
@@ -459,6 +528,14 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
         const size_t goff = size_t(rl) * a.g.N;
         const float4 *g0 = a.g0 + goff, *g1 = a.g1 + goff, *g2 = a.g2 + goff;
         const uint2* lst = a.bidx + off;
+        if (a.loss_target && inside) {          // the fused loss reads its target at the END of the item: fetch it to L2 now
+            const size_t pix = size_t(py) * a.g.W + px;
+            const float* tgp = a.loss_target + 3 * size_t(r) * P + pix;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(tgp));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(tgp + P));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(tgp + 2 * P));
+            if (a.loss_mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.loss_mask + size_t(r) * P + pix));
+        }
 
         float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, D = 0.0f, Wt = 0.0f;
         unsigned int last = 0;
@@ -627,7 +704,14 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
         }
         if (!kExact) Wt = 1.0f - T;                  // sum of the blend weights up to rounding (the oracle sums them)
         write_pixel(a, r, P, px, py, inside, lane, C0 + T * bg0, C1 + T * bg1, C2 + T * bg2, D, Wt, last);
-        if (dense && lane == 0) atomicSub(&s_dense[part], 1);
+#ifdef SGR_FWD_TRACE
+        if (lane == 0 && bitem < kFwdTraceCap) {
+            unsigned int smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            g_fwd_trace[bitem][0] = t_begin; g_fwd_trace[bitem][1] = global_timer_ns();
+            g_fwd_trace[bitem][2] = n; g_fwd_trace[bitem][3] = (smid << 8) | unsigned(warp);
+        }
+#endif
         if (a.tile_time && lane == 0) {          // diagnostics: start of block 0, duration of the slowest block
             const unsigned long long now = global_timer_ns();
             if (blk == 0) a.tile_time[tg].x = (unsigned int)t_begin;
@@ -635,32 +719,7 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
         }
     }
 
-    // ---------------- blocks of tiles without instances: background only
-    // whole tiles are popped (8 uniform items per global atomic round trip)
-    for (unsigned int item = 0xffffffffu;;) {
-        if (item == 0xffffffffu || (item % kBlocksPerTile) == kBlocksPerTile - 1) {
-            unsigned int w = 0;
-            if (lane == 0) w = atomicAdd(&a.wc->empty_cursor, unsigned(kBlocksPerTile));
-            item = __shfl_sync(kFull, w, 0);
-        } else {
-            ++item;
-        }
-        if (item >= n_empty_items) break;
-        const unsigned int tile_local = a.work_empty[item / kBlocksPerTile];
-        const int blk = item % kBlocksPerTile;
-        const int rl = tile_local / a.g.num_tiles;
-        const int tile = tile_local - rl * a.g.num_tiles;
-        const int r = a.render_base + rl;
-        const int tx = tile % a.g.tiles_x, ty = tile / a.g.tiles_x;
-        const int px = tx * kTile + (blk & 1) * kBlockW + (lane & 7), py = ty * kTile + (blk >> 1) * kBlockH + (lane >> 3);
-        if (a.loss_target) {
-            float part = 0.0f;
-            if (px < a.g.W && py < a.g.H) part = loss_pixel(a, size_t(r) * P, P, size_t(py) * a.g.W + px, bg0, bg1, bg2);
-            part = warp_sum(part);
-            if (lane == 0) a.loss_part[size_t(tile_local) * kBlocksPerTile + blk] = part;
-        }
-        write_pixel(a, r, P, px, py, px < a.g.W && py < a.g.H, lane, bg0, bg1, bg2, 0.0f, 0.0f, 0u);
-    }
+    empty_tiles();
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -1023,7 +1082,7 @@ cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out
     a.out_color = out_color; a.out_depth = out_depth; a.out_alpha = out_alpha; a.out_feed = out_feed;
     a.clamp_mask = c.clamp_mask;
     a.ck0 = c.ck0; a.ck1 = c.ck1; a.plan = c.plan; a.bwd_items = c.bwd_items; a.bwd_items_stride = c.bwd_items_stride;
-    a.work_blend = c.work_blend; a.work_empty = c.work_empty; a.wc = c.work_counts;
+    a.work_blend = c.work_blend; a.work_empty = c.work_empty; a.wc = c.work_counts; a.dense_items = c.dense_items;
     a.clamp_color = ((c.p->flags & SGR_FLAG_CLAMP_COLOR) || c.loss_target) ? 1 : 0;
     a.loss_target = c.loss_target; a.loss_mask = c.loss_mask; a.loss_dL_dcolor = c.loss_dL_dcolor;
     a.loss_part = c.loss_part; a.loss_scale = c.loss_scale;
@@ -1045,6 +1104,14 @@ cudaError_t launch_blend_forward(const ChunkCtx& c, float* out_color, float* out
     else blend_forward_kernel<false><<<grid, kFwdThreads, smem, c.stream>>>(a);
     return cudaGetLastError();
 }
+
+#ifdef SGR_FWD_TRACE
+extern "C" int sgr_debug_fwd_trace(unsigned long long* out, unsigned int rows) {   // experiment build only
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_fwd_trace, sizeof(unsigned long long) * 4 * (rows < kFwdTraceCap ? rows : kFwdTraceCap));
+    return 0;
+}
+#endif
 
 cudaError_t launch_loss_reduce(const ChunkCtx& c, float* loss_out) {
     const unsigned int n = unsigned(c.num_renders) * c.g.num_tiles * kBlocksPerTile;

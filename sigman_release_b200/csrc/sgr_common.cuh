@@ -25,6 +25,20 @@ constexpr int kBlocksPerTile = 8;            // a 16x16 tile = eight 8x4 pixel b
 constexpr int kSegB = 256;
 constexpr int kCkptPerSlot = 32;             // one entry per pixel of the block
 constexpr int kBwdClasses = 4;               // backward items by number of records that really blended (most first)
+// Dense blocks.  A warp walks a block list at its own issue rate — about 0.18 instructions per cycle next to three
+// other warps on its scheduler, 0.27 alone — so the ~100 longest lists of a launch (tools/fwd_trace.py: 140-160 us
+// each, started at t = 0) outlast the throughput-bound part of the forward blend (everything else is done after
+// ~105 us).  The tile sort therefore queues the block lists of at least kDenseEntries entries separately, and the first
+// ceil(#dense / kDenseWarps) CTAs of the forward blend run only kDenseWarps warps (one or two per scheduler) on them;
+// their other warps sleep until the CTA's dense walks are over.  A scheduling decision only: no arithmetic changes.
+#ifndef SGR_FWD_DENSE_ENTRIES
+#define SGR_FWD_DENSE_ENTRIES 1536
+#endif
+#ifndef SGR_FWD_DENSE_WARPS
+#define SGR_FWD_DENSE_WARPS 4
+#endif
+constexpr unsigned int kDenseEntries = SGR_FWD_DENSE_ENTRIES;
+constexpr int kDenseWarps = SGR_FWD_DENSE_WARPS;
 
 // ------------------------------------------------------------------------------------------------
 // Device-resident status / counters at the start of `state`.
@@ -57,7 +71,7 @@ struct StateLayout {
 };
 // Layout of `scratch` (valid only inside one call).
 struct ScratchLayout {
-    uint64_t keys, keys_tmp, rect, cursor, work_blend, work_empty, work_counts, loss_part, accum, total;
+    uint64_t keys, keys_tmp, rect, cursor, work_blend, work_empty, work_counts, dense_items, loss_part, accum, total;
 };
 
 __host__ __device__ inline uint64_t align_up(uint64_t x, uint64_t a = 256) { return (x + a - 1) / a * a; }
@@ -114,6 +128,7 @@ inline ScratchLayout make_scratch_layout(int B, int V, int N, int H, int W, uint
     L.work_blend = o;  o = align_up(o + Rc * T * 4);
     L.work_empty = o;  o = align_up(o + Rc * T * 4);
     L.work_counts = o; o = align_up(o + 256);
+    L.dense_items = o; o = align_up(o + Rc * T * kBlocksPerTile * 4);              // block items of the dense lists
     L.loss_part = o;   o = align_up(o + Rc * T * 8 * 4);                           // fused loss: one partial per work item
     L.accum = o;       o = align_up(o + Rc * N * 4 * kAccumPlanes);
     L.total = o;
@@ -130,6 +145,8 @@ struct WorkCounts {
     unsigned int n_empty;      // tiles without instances (background only)
     unsigned int blend_cursor; // dynamic work queue heads of the persistent blend kernels
     unsigned int empty_cursor;
+    unsigned int n_dense;      // dense block lists (queued by the tile sorts)
+    unsigned int dense_cursor;
 };
 
 constexpr int kSmallSortCap = 4096;       // lists shorter than this are sorted in a 36 KB shared-memory CTA (power of two)
@@ -272,6 +289,7 @@ struct ChunkCtx {
     unsigned int* cursor;     // [Rc*T]
     unsigned int *work_blend, *work_empty;
     WorkCounts* work_counts;
+    unsigned int* dense_items; // [Rc*T*8] chunk-local tile * 8 + block of the dense block lists
     float* loss_part;         // [Rc*T*8] fused-loss partial sums, one per (render, tile, pixel block)
     float* accum;             // [kAccumPlanes][Rc*N]
     // optional fused loss (forward)
