@@ -391,7 +391,9 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
     __shared__ int s_dense_busy;                  // warps of this CTA that still walk dense lists
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned int n_dense = a.wc->n_dense;
-    const bool dense_cta = blockIdx.x * unsigned(kDenseWarps) < n_dense;
+    // at most a third of the CTAs turn dense (a launch whose lists are mostly dense is throughput-bound, not tail-
+    // bound); dense lists beyond their capacity are taken by whoever runs out of ordinary items
+    const bool dense_cta = blockIdx.x * unsigned(kDenseWarps) < n_dense && blockIdx.x * 3u < gridDim.x;
     bool dense_mode = dense_cta && warp < kDenseWarps;
     if (threadIdx.x == 0) s_dense_busy = dense_cta ? kDenseWarps : 0;
     __syncthreads();
@@ -475,8 +477,10 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
     };
 
     // ---------------- blocks of tiles with instances
+    bool main_done = false;
     for (;;) {
         unsigned int bitem;                       // chunk-local tile * 8 + block
+        bool take_dense = dense_mode;
         if (dense_mode) {
             const unsigned int d = pop_item(&a.wc->dense_cursor, n_dense, lane);
             if (d == 0xffffffffu) {               // no dense list left: wake the CTA's other warps, join the main queue
@@ -487,19 +491,25 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
             bitem = a.dense_items[d];
         } else {
             int wait = 0;                         // (warp-uniform: read by one lane)
-            if (dense_cta && warp >= kDenseWarps)
+            if (dense_cta && warp >= kDenseWarps + kDenseMates)
                 wait = __shfl_sync(kFull, *reinterpret_cast<volatile int*>(&s_dense_busy), 0);
             if (wait > 0) {
-                // this CTA's schedulers belong to its dense walks for now: background tiles (memory latency, hardly any
-                // instructions) are the only work taken meanwhile
-                empty_tiles();
+                // this CTA's schedulers belong to its dense walks for now
+                if (kDenseWaitersDoEmpty) empty_tiles();
                 if (lane == 0)
                     while (*reinterpret_cast<volatile int*>(&s_dense_busy) > 0) __nanosleep(1000);
                 __syncwarp();
             }
-            const unsigned int item = pop_item(&a.wc->blend_cursor, n_items, lane);
-            if (item == 0xffffffffu) break;
-            bitem = a.work_blend[item / kBlocksPerTile] * kBlocksPerTile + item % kBlocksPerTile;
+            const unsigned int item = main_done ? 0xffffffffu : pop_item(&a.wc->blend_cursor, n_items, lane);
+            if (item == 0xffffffffu) {            // ordinary items are gone: help with the dense lists, if any are left
+                main_done = true;
+                const unsigned int d = pop_item(&a.wc->dense_cursor, n_dense, lane);
+                if (d == 0xffffffffu) break;
+                bitem = a.dense_items[d];
+                take_dense = true;
+            } else {
+                bitem = a.work_blend[item / kBlocksPerTile] * kBlocksPerTile + item % kBlocksPerTile;
+            }
         }
         const unsigned int tile_local = bitem / kBlocksPerTile;
         const int blk = bitem % kBlocksPerTile;
@@ -509,7 +519,7 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
         const size_t tg = size_t(r) * a.g.num_tiles + tile;
         const size_t bi = tg * kBlocksPerTile + blk;
         const unsigned int n = a.blk_cnt[bi];                       // records of this block's list
-        if (!dense_mode && n >= kDenseEntries) continue;            // queued as a dense list (same test as the tile sort)
+        if (!take_dense && n >= kDenseEntries) continue;            // queued as a dense list (same test as the tile sort)
         const size_t off = a.blk_off[bi];
         const unsigned int nb = (n + kFwdBatch - 1) / kFwdBatch;
         const int tx = tile % a.g.tiles_x, ty = tile / a.g.tiles_x;

@@ -37,8 +37,16 @@ constexpr int kBwdClasses = 4;               // backward items by number of reco
 #ifndef SGR_FWD_DENSE_WARPS
 #define SGR_FWD_DENSE_WARPS 4
 #endif
+#ifndef SGR_FWD_DENSE_MATES
+#define SGR_FWD_DENSE_MATES 4
+#endif
+#ifndef SGR_FWD_DENSE_EMPTY
+#define SGR_FWD_DENSE_EMPTY 0
+#endif
 constexpr unsigned int kDenseEntries = SGR_FWD_DENSE_ENTRIES;
 constexpr int kDenseWarps = SGR_FWD_DENSE_WARPS;
+constexpr int kDenseMates = SGR_FWD_DENSE_MATES;            // further warps of a dense CTA that work on ordinary items meanwhile
+constexpr bool kDenseWaitersDoEmpty = SGR_FWD_DENSE_EMPTY;  // the waiting warps process background tiles before they sleep
 
 // ------------------------------------------------------------------------------------------------
 // Device-resident status / counters at the start of `state`.

@@ -17,12 +17,29 @@ from common import gpu_forward
 VIEWS = [30, 37, 45, 53, 65, 85, 0, 8]
 sc = scenes.body_gaussians(100_000, seed=0)
 L = _native.lib()
+FUSED = len(sys.argv) > 1 and sys.argv[1] == "loss"      # the bench's forward: fused clamp + L1 loss epilogue
+if FUSED:
+    from sigman_release_b200 import cameras
+    from common import TAN, to_dev
+    t = dict(means3D=to_dev(sc["means3D"])[None], cov3D=to_dev(sc["cov3D"])[None], colors=to_dev(sc["colors"])[None],
+             opacities=to_dev(sc["opacities"]).reshape(1, -1))
+    for v in t.values():
+        v.requires_grad_(True)
+    vm, pm, _ = cameras.orbit_cameras(VIEWS)
+    vmt, pmt, bg = to_dev(vm)[None], to_dev(pm)[None], torch.ones(3, device="cuda")
+    target = torch.rand((1, len(VIEWS), 3, 512, 512), device="cuda")
+
+    def forward():
+        rasterizer.render_l1_loss(t["means3D"], t["cov3D"], t["colors"], t["opacities"], vmt, pmt, bg, 512, 512, TAN, TAN, target)
+else:
+    def forward():
+        gpu_forward(sc, VIEWS, 512, 512, requires_grad=True)
 for it in range(3):
-    gpu_forward(sc, VIEWS, 512, 512, requires_grad=True)
+    forward()
 torch.cuda.synchronize()
 L.sgr_profile_enable(1)
 for it in range(5):
-    gpu_forward(sc, VIEWS, 512, 512, requires_grad=True)
+    forward()
 torch.cuda.synchronize()
 ms = (ctypes.c_double * len(_native.STAGES))(); cnt = (ctypes.c_uint32 * len(_native.STAGES))()
 L.sgr_profile_collect(ms, cnt)
