@@ -292,7 +292,7 @@ int sgr_backward(const SgrBackwardArgs* args) {
     (void)BN;   // the per-subject gradients are stored (not accumulated) by the chunk holding the subject's first view
     for (int r0 = 0; r0 < R; r0 += rpc) {
         set_chunk(c, p, args->state, r0, rpc, R);
-        SGR_CUDA(cudaMemsetAsync(c.accum, 0, size_t(c.num_renders) * p.num_gaussians * 4 * kAccumPlanes, stream));
+        SGR_CUDA(cudaMemsetAsync(c.accum, 0, size_t(c.num_renders) * p.num_gaussians * 4 * kAccumStride, stream));
         if (p.flags & SGR_FLAG_SIMPLE_BLEND) {
             SGR_STAGE(kStBlendBwd, launch_blend_backward_simple(c, args->out_alpha, args->dL_dcolor, args->dL_ddepth, args->dL_dalpha));
         } else {

@@ -111,6 +111,10 @@ __device__ __forceinline__ float rcp_approx(float x) {       // MUFU.RCP, 1 ulp;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// 16-byte vector reduction (sm_90+): four float adds to one aligned 16-byte chunk in one L2 transaction.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -886,7 +890,7 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
         }
         const float bg_dot = (bg0 * dp0 + bg1 * dp1) + bg2 * dp2;
         const float K = T_final * (bg_dot - dalp);
-        float* acc = a.accum + size_t(rl) * a.g.N;
+        float* acc = a.accum + size_t(rl) * a.g.N * kAccumStride;
 
         // walk step k handles list batch (nb - 1 - k): its index entries arrive by TMA one step ahead; its records
         // (and Gaussian ids) are gathered at the start of the step — only those the forward found to blend
@@ -1021,17 +1025,11 @@ __global__ void __launch_bounds__(kBlendThreads, SGR_BWD_MIN_CTAS) blend_backwar
                             if (kDepthAlphaGrads) s9 = fmaf(w, sm.dpix[3][pl], s9);
                         }
                         if (cvalid) {
-                            float* g = acc + ixs[j].x;               // the record's Gaussian id
-                            if (s0 != 0.0f) atomicAdd(g + 0 * a.plane, s0 * ddelx_dx);
-                            if (s1 != 0.0f) atomicAdd(g + 1 * a.plane, s1 * ddely_dy);
-                            if (s2 != 0.0f) atomicAdd(g + 2 * a.plane, -0.5f * s2);
-                            if (s3 != 0.0f) atomicAdd(g + 3 * a.plane, -0.5f * s3);
-                            if (s4 != 0.0f) atomicAdd(g + 4 * a.plane, -0.5f * s4);
-                            if (s5 != 0.0f) atomicAdd(g + 5 * a.plane, s5);
-                            if (s6 != 0.0f) atomicAdd(g + 6 * a.plane, s6);
-                            if (s7 != 0.0f) atomicAdd(g + 7 * a.plane, s7);
-                            if (s8 != 0.0f) atomicAdd(g + 8 * a.plane, s8);
-                            if (kDepthAlphaGrads && s9 != 0.0f) atomicAdd(g + 9 * a.plane, s9);
+                            float* g = acc + size_t(ixs[j].x) * kAccumStride;   // the record's Gaussian id -> its row
+                            red_add_v4(g, s0 * ddelx_dx, s1 * ddely_dy, -0.5f * s2, -0.5f * s3);
+                            red_add_v4(g + 4, -0.5f * s4, s5, s6, s7);
+                            if (kDepthAlphaGrads) red_add_v4(g + 8, s8, s9, 0.0f, 0.0f);
+                            else atomicAdd(g + 8, s8);
                         }
                     }
                 }

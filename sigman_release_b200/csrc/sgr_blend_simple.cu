@@ -93,7 +93,7 @@ struct SimpleBwdArgs {
     const float* bg;
     const unsigned int* n_contrib;
     const float *out_alpha, *dL_dcolor, *dL_ddepth, *dL_dalpha;
-    float* accum;             // [kAccumPlanes][plane]
+    float* accum;             // [plane][kAccumStride]
     size_t plane;
 };
 
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kTilePixels) blend_backward_simple_kernel(Simp
     float ar0 = 0, ar1 = 0, ar2 = 0, adr = 0, aar = 0, last_alpha = 0, lc0 = 0, lc1 = 0, lc2 = 0, last_depth = 0;
     const float bg_dot = (a.bg[0] * dp0 + a.bg[1] * dp1) + a.bg[2] * dp2;
     const float ddelx_dx = 0.5f * float(a.g.W), ddely_dy = 0.5f * float(a.g.H);
-    float* acc = a.accum + size_t(rl) * a.g.N;
+    float* acc = a.accum + size_t(rl) * a.g.N * kAccumStride;
 
     const unsigned int rounds = (n_eff + kTilePixels - 1) / kTilePixels;
     for (unsigned int rd = rounds; rd-- > 0;) {
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kTilePixels) blend_backward_simple_kernel(Simp
 #pragma unroll
                 for (int k = 0; k < kAccumPlanes; ++k) {
                     const float s = warp_sum(v[k]);
-                    if ((threadIdx.x & 31) == 0 && s != 0.0f) atomicAdd(acc + size_t(k) * a.plane + id, s);
+                    if ((threadIdx.x & 31) == 0 && s != 0.0f) atomicAdd(acc + size_t(id) * kAccumStride + k, s);
                 }
             }
         }

@@ -123,6 +123,10 @@ inline StateLayout make_state_layout(int B, int V, int N, int H, int W, uint64_t
 }
 
 constexpr int kAccumPlanes = 10;          // mean2D.xy, conic A/B/C, opacity, rgb, depth
+// The gradient accumulators are one 48-byte row per (render, Gaussian): (mean2D.x, mean2D.y, conic A, conic B |
+// conic C, opacity, r, g | b, depth, -, -), so that the blend backward adds a Gaussian's terms with three 16-byte vector
+// atomics (red.global.add.v4.f32) instead of ten scalar ones into ten planes.
+constexpr int kAccumStride = 12;
 
 inline ScratchLayout make_scratch_layout(int B, int V, int N, int H, int W, uint64_t cap, int rpc) {
     const uint64_t R = uint64_t(B) * V, T = uint64_t(tiles_x(W)) * tiles_y(H);
@@ -138,7 +142,7 @@ inline ScratchLayout make_scratch_layout(int B, int V, int N, int H, int W, uint
     L.work_counts = o; o = align_up(o + 256);
     L.dense_items = o; o = align_up(o + Rc * T * kBlocksPerTile * 4);              // block items of the dense lists
     L.loss_part = o;   o = align_up(o + Rc * T * 8 * 4);                           // fused loss: one partial per work item
-    L.accum = o;       o = align_up(o + Rc * N * 4 * kAccumPlanes);
+    L.accum = o;       o = align_up(o + Rc * N * 4 * kAccumStride);
     L.total = o;
     return L;
 }
@@ -299,7 +303,7 @@ struct ChunkCtx {
     WorkCounts* work_counts;
     unsigned int* dense_items; // [Rc*T*8] chunk-local tile * 8 + block of the dense block lists
     float* loss_part;         // [Rc*T*8] fused-loss partial sums, one per (render, tile, pixel block)
-    float* accum;             // [kAccumPlanes][Rc*N]
+    float* accum;             // [Rc*N][kAccumStride]
     // optional fused loss (forward)
     const float *loss_target, *loss_mask;
     float* loss_dL_dcolor;

@@ -14,7 +14,7 @@ struct PreBwdArgs {
     int render_base, num_renders;
     const float *means, *cov, *view, *proj;
     const int32_t* radii;
-    const float* accum;          // [kAccumPlanes][Rc*N]
+    const float* accum;          // [Rc*N][kAccumStride]
     size_t plane;                // Rc*N
     float *d_means3D, *d_cov3D, *d_colors, *d_opac, *d_means2D;
 };
@@ -53,9 +53,13 @@ __global__ void __launch_bounds__(32 * kPreBwdSlots, SGR_PREBWD_MIN_CTAS) prepro
         // all loads of the iteration are issued together (one exposed memory latency): nearly every Gaussian of a
         // framed subject is visible, so waiting for the radius before fetching the accumulators only serialises them
         const int rad = a.radii[size_t(r) * N + i];
-        float acc[kAccumPlanes];
-#pragma unroll
-        for (int k = 0; k < kAccumPlanes; ++k) acc[k] = a.accum[k * a.plane + oi];
+        float acc[kAccumStride];
+        {
+            const float4* row = reinterpret_cast<const float4*>(a.accum + oi * kAccumStride);
+            const float4 v0 = row[0], v1 = row[1], v2 = row[2];
+            acc[0] = v0.x; acc[1] = v0.y; acc[2] = v0.z; acc[3] = v0.w; acc[4] = v1.x; acc[5] = v1.y; acc[6] = v1.z;
+            acc[7] = v1.w; acc[8] = v2.x; acc[9] = v2.y; acc[10] = v2.z; acc[11] = v2.w;
+        }
         const bool vis = rad > 0;
         if (a.d_means2D && live) {
             float* o = a.d_means2D + (size_t(r) * N + i) * 3;
