@@ -22,8 +22,13 @@ import subprocess
 import sys
 import threading
 import time
+import warnings
 
 import numpy as np
+
+# GraphedStep warms a step up on a side stream (torch's capture recipe), so the leaves' AccumulateGrad nodes belong to
+# that stream; the eager passes below then run on the default stream.  Harmless here (every pass is synchronised).
+warnings.filterwarnings("ignore", message="The AccumulateGrad node's stream does not match")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:

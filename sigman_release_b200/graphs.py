@@ -30,17 +30,22 @@ __all__ = ["GraphedStep"]
 class GraphedStep:
     def __init__(self, fn: Callable[[], object], warmup: int = 3, device=None):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        try:        # the warm-up runs on a side stream on purpose; the leaves were created on the caller's stream
-            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
-        except AttributeError:
-            pass
-        side = torch.cuda.Stream(device=self.device)
-        side.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(side):                       # eager warm-up on a side stream (torch's capture recipe)
-            for _ in range(max(1, warmup)):
-                fn()
-        torch.cuda.current_stream(self.device).wait_stream(side)
-        torch.cuda.synchronize(self.device)
+        # the warm-up runs on a side stream on purpose while the leaves were created on the caller's stream: silence
+        # autograd's stream-mismatch warning for the warm-up only and restore the setting afterwards
+        setter = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if setter is not None:
+            setter(False)
+        try:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):                   # eager warm-up on a side stream (torch's capture recipe)
+                for _ in range(max(1, warmup)):
+                    fn()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+        finally:
+            if setter is not None:
+                setter(True)                                # (the default)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.result = fn()
