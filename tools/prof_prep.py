@@ -3,7 +3,8 @@ scale / covariance kernel with its backward, 8 subjects x 100 K Gaussians (BASEL
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from sigman_release_b200 import scenes, distCUDA2_batched, prep_cov3d
+from sigman_release_b200 import scenes
+from sigman_release_b200.renderer import distCUDA2_batched, prep_cov3d
 
 B, N = 8, 100_000
 pts = torch.stack([torch.as_tensor(scenes.body_gaussians(N, seed=s)["means3D"]) for s in range(B)]).float().cuda()
