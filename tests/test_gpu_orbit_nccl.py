@@ -31,7 +31,8 @@ def _scene(dev):
 
 
 def _worker(rank, world, port, ret):
-    from sigman_release_b200.orbit import WIRE_COMPACT, WIRE_EXACT, rasterizer_planes, render_orbit_overlapped
+    from sigman_release_b200.orbit import (WIRE_COMPACT, WIRE_EXACT, OrbitRenderer, rasterizer_planes,
+                                           render_orbit_overlapped)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -46,10 +47,18 @@ def _worker(rank, world, port, ret):
             exact = render_orbit_overlapped(fn, nv, H, W, dev, wire=WIRE_EXACT, chunk=3)
             compact = render_orbit_overlapped(fn, nv, H, W, dev, wire=WIRE_COMPACT, chunk=2)
             c, d, a = fn(list(range(nv)), None)                       # all views on this GPU
+            # the same with preallocated buffers and one CUDA graph per chunk: eager warm-up call, then two replays
+            orb = OrbitRenderer(t["means3D"], t["cov3D"], t["colors"], t["opacities"], torch.ones(3, device=dev), H, W, tan,
+                                vm, pm, wire=WIRE_EXACT, chunk=3)
+            graphed = [orb.render().clone() for _ in range(3)]
+            orb_c = OrbitRenderer(t["means3D"], t["cov3D"], t["colors"], t["opacities"], torch.ones(3, device=dev), H, W,
+                                  tan, vm, pm, wire=WIRE_COMPACT, chunk=2)
+            graphed_c = [orb_c.render().clone() for _ in range(2)]
         torch.cuda.synchronize()
         single = torch.cat([c, d, a], dim=1)
         ret[rank] = (bool(torch.equal(exact, single)), float((compact[:, 0:3] - single[:, 0:3]).abs().max()),
-                     float((compact[:, 3:] - single[:, 3:]).abs().max()))
+                     float((compact[:, 3:] - single[:, 3:]).abs().max()),
+                     all(bool(torch.equal(g, single)) for g in graphed), all(bool(torch.equal(g, compact)) for g in graphed_c))
     finally:
         dist.destroy_process_group()
 
@@ -60,9 +69,11 @@ def test_overlapped_orbit_over_nccl_equals_single_gpu_render():
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     for r in range(world):
-        same, err_rgb, err_da = ret[r]
+        same, err_rgb, err_da, same_graphed, same_graphed_compact = ret[r]
         assert same, f"rank {r}: exact wire format differs from the single-GPU render"
         assert err_rgb <= 0.5 / 255 + 1e-6 and err_da <= 5e-3
+        assert same_graphed, f"rank {r}: OrbitRenderer (graph replay) differs from the single-GPU render"
+        assert same_graphed_compact, f"rank {r}: OrbitRenderer (compact wire) differs from render_orbit_overlapped"
 
 
 def test_overlapped_orbit_single_process_writes_into_the_gather_buffer():
@@ -77,3 +88,24 @@ def test_overlapped_orbit_single_process_writes_into_the_gather_buffer():
         got = render_orbit_overlapped(fn, nv, H, W, dev, chunk=4)
         c, d, a = fn(list(range(nv)), None)
     assert torch.equal(got, torch.cat([c, d, a], dim=1))
+
+
+def test_orbit_renderer_graph_replay_single_process():
+    """OrbitRenderer at world size 1: eager warm-up call and graph replays reproduce the direct render; refreshing the
+    static subject tensors in place changes the result accordingly."""
+    from sigman_release_b200.orbit import OrbitRenderer, rasterizer_planes
+    dev = torch.device("cuda", 0)
+    t, vm, pm, tan, nv = _scene(dev)
+    H = W = 96
+    bg = torch.ones(3, device=dev)
+    fn = rasterizer_planes(t["means3D"], t["cov3D"], t["colors"], t["opacities"], bg, H, W, tan, vm, pm)
+    orb = OrbitRenderer(t["means3D"], t["cov3D"], t["colors"], t["opacities"], bg, H, W, tan, vm, pm, chunk=5)
+    with torch.no_grad():
+        c, d, a = fn(list(range(nv)), None)
+        want = torch.cat([c, d, a], dim=1)
+        for _ in range(3):
+            assert torch.equal(orb.render(), want)
+        t["colors"].mul_(0.5)                                          # static inputs refreshed in place
+        c, d, a = fn(list(range(nv)), None)
+        assert torch.equal(orb.render(), torch.cat([c, d, a], dim=1))
+        assert not torch.equal(orb.render(), want)
