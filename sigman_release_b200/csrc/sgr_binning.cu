@@ -1,5 +1,6 @@
 // sgr_binning.cu — tile binning: per-tile offsets (scan), work lists, and the per-tile depth sort that emits the
-// depth-ordered instance stream (sorted ids + gathered 48-byte records) consumed by the blend kernels.
+// depth-ordered id lists (upstream's point_list) and, per 8x4 pixel block of every tile, the depth-ordered list of
+// (Gaussian id, tile-list position, quarter mask) entries consumed by the blend kernels.
 //
 // Replaces upstream's InclusiveSum + global 64-bit DeviceRadixSort + identifyTileRanges.  Upstream
 // sorts ONE global array keyed (tile << 32 | depth bits); the stable sort resolves (tile, depth) ties by ascending
@@ -308,7 +309,7 @@ __device__ __forceinline__ void block_exclusive_scan(unsigned int* hist, unsigne
 }
 
 // Sorts the n keys of one tile: writes the depth-ordered ids (upstream's point_list) and then either the tile's
-// gathered 48-byte records (simple) or the eight per-block record lists.  kb: n-element key buffer (shared or global).
+// gathered 48-byte records (SGR_FLAG_SIMPLE_BLEND) or the eight per-block entry lists.  kb: n-element key buffer (shared or global).
 // KPT > 0: the tile has at most THREADS * KPT keys and every thread keeps its keys in registers, so the three passes
 // over the unsorted keys (range, histogram, scatter) cost ONE exposed global-memory latency instead of three (the
 // per-tile sort is a latency chain, not a bandwidth problem); KPT == 0 re-reads the keys from global memory.

@@ -25,7 +25,11 @@
 //     walk in reverse over descending lists with phases A+B (alpha, G, then the per-pixel transmittance / colour
 //     recurrences producing dL/dalpha and the blend weight, stashed) and C: the roles flip to lane = (Gaussian,
 //     quarter) pair, each lane summing the gradient terms of its quarter's 8 pixels in registers (XOR-swizzled stash,
-//     no shuffles) before one atomic per component.  Gradient arithmetic is free to use FMA (tolerance, not bit-exact);
+//     no shuffles) before three 16-byte vector atomics into the Gaussian's accumulator row (red.global.add.v4.f32).
+//     Gradient arithmetic is free to use FMA (tolerance, not bit-exact);
+//   * the block lists of at least kDenseEntries entries are queued separately by the tile sort and walked on "dense"
+//     CTAs that keep one dense walk + one ordinary warp per scheduler awake (sgr_common.cuh): a warp is latency-bound,
+//     and the longest walks otherwise outlast the rest of the launch;
 //   * optional epilogue: clamp + masked L1 loss + dL/dcolour (SgrForwardArgs::loss_*).
 //
 // Compiled with --fmad=false: the per-pixel expressions are the oracle's (oracle/sgr_oracle.cpp::blend_forward /
