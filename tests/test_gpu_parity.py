@@ -442,21 +442,24 @@ def test_dense_quarter_lists_fill_whole_batches():
     assert_grads_like_fp32({k: v.grad[0] for k, v in t.items()}, ref32, ref64)
 
 
-def test_full_hd_image_uses_the_global_histogram_path():
+@pytest.mark.parametrize("views,rpc", [([30, 8], 1), ([30, 8, 53], 3)])
+def test_full_hd_image_uses_the_global_histogram_path(views, rpc):
     """1080 x 1920: 8160 tiles per render (> the 4096 tiles whose counters fit the per-CTA shared-memory histogram of
-    the preprocess / scatter kernels), two views, chunked one render at a time."""
+    the preprocess / scatter kernels), chunked one render at a time, and three renders in one chunk (24 480 tiles: the
+    plan kernel's carried scan runs over three strips of 8192 tiles, the last one partial)."""
     H, W = 1080, 1920
+    V = len(views)
     sc = small_scene(n=2500, seed=9, spread=0.9, smin=0.004, smax=0.05)
-    out, t, (vm, pm) = gpu_forward(sc, [30, 8], H, W, requires_grad=True, renders_per_chunk=1)
+    out, t, (vm, pm) = gpu_forward(sc, views, H, W, requires_grad=True, renders_per_chunk=rpc)
     state, dims = saved_state(out[0])
-    for v in range(2):
+    for v in range(V):
         r, ora = oracle_forward(sc, vm[v], pm[v], H, W)
         _assert_forward_equal(out, ora, render=v)
-        ranges, ncon, pl = debug_state(state, 1, 2, 2500, H, W, dims[7], v)
+        ranges, ncon, pl = debug_state(state, 1, V, 2500, H, W, dims[7], v)
         b = r.binning()
         np.testing.assert_array_equal(ranges, b["ranges"])
         np.testing.assert_array_equal(pl, b["point_list"])
-    g = np.random.default_rng(1).normal(size=(2, 3, H, W)).astype(np.float32)
+    g = np.random.default_rng(1).normal(size=(V, 3, H, W)).astype(np.float32)
     (out[0][0] * to_dev(g)).sum().backward()
     ref32, ref64, _ = oracle_grads(sc, vm, pm, H, W, list(g))
     assert_grads_like_fp32({k: v.grad[0] for k, v in t.items()}, ref32, ref64)
