@@ -426,6 +426,12 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
     // ---------------- tiles without instances: background only.  Whole tiles are popped; the fused loss's loads of
     // four blocks are issued together (the phase is a chain of memory latencies, not work).  Called by every warp
     // after the main queue, and before it by the warps that would otherwise sleep beside a dense walk.
+    const bool vec_ok = (a.g.W & 3) == 0 &&
+        ((reinterpret_cast<uintptr_t>(a.out_color) | reinterpret_cast<uintptr_t>(a.out_depth) |
+          reinterpret_cast<uintptr_t>(a.out_alpha) | reinterpret_cast<uintptr_t>(a.n_contrib) |
+          reinterpret_cast<uintptr_t>(a.clamp_mask) | reinterpret_cast<uintptr_t>(a.loss_target) |
+          reinterpret_cast<uintptr_t>(a.loss_mask) | reinterpret_cast<uintptr_t>(a.loss_dL_dcolor) |
+          reinterpret_cast<uintptr_t>(a.out_feed)) & 15) == 0;       // (null pointers count as aligned)
     auto empty_tiles = [&]() {
         for (;;) {
             unsigned int w = 0;
@@ -438,6 +444,79 @@ __global__ void __launch_bounds__(kFwdThreads, SGR_FWD_MIN_CTAS) blend_forward_k
             const int r = a.render_base + rl;
             const int tx = tile % a.g.tiles_x, ty = tile / a.g.tiles_x;
             const size_t rP = size_t(r) * P;
+            if (vec_ok && (tx + 1) * kTile <= a.g.W && (ty + 1) * kTile <= a.g.H) {
+                // A tile entirely inside the image, rows 16-byte aligned: lane = (row lane >> 2 of a half tile, four
+                // pixels (lane & 3) * 4 ..), everything as 16-byte accesses, the loads of both half tiles first.
+                const int x4 = tx * kTile + (lane & 3) * 4;
+                float4 tg[2][3], mk[2];
+                size_t pix[2];
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    pix[hf] = size_t(ty * kTile + hf * 8 + (lane >> 2)) * a.g.W + x4;
+                    if (a.loss_target) {
+                        mk[hf] = a.loss_mask ? *reinterpret_cast<const float4*>(a.loss_mask + rP + pix[hf])
+                                             : make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch)
+                            tg[hf][ch] = *reinterpret_cast<const float4*>(a.loss_target + 3 * rP + ch * P + pix[hf]);
+                    }
+                }
+                const float cs[3] = {bg0, bg1, bg2};
+                float cl[3];
+                unsigned int cmask = 0;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const bool pass = cs[ch] >= 0.0f && cs[ch] <= 1.0f;
+                    cmask |= pass ? 0u : (1u << ch);
+                    cl[ch] = a.clamp_color ? fminf(fmaxf(cs[ch], 0.0f), 1.0f) : cs[ch];
+                }
+                float part = 0.0f;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    float* oc = a.out_color + 3 * rP + pix[hf];
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch)
+                        *reinterpret_cast<float4*>(oc + ch * P) = make_float4(cl[ch], cl[ch], cl[ch], cl[ch]);
+                    *reinterpret_cast<float4*>(a.out_depth + rP + pix[hf]) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    *reinterpret_cast<float4*>(a.out_alpha + rP + pix[hf]) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    *reinterpret_cast<uint4*>(a.n_contrib + rP + pix[hf]) = make_uint4(0u, 0u, 0u, 0u);
+                    if (a.clamp_color) *reinterpret_cast<unsigned int*>(a.clamp_mask + rP + pix[hf]) = cmask * 0x01010101u;
+                    if (a.out_feed && ((lane >> 2) & 1) == 0) {      // 2x2 means of a constant image: even rows write
+                        const size_t Pq = P >> 2;
+                        const size_t q = size_t((ty * kTile + hf * 8 + (lane >> 2)) >> 1) * (a.g.W >> 1) + (x4 >> 1);
+                        float* of = a.out_feed + size_t(r) * 3 * Pq + q;
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            const float v = 0.5f * (4.0f * cl[ch]) - 1.0f;
+                            *reinterpret_cast<float2*>(of + ch * Pq) = make_float2(v, v);
+                        }
+                    }
+                    if (a.loss_target) {
+                        const float mks[4] = {mk[hf].x, mk[hf].y, mk[hf].z, mk[hf].w};
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {          // loss_pixel() on the background colour
+                            const float tgs[4] = {tg[hf][ch].x, tg[hf][ch].y, tg[hf][ch].z, tg[hf][ch].w};
+                            const bool pass = cs[ch] >= 0.0f && cs[ch] <= 1.0f;
+                            float dl[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float c1 = fminf(fmaxf(cs[ch], 0.0f), 1.0f);
+                                const float diff = c1 * mks[k] - tgs[k] * mks[k];
+                                const float gs = mks[k] * a.loss_scale;
+                                part += fabsf(diff);
+                                dl[k] = pass ? (diff > 0.0f ? gs : diff < 0.0f ? -gs : 0.0f) : 0.0f;
+                            }
+                            *reinterpret_cast<float4*>(a.loss_dL_dcolor + 3 * rP + ch * P + pix[hf]) =
+                                make_float4(dl[0], dl[1], dl[2], dl[3]);
+                        }
+                    }
+                }
+                if (a.loss_target) {                  // one partial for the tile (slot of block 0), zeros for the others
+                    part = warp_sum(part);
+                    if (lane < kBlocksPerTile) a.loss_part[size_t(tile_local) * kBlocksPerTile + lane] = lane == 0 ? part : 0.0f;
+                }
+                continue;
+            }
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 float tg[4][3], mk[4];
