@@ -160,6 +160,12 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(PreArgs a) {
     }
 }
 
+#ifndef SGR_SCATTER_ITERS
+#define SGR_SCATTER_ITERS 3
+#endif
+constexpr int kScatterIters = SGR_SCATTER_ITERS;   // sub-batches of 256 Gaussians per scatter CTA (1048 CTAs for 8 x 100 K:
+                                                   // one wave; with 2 the 1568 CTAs ran as 1.3 waves: 23 -> 21 us)
+
 struct ScatterArgs {
     RenderGeom g;
     int render_base;
@@ -172,7 +178,7 @@ struct ScatterArgs {
 };
 
 // duplicateWithKeys: one (depth bits << 32 | gaussian id) key per covered tile, appended to the tile's segment.
-// A CTA handles kPreIters * 256 Gaussians of one render: it counts its instances per tile in shared memory, reserves a
+// A CTA handles kScatterIters * 256 Gaussians of one render: it counts its instances per tile in shared memory, reserves a
 // contiguous range per touched tile with ONE global atomic, and then places its keys with shared-memory atomics.
 __global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs a) {
     extern __shared__ unsigned int s_sc[];       // cnt[num_tiles], base[num_tiles] when num_tiles <= kHistTiles
@@ -184,11 +190,11 @@ __global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs a) {
     unsigned int* s_base = s_sc + T;
     const size_t tb = size_t(a.render_base + rl) * T;
     unsigned int* cur = a.cursor + size_t(rl) * T;
-    const int i_lo = blockIdx.x * kPreIters * 256;
+    const int i_lo = blockIdx.x * kScatterIters * 256;
     if (use_hist) {
         for (int k = threadIdx.x; k < T; k += 256) s_cnt[k] = 0;
         __syncthreads();
-        for (int it = 0; it < kPreIters; ++it) {
+        for (int it = 0; it < kScatterIters; ++it) {
             const int i = i_lo + it * 256 + threadIdx.x;
             if (i >= a.g.N) break;
             const uint2 rc = a.rect[size_t(rl) * a.g.N + i];
@@ -204,7 +210,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(ScatterArgs a) {
         }
         __syncthreads();
     }
-    for (int it = 0; it < kPreIters; ++it) {
+    for (int it = 0; it < kScatterIters; ++it) {
         const int i = i_lo + it * 256 + threadIdx.x;
         if (i >= a.g.N) break;
         const size_t oi = size_t(rl) * a.g.N + i;
@@ -242,7 +248,7 @@ cudaError_t launch_scatter(const ChunkCtx& c) {
     ScatterArgs a;
     a.g = c.g; a.render_base = c.render_base; a.g2 = c.g2; a.rect = c.rect; a.tile_off = c.tile_off;
     a.cursor = c.cursor; a.keys = c.keys; a.wc = c.work_counts;
-    const int per_cta = 256 * kPreIters;
+    const int per_cta = 256 * kScatterIters;
     dim3 grid((c.g.N + per_cta - 1) / per_cta, c.num_renders);
     const size_t smem = c.g.num_tiles <= kHistTiles ? size_t(c.g.num_tiles) * 8 : 0;
     scatter_kernel<<<grid, 256, smem, c.stream>>>(a);
