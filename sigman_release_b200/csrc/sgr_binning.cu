@@ -543,7 +543,7 @@ __device__ __forceinline__ void sort_one_tile(const SortArgs& a, int tile_local,
 }
 
 #ifndef SGR_SORT_SMALL_MIN_CTAS
-#define SGR_SORT_SMALL_MIN_CTAS 3
+#define SGR_SORT_SMALL_MIN_CTAS 4
 #endif
 __global__ void __launch_bounds__(kSmallSortThreads, SGR_SORT_SMALL_MIN_CTAS) sort_small_kernel(SortArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];                // kSmallSortSmem bytes
