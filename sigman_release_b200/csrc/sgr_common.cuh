@@ -22,7 +22,10 @@ constexpr int kBlocksPerTile = 8;            // a 16x16 tile = eight 8x4 pixel b
 // blend kernels' batch).  The forward blend checkpoints every pixel's running state at the segment boundaries of
 // lists longer than one segment; slot (block list, s) = blk_off / (kSegB / 2) + s, s < #segments, the last slot
 // holding the final state (a list of m > kSegB records spans at least ceil(m / kSegB) slots of that numbering).
-constexpr int kSegB = 256;
+#ifndef SGR_SEGB
+#define SGR_SEGB 256
+#endif
+constexpr int kSegB = SGR_SEGB;
 constexpr int kCkptPerSlot = 32;             // one entry per pixel of the block
 constexpr int kBwdClasses = 4;               // backward items by number of records that really blended (most first)
 // Dense blocks.  A warp walks a block list at its own issue rate — about 0.18 instructions per cycle next to three
