@@ -216,22 +216,50 @@ __global__ void __launch_bounds__(256) knn_fill_kernel(const float* __restrict__
     sorted_all[size_t(b) * N + pos] = make_float4(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], __int_as_float(i));
 }
 
+// Keeps the three smallest of {b0 <= b1 <= b2, d}: a branch-free min / max chain (five FMNMX).
 __device__ __forceinline__ void insert3(float d, float& b0, float& b1, float& b2) {
-    if (d < b2) {
-        if (d < b1) {
-            b2 = b1;
-            if (d < b0) { b1 = b0; b0 = d; } else b1 = d;
-        } else b2 = d;
-    }
+    const float m0 = fmaxf(b0, d);
+    b0 = fminf(b0, d);
+    const float m1 = fmaxf(b1, m0);
+    b1 = fminf(b1, m0);
+    b2 = fminf(b2, m1);
 }
 
-// One thread per point, IN CELL ORDER (thread j takes sorted[j]): the threads of a warp sit in the same or adjacent
-// cells, so their cell-table and point reads coalesce and their ring walks have the same length.
+// kLanes lanes per point, points IN CELL ORDER (lane group g takes sorted[g]): the lanes of a point stride through the
+// candidates of every cell row of the point's ring (private three-best lists, merged per ring with shuffles), and the
+// points of a warp — same or adjacent cells — walk rings of the same shape over the same cache lines.
+//   kLanes = 1: the fewest instructions per point — what a launch that fills the machine wants (8 x 100 K points:
+//               502 us per call against 578 us with eight lanes; tools/knn_bench.py);
+//   kLanes = 8: a row of up to eight candidates costs one trip instead of eight — the latency of one subject's call
+//               (100 K points: 121 us per call against 182 us with one lane).
+// The three-best insertion is a branch-free min / max chain (with the branchy form: 591 / 248 us).
+
+// Merges the three-best lists of a point's eight lanes: every lane returns the group's three smallest values.
+__device__ __forceinline__ void merge3_group(float& b0, float& b1, float& b2, int lane) {
+    const unsigned int gmask = 0xffu << (lane & 24);
+    float m[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float v = b0;
+        v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+        v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+        v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+        m[r] = v;
+        // exactly one lane holding the minimum pops it (equal distances of different candidates stay counted)
+        const unsigned int owners = __ballot_sync(0xffffffffu, b0 == v) & gmask;
+        if (owners && lane == __ffs(owners) - 1) { b0 = b1; b1 = b2; b2 = __int_as_float(0x7f800000); }
+    }
+    b0 = m[0]; b1 = m[1]; b2 = m[2];
+}
+
+template <int kKnnLanes>
 __global__ void __launch_bounds__(128) knn_query_kernel(int N, const KnnHeader* h_all,
                                                         const unsigned int* __restrict__ cell_start_all,
                                                         const float4* __restrict__ sorted_all, float* __restrict__ out_all) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= N) return;
+    const int lane = threadIdx.x & 31, sub = lane & (kKnnLanes - 1);
+    const int j_raw = (blockIdx.x * blockDim.x + threadIdx.x) / kKnnLanes;
+    const bool live = j_raw < N;
+    const int j = live ? j_raw : N - 1;          // surplus groups shadow the last point (the warp shuffles together)
     const int b = blockIdx.y;
     const KnnHeader* h = h_all + b;
     const unsigned int* cell_start = cell_start_all + size_t(b) * (kMaxCells + 1);
@@ -241,47 +269,50 @@ __global__ void __launch_bounds__(128) knn_query_kernel(int N, const KnnHeader* 
     const int3 c = cell_coord(h, px, py, pz);
     const int dx = h->dim[0], dy = h->dim[1], dz = h->dim[2];
     const float cell = h->cell;
-    float b0, b1, b2;
-    b0 = b1 = b2 = __int_as_float(0x7f800000);      // fewer than 3 other points -> +inf, like the oracle
+    const float inf = __int_as_float(0x7f800000);
+    float b0 = inf, b1 = inf, b2 = inf;          // this lane's three best (fewer than 3 other points -> +inf, like the oracle)
+    float third = inf;                           // the point's third-best distance after the last merge (group-uniform)
+    bool done = false;
     const int max_ring = max(dx, max(dy, dz));
     for (int ring = 0; ring <= max_ring; ++ring) {
-        if (ring >= 1) {
+        if (ring >= 2) {
             // every unvisited point lies at least (ring - 1) * cell + (distance to the nearest face of the own cell)
             // away; use the weaker bound (ring - 1) * cell, shrunk slightly for rounding of the cell assignment
             const float bound = float(ring - 1) * cell * 0.999f;
-            if (bound * bound > b2) break;
+            if (bound * bound > third) done = true;
         }
-        const int z0 = c.z - ring, z1 = c.z + ring, y0 = c.y - ring, y1 = c.y + ring, x0 = c.x - ring, x1 = c.x + ring;
-        for (int z = max(z0, 0); z <= min(z1, dz - 1); ++z)
-            for (int y = max(y0, 0); y <= min(y1, dy - 1); ++y) {
-                const bool shell_row = (z == z0 || z == z1 || y == y0 || y == y1);
-                if (shell_row) {
-                    // the row's cells are consecutive in the table: one [start, end) range for the whole row
-                    const int xa = max(x0, 0), xb = min(x1, dx - 1);
+        if (__all_sync(0xffffffffu, done)) break;
+        if (!done) {
+            const int z0 = c.z - ring, z1 = c.z + ring, y0 = c.y - ring, y1 = c.y + ring, x0 = c.x - ring, x1 = c.x + ring;
+            for (int z = max(z0, 0); z <= min(z1, dz - 1); ++z)
+                for (int y = max(y0, 0); y <= min(y1, dy - 1); ++y) {
+                    const bool shell_row = (z == z0 || z == z1 || y == y0 || y == y1);
                     const unsigned int id = (unsigned(z) * dy + y) * dx;
-                    const unsigned int s = cell_start[id + xa], e = cell_start[id + xb + 1];
-                    for (unsigned int k = s; k < e; ++k) {
-                        const float4 q = __ldg(sorted + k);
-                        if (k == unsigned(j)) continue;
-                        const float ddx = q.x - px, ddy = q.y - py, ddz = q.z - pz;
-                        insert3(ddx * ddx + ddy * ddy + ddz * ddz, b0, b1, b2);
-                    }
-                } else {                                  // interior rows: only the two end cells
-                    for (int x = x0; x <= x1; x += max(1, x1 - x0)) {
-                        if (x < 0 || x >= dx) continue;
-                        const unsigned int id = (unsigned(z) * dy + y) * dx + x;
-                        const unsigned int s = cell_start[id], e = cell_start[id + 1];
-                        for (unsigned int k = s; k < e; ++k) {
+                    // shell rows: the row's cells are consecutive in the table, one [start, end) range for the whole
+                    // row; interior rows: only the two end cells
+                    const int nseg = shell_row ? 1 : 2;
+                    for (int sg = 0; sg < nseg; ++sg) {
+                        int xa, xb;
+                        if (shell_row) { xa = max(x0, 0); xb = min(x1, dx - 1); }
+                        else { xa = xb = sg == 0 ? x0 : x1; if (xa < 0 || xa >= dx) continue; }
+                        const unsigned int s = cell_start[id + xa], e = cell_start[id + xb + 1];
+                        for (unsigned int k = s + sub; k < e; k += kKnnLanes) {
                             const float4 q = __ldg(sorted + k);
-                            if (k == unsigned(j)) continue;
                             const float ddx = q.x - px, ddy = q.y - py, ddz = q.z - pz;
-                            insert3(ddx * ddx + ddy * ddy + ddz * ddz, b0, b1, b2);
+                            const float d = ddx * ddx + ddy * ddy + ddz * ddz;
+                            insert3(k != unsigned(j) ? d : inf, b0, b1, b2);
                         }
                     }
                 }
-            }
+        }
+        if (ring >= 1) {                          // (the ring-1 shell is always visited: nothing to decide after ring 0)
+            if (kKnnLanes > 1) merge3_group(b0, b1, b2, lane);
+            third = b2;
+            if (kKnnLanes > 1 && sub != 0) b0 = b1 = b2 = inf;     // the merged list lives in the group's first lane
+        }
     }
-    out_all[size_t(b) * N + __float_as_int(me.w)] = (b0 + b1 + b2) / 3.0f;
+    if (kKnnLanes > 1 && max_ring == 0) merge3_group(b0, b1, b2, lane);
+    if (live && sub == 0) out_all[size_t(b) * N + __float_as_int(me.w)] = (b0 + b1 + b2) / 3.0f;
 }
 
 }  // namespace
@@ -328,7 +359,11 @@ int sgr_knn_mean_dist2_batched(const float* points, int32_t B, int32_t N, float*
     knn_scan_tops_kernel<<<B, kScanBlocks, 0, s>>>(h, block_sum, cell_start, N);
     knn_scan_add_kernel<<<dim3(296, B), 256, 0, s>>>(h, block_sum, cell_start);
     knn_fill_kernel<<<dim3(gb, B), 256, 0, s>>>(points, N, cell_of, cell_start, cell_fill, sorted);
-    knn_query_kernel<<<dim3((N + 127) / 128, B), 128, 0, s>>>(N, h, cell_start, sorted, out);
+    // one lane per point when the launch fills the machine anyway, eight when a single small set leaves it idle
+    if ((long long)B * N > 262144)
+        knn_query_kernel<1><<<dim3((N + 127) / 128, B), 128, 0, s>>>(N, h, cell_start, sorted, out);
+    else
+        knn_query_kernel<8><<<dim3((N * 8 + 127) / 128, B), 128, 0, s>>>(N, h, cell_start, sorted, out);
     if ((e = cudaGetLastError()) != cudaSuccess) return sgr_set_error_(SGR_E_CUDA, cudaGetErrorString(e));
     sgr_count_launches_(9);
     return SGR_OK;
